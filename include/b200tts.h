@@ -1,0 +1,154 @@
+/*
+ * b200tts -- C ABI of the B200-native Tacotron-2 training hot path (sm_100a only).
+ *
+ * The reference (Tomiinek/Multilingual_Text_to_Speech) has no FFI / plugin layer: its boundary for this
+ * path is the Python nn.Module surface.  This header is the boundary a native
+ * binding would use instead; every entry point names the reference code it replaces.  The Python
+ * host package (multilingual_text_to_speech_b200) binds it with ctypes and re-exposes the
+ * reference's module classes on top.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all tensors are dense row-major fp32 DEVICE pointers unless
+ *     marked [host]; integer ids / lengths are int32; dropout keep-masks are uint8 (1 = keep).
+ *   - the library never allocates: outputs and workspaces are caller-owned, sizes come from the
+ *     *_workspace_bytes() queries (256-byte aligned base pointers expected).
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     immediately; 0 = ok, negative = error, message via b200tts_last_error().
+ *   - there is NO CPU fallback: every entry point fails with B200TTS_ERR_CUDA when no sm_100 device
+ *     is present.
+ */
+#ifndef B200TTS_H_
+#define B200TTS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TTS_OK 0
+#define B200TTS_ERR_INVALID (-1)
+#define B200TTS_ERR_CUDA (-2)
+#define B200TTS_ERR_UNSUPPORTED (-3)
+#define B200TTS_ERR_WORKSPACE (-4)
+
+#define B200TTS_CELL_DROPOUT 0 /* DropoutLSTMCell  modules/layers.py:37-47 */
+#define B200TTS_CELL_ZONEOUT 1 /* ZoneoutLSTMCell  modules/layers.py:18-34 */
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* b200tts_last_error(void);
+int b200tts_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+unsigned long long b200tts_launch_count(void);
+
+/* ---- generic dense contraction (the time-batched GEMMs of the path) ----------------------- */
+/* C = alpha * op(A) . op(B) + beta * C + bias[n];  op(A)(m,k) = transA ? A[k*lda+m] : A[m*lda+k],
+ * op(B)(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n].  Replaces the torch.nn.Linear / cuBLAS call sites
+ * K8, K9, K15 of SURVEY.md section 2.3.  `workspace` (floats) is needed for splitk > 1.        */
+int b200tts_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                     const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int batch,
+                     long long strideA, long long strideB, long long strideC, int splitk, float* workspace,
+                     void* stream);
+
+/* ---- decoder: Decoder._decode, modules/tacotron2.py:148-209 -------------------------------- */
+typedef struct {
+    int B, L, T;            /* batch, padded text length, mel frames */
+    int M, D, P, A, C, K, N; /* memory dim, decoder dim, prenet dim, attention dim, location channels,
+                                location kernel size, mel channels */
+    int cell_kind;          /* B200TTS_CELL_* */
+    int training;           /* nn.Module.training of the cells (prenet dropout is always on) */
+    float rate_h, rate_c;   /* dropout_hidden | (zoneout_hidden, zoneout_cell) */
+    float prenet_rate;      /* hp.dropout used by the prenet */
+} b200tts_decoder_shape;
+
+/* Parameter block in the reference's own layouts ([out, in] Linear weights; names = state_dict keys). */
+typedef struct {
+    float* prenet_w0;   /* _prenet._layers.0.weight [P, N] */
+    float* prenet_b0;   /* [P] */
+    float* prenet_w1;   /* _prenet._layers.1.weight [P, P] */
+    float* prenet_b1;   /* [P] */
+    float* att_w_ih;    /* _decoder._attention_lstm.weight_ih [4D, P+M]  (gate order i,f,g,o) */
+    float* att_w_hh;    /* [4D, D] */
+    float* att_b_ih;    /* [4D] */
+    float* att_b_hh;    /* [4D] */
+    float* gen_w_ih;    /* _decoder._generator_lstm.weight_ih [4D, D+M] */
+    float* gen_w_hh;    /* [4D, D] */
+    float* gen_b_ih;    /* [4D] */
+    float* gen_b_hh;    /* [4D] */
+    float* attn_query;  /* _attention._query.weight [A, D] */
+    float* attn_memory; /* _attention._memory.weight [A, M] */
+    float* attn_location;     /* _attention._location.weight [A, C] */
+    float* attn_loc_features; /* _attention._loc_features.weight [C, 1, K] */
+    float* attn_bias;   /* _attention._bias [1, A] */
+    float* attn_energy; /* _attention._energy.weight [1, A] */
+    float* frame_w;     /* _decoder._frame_prediction.weight [N, D+M] */
+    float* frame_b;     /* [N] */
+    float* stop_w;      /* _decoder._stop_prediction.weight [1, D+M] */
+    float* stop_b;      /* [1] */
+} b200tts_decoder_params;
+
+typedef struct {
+    const float* memory;          /* [B, L, M] encoder output ++ speaker/language embeddings */
+    const int32_t* text_lengths;  /* [B] */
+    const float* target;          /* [B, N, T] ground-truth mel frames */
+    const uint8_t* teacher;       /* [host] [T] 1 = ground truth fed at step i (tacotron2.py:171,181); NULL = all 1 */
+    /* keep masks, NULL = no dropout at that site.  Time-major: row i belongs to decoder step i. */
+    const uint8_t* mask_prenet0;  /* [T, B, P] */
+    const uint8_t* mask_prenet1;  /* [T, B, P] */
+    const uint8_t* mask_att_h;    /* [T, B, D] */
+    const uint8_t* mask_att_c;    /* [T, B, D] zoneout only */
+    const uint8_t* mask_gen_h;    /* [T, B, D] */
+    const uint8_t* mask_gen_c;    /* [T, B, D] zoneout only */
+    const uint8_t* mask_step_prenet0; /* [T, B, P] prenet masks of free-running steps */
+    const uint8_t* mask_step_prenet1; /* [T, B, P] */
+} b200tts_decoder_inputs;
+
+typedef struct {
+    float* spectrogram; /* [B, T, N] */
+    float* stop;        /* [B, T]   logits */
+    float* alignments;  /* [B, T, L] */
+} b200tts_decoder_outputs;
+
+/* Bytes of the forward workspace; it also carries everything the backward pass re-reads. */
+size_t b200tts_decoder_workspace_bytes(const b200tts_decoder_shape* shape);
+size_t b200tts_decoder_bwd_workspace_bytes(const b200tts_decoder_shape* shape);
+
+int b200tts_decoder_forward(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
+                            const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+typedef struct {
+    const float* d_spectrogram; /* [B, T, N] or NULL */
+    const float* d_stop;        /* [B, T]    or NULL */
+    const float* d_alignments;  /* [B, T, L] or NULL */
+} b200tts_decoder_output_grads;
+
+/* Backward of the teacher-forced decode (autograd replay of tacotron2.py:148-209, train.py:83).
+ * `fwd_workspace` is the buffer the matching forward call filled and `fwd_out` its outputs (the
+ * alignments are re-read).  Parameter gradients are ACCUMULATED into `d_params` (+=, like autograd
+ * .grad); `d_memory` [B, L, M] is overwritten (may be NULL). */
+int b200tts_decoder_backward(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
+                             const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* fwd_out,
+                             const b200tts_decoder_output_grads* dout, const void* fwd_workspace, void* bwd_workspace,
+                             size_t bwd_workspace_bytes, const b200tts_decoder_params* d_params, float* d_memory,
+                             void* stream);
+
+/* ---- single attention step: LocationSensitiveAttention.forward, modules/attention.py:39-45,67-86 ---- */
+/* query [B, D]; memory [B, L, M]; memory_transform [B, L, A] (= AttentionBase.reset, attention.py:25);
+ * cum_weights [B, L] is read and updated in place; context [B, M], weights [B, L] written.
+ * workspace floats: b200tts_attention_step_workspace_elems(B, L, A).                           */
+size_t b200tts_attention_step_workspace_elems(int B, int L, int A);
+int b200tts_attention_step(int B, int L, int M, int D, int A, int C, int K, const float* query, const float* memory,
+                           const float* memory_transform, const int32_t* text_lengths, const float* w_query,
+                           const float* w_location, const float* w_loc_features, const float* bias,
+                           const float* w_energy, float* cum_weights, float* context, float* weights,
+                           float* workspace, void* stream);
+
+/* ---- dropout-mask generation (counter-based RNG; replaces the Philox draws inside F.dropout) ---- */
+int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TTS_H_ */

@@ -1,0 +1,102 @@
+"""ctypes binding of libb200tts.so (C ABI declared in include/b200tts.h).
+
+The library is the product: if it is missing or fails to load, every op raises -- there is no
+eager-PyTorch or CPU fallback (north_star: "no CPU fallback").
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_uint8, c_uint64, c_ulonglong, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libb200tts.so')
+
+CELL_DROPOUT, CELL_ZONEOUT = 0, 1
+
+
+class B200TTSError(RuntimeError):
+    pass
+
+
+class DecoderShape(Structure):
+    _fields_ = [(n, c_int) for n in ('B', 'L', 'T', 'M', 'D', 'P', 'A', 'C', 'K', 'N', 'cell_kind', 'training')] + \
+               [('rate_h', c_float), ('rate_c', c_float), ('prenet_rate', c_float)]
+
+
+DECODER_PARAM_FIELDS = ('prenet_w0', 'prenet_b0', 'prenet_w1', 'prenet_b1', 'att_w_ih', 'att_w_hh', 'att_b_ih', 'att_b_hh',
+                        'gen_w_ih', 'gen_w_hh', 'gen_b_ih', 'gen_b_hh', 'attn_query', 'attn_memory', 'attn_location',
+                        'attn_loc_features', 'attn_bias', 'attn_energy', 'frame_w', 'frame_b', 'stop_w', 'stop_b')
+
+
+class DecoderParams(Structure):
+    _fields_ = [(n, c_void_p) for n in DECODER_PARAM_FIELDS]
+
+
+class DecoderInputs(Structure):
+    _fields_ = [(n, c_void_p) for n in ('memory', 'text_lengths', 'target', 'teacher', 'mask_prenet0', 'mask_prenet1',
+                                        'mask_att_h', 'mask_att_c', 'mask_gen_h', 'mask_gen_c', 'mask_step_prenet0',
+                                        'mask_step_prenet1')]
+
+
+class DecoderOutputs(Structure):
+    _fields_ = [(n, c_void_p) for n in ('spectrogram', 'stop', 'alignments')]
+
+
+class DecoderOutputGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in ('d_spectrogram', 'd_stop', 'd_alignments')]
+
+
+# name -> (restype, argtypes); the "-m not gpu" suite checks every symbol of the header resolves
+SIGNATURES = {
+    'b200tts_last_error': (c_char_p, []),
+    'b200tts_version': (c_int, []),
+    'b200tts_launch_count': (c_ulonglong, []),
+    'b200tts_gemm_f32': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float,
+                                 c_void_p, c_int, c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_int, c_void_p,
+                                 c_void_p]),
+    'b200tts_decoder_workspace_bytes': (c_size_t, [POINTER(DecoderShape)]),
+    'b200tts_decoder_bwd_workspace_bytes': (c_size_t, [POINTER(DecoderShape)]),
+    'b200tts_decoder_forward': (c_int, [POINTER(DecoderShape), POINTER(DecoderParams), POINTER(DecoderInputs),
+                                        POINTER(DecoderOutputs), c_void_p, c_size_t, c_void_p]),
+    'b200tts_decoder_backward': (c_int, [POINTER(DecoderShape), POINTER(DecoderParams), POINTER(DecoderInputs),
+                                         POINTER(DecoderOutputs), POINTER(DecoderOutputGrads), c_void_p, c_void_p,
+                                         c_size_t, POINTER(DecoderParams), c_void_p, c_void_p]),
+    'b200tts_attention_step_workspace_elems': (c_size_t, [c_int, c_int, c_int]),
+    'b200tts_attention_step': (c_int, [c_int] * 7 + [c_void_p] * 13),
+    'b200tts_fill_keep_mask': (c_int, [c_void_p, c_size_t, c_float, c_uint64, c_uint64, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the shared library; raise B200TTSError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200TTSError(f'{LIB_PATH} is missing: run `python -m multilingual_text_to_speech_b200.build` '
+                           '(or __graft_entry__.build()); there is no fallback path')
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise B200TTSError(f'cannot load {LIB_PATH}: {exc}') from exc
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is absent
+        fn.restype, fn.argtypes = restype, argtypes
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().b200tts_last_error()
+        raise B200TTSError(f'{what} failed with status {status}: {msg.decode() if msg else ""}')
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(load().b200tts_launch_count())

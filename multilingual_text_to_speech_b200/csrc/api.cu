@@ -1,0 +1,156 @@
+// extern "C" surface of libb200tts (see include/b200tts.h) + error / launch bookkeeping.
+#include <stdarg.h>
+#include <atomic>
+#include "decoder_internal.cuh"
+
+namespace b200tts {
+
+static thread_local char g_error[1024] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) {
+        if (what[0] == 'c' && strncmp(what, "cudaGetLastError", 16) == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+        return B200TTS_OK;
+    }
+    set_last_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    return B200TTS_ERR_CUDA;
+}
+
+static int require_device() {
+    static int cached = 0;   // 0 unknown, 1 ok, -1 bad
+    if (cached == 1) return B200TTS_OK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+        set_last_error("no usable CUDA device (%s); b200tts has no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        return B200TTS_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        set_last_error("device %s is sm_%d%d; b200tts is built for sm_100a only", prop.name, prop.major, prop.minor);
+        return B200TTS_ERR_UNSUPPORTED;
+    }
+    cached = 1;
+    return B200TTS_OK;
+}
+
+int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                         const b200tts_decoder_outputs& out, float* ws, size_t ws_bytes, cudaStream_t st);
+int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                          const b200tts_decoder_outputs& fwd_out, const b200tts_decoder_output_grads& dout, const float* fws,
+                          float* bws, size_t bws_bytes, const b200tts_decoder_params& dw, float* d_memory, cudaStream_t st);
+size_t decoder_bwd_workspace_floats(const b200tts_decoder_shape& s);
+int attention_step_impl(int B, int L, int M, int D, int A, int C, int K, const float* query, const float* memory,
+                        const float* memT, const int* lengths, const float* Wq, const float* Wloc, const float* Wc,
+                        const float* bias, const float* v, float* cum, float* ctx, float* weights, float* workspace,
+                        cudaStream_t st);
+
+namespace {
+// counter-based generator: splitmix64 finaliser over (seed, stream, index/4); 16 bits per decision
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsigned threshold, unsigned long long key) {
+    const size_t groups = (n + 3) / 4;
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long r = mix64(key + g * 0x9E3779B97F4A7C15ull);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t i = g * 4 + j;
+            if (i < n) mask[i] = (((unsigned)(r >> (16 * j)) & 0xFFFFu) >= threshold) ? 1 : 0;
+        }
+    }
+}
+}  // namespace
+
+}  // namespace b200tts
+
+using namespace b200tts;
+
+extern "C" {
+
+const char* b200tts_last_error(void) { return g_error; }
+int b200tts_version(void) { return 100; }
+unsigned long long b200tts_launch_count(void) { return g_launches.load(); }
+
+int b200tts_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                     int ldb, float beta, float* C, int ldc, const float* bias, int batch, long long strideA,
+                     long long strideB, long long strideC, int splitk, float* workspace, void* stream) {
+    B200_TRY(require_device());
+    GemmDesc d;
+    d.A = A; d.B = B; d.C = C; d.bias = bias; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
+    d.transA = transA; d.transB = transB; d.alpha = alpha; d.beta = beta; d.batch = batch < 1 ? 1 : batch;
+    d.strideA = strideA; d.strideB = strideB; d.strideC = strideC; d.splitk = splitk < 1 ? 1 : splitk; d.partial = workspace;
+    return gemm_f32(d, (cudaStream_t)stream);
+}
+
+size_t b200tts_decoder_workspace_bytes(const b200tts_decoder_shape* shape) {
+    if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
+    return decoder_layout(*shape).total * sizeof(float);
+}
+
+size_t b200tts_decoder_bwd_workspace_bytes(const b200tts_decoder_shape* shape) {
+    if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
+    return decoder_bwd_workspace_floats(*shape) * sizeof(float);
+}
+
+int b200tts_decoder_forward(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
+                            const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    B200_REQUIRE(shape && params && in && out, "decoder_forward: null argument");
+    B200_TRY(require_device());
+    return decoder_forward_impl(*shape, *params, *in, *out, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200tts_decoder_backward(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
+                             const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* fwd_out,
+                             const b200tts_decoder_output_grads* dout, const void* fwd_workspace, void* bwd_workspace,
+                             size_t bwd_workspace_bytes, const b200tts_decoder_params* d_params, float* d_memory,
+                             void* stream) {
+    B200_REQUIRE(shape && params && in && fwd_out && dout && fwd_workspace && bwd_workspace && d_params,
+                 "decoder_backward: null argument");
+    B200_TRY(require_device());
+    return decoder_backward_impl(*shape, *params, *in, *fwd_out, *dout, (const float*)fwd_workspace, (float*)bwd_workspace,
+                                 bwd_workspace_bytes, *d_params, d_memory, (cudaStream_t)stream);
+}
+
+size_t b200tts_attention_step_workspace_elems(int B, int L, int A) { return (size_t)B * A + (size_t)B * L; }
+
+int b200tts_attention_step(int B, int L, int M, int D, int A, int C, int K, const float* query, const float* memory,
+                           const float* memory_transform, const int32_t* text_lengths, const float* w_query,
+                           const float* w_location, const float* w_loc_features, const float* bias, const float* w_energy,
+                           float* cum_weights, float* context, float* weights, float* workspace, void* stream) {
+    B200_TRY(require_device());
+    B200_REQUIRE(query && memory && memory_transform && text_lengths && cum_weights && context && weights && workspace,
+                 "attention_step: null argument");
+    return attention_step_impl(B, L, M, D, A, C, K, query, memory, memory_transform, text_lengths, w_query, w_location,
+                               w_loc_features, bias, w_energy, cum_weights, context, weights, workspace, (cudaStream_t)stream);
+}
+
+int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream) {
+    B200_TRY(require_device());
+    B200_REQUIRE(mask || n == 0, "fill_keep_mask: null mask");
+    B200_REQUIRE(drop_rate >= 0.f && drop_rate < 1.f, "fill_keep_mask: rate must be in [0,1)");
+    if (n == 0) return B200TTS_OK;
+    const unsigned threshold = (unsigned)(drop_rate * 65536.0f + 0.5f);
+    const unsigned long long key = mix64(seed ^ 0xD6E8FEB86659FD93ull) ^ (stream_id * 0xA24BAED4963EE407ull);
+    size_t groups = (n + 3) / 4;
+    int blocks = (int)((groups + 255) / 256 > 148 * 16 ? 148 * 16 : (groups + 255) / 256);
+    fill_keep_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, key);
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Shared device/host helpers for the b200tts hot-path library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200tts.h"
+
+namespace b200tts {
+
+void set_last_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what, const char* file, int line);
+
+#define B200_CUDA(call)                                                             \
+    do {                                                                            \
+        int _st = ::b200tts::check_cuda((call), #call, __FILE__, __LINE__);         \
+        if (_st != B200TTS_OK) return _st;                                          \
+    } while (0)
+
+#define B200_LAUNCH_CHECK() B200_CUDA(cudaGetLastError())
+
+#define B200_REQUIRE(cond, ...)                                                     \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            ::b200tts::set_last_error(__VA_ARGS__);                                 \
+            return B200TTS_ERR_INVALID;                                             \
+        }                                                                           \
+    } while (0)
+
+#define B200_TRY(expr)                                                              \
+    do {                                                                            \
+        int _st = (expr);                                                           \
+        if (_st != B200TTS_OK) return _st;                                          \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum / max; `scratch` must hold >= 33 floats; every thread gets the result.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nw ? scratch[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nw ? scratch[lane] : -INFINITY;
+        t = warp_max(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// GEMM (gemm_f32.cu):  C = alpha * op(A) . op(B) + beta * C + bias[n]
+//   op(A)(m,k) = transA ? A[k*lda+m] : A[m*lda+k];  op(B)(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n]
+//   batch > 1: pointers advance by stride{A,B,C}.  splitk > 1: raw partial sums are written to
+//   `partial` as [splitk][batch][M][N] (dense) and, unless `keep_partials`, reduced into C.
+// ---------------------------------------------------------------------------------------------
+struct GemmDesc {
+    const float* A = nullptr;
+    const float* B = nullptr;
+    float* C = nullptr;
+    const float* bias = nullptr;
+    int M = 0, N = 0, K = 0;
+    int lda = 0, ldb = 0, ldc = 0;
+    int transA = 0, transB = 0;
+    float alpha = 1.f, beta = 0.f;
+    int batch = 1;
+    long long strideA = 0, strideB = 0, strideC = 0;
+    int splitk = 1;
+    float* partial = nullptr;     // required when splitk > 1
+    int keep_partials = 0;        // 1: leave the reduction to the consumer kernel (C untouched)
+};
+
+int gemm_f32(const GemmDesc& d, cudaStream_t stream);
+size_t gemm_partial_elems(const GemmDesc& d);
+
+}  // namespace b200tts

@@ -1,0 +1,88 @@
+// Internal layout of the decoder workspace shared by the forward and backward orchestrators.
+#pragma once
+#include "common.cuh"
+#include "../../include/b200tts.h"
+
+namespace b200tts {
+
+constexpr int CELL_UNITS = 32;      // hidden units per CTA of the LSTM cell kernels
+constexpr int ATT_THREADS = 256;    // attention step kernels: 8 warps
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static inline int pick_splitk(int M, int N, int K) {
+    const int tiles = cdiv(M, 64) * cdiv(N, 64);
+    int s = (148 + tiles / 2) / (tiles > 0 ? tiles : 1);
+    if (s < 1) s = 1;
+    if (s > 8) s = 8;
+    const int kmax = cdiv(K, 16);
+    if (s > kmax) s = kmax > 0 ? kmax : 1;
+    return s;
+}
+
+// All offsets are in floats from the workspace base.
+struct DecoderLayout {
+    // saved for backward
+    size_t xtm;      // [T, B, N]      prenet input, time-major, row i = frame fed at step i
+    size_t p0, p1;   // [T, B, P]      prenet activations after relu+dropout
+    size_t ga, gg;   // [T, B, 4D]     attention / generator LSTM gates (post activation i,f,g,o)
+    size_t ai;       // [T+1, B, M+D]  row i = [ctx_{i-1} | h_att_{i-1}]  (row 0 = 0)
+    size_t ca;       // [T+1, B, D]    attention LSTM cell state (row 0 = 0)
+    size_t hg, cg;   // [T+1, B, D]    generator LSTM states
+    size_t q;        // [T, B, A]      attention queries
+    size_t cum;      // [T+1, B, L]    cumulative attention weights BEFORE step i
+    size_t memT;     // [B, L, A]      memory . Wm^T
+    size_t fs;       // [T, B, N+1]    frame | stop logits, time-major
+    // derived parameters
+    size_t wcat_att; // [4D, M+D] = [W_ih_att[:, P:] | W_hh_att]
+    size_t bsum_att, bsum_gen;  // [4D]
+    size_t wfs;      // [N+1, D+M] = [frame_w ; stop_w]
+    size_t bfs;      // [N+1]
+    // scratch
+    size_t qpart;    // [ncell_blocks, B, A]
+    size_t part;     // split-K partials
+    size_t total;
+    int split_att, split_gen, ncell_blocks;
+};
+
+static inline DecoderLayout decoder_layout(const b200tts_decoder_shape& s) {
+    DecoderLayout l;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
+    const size_t T = s.T, B = s.B, D = s.D, M = s.M, P = s.P, A = s.A, N = s.N, L = s.L;
+    l.xtm = take(T * B * N);
+    l.p0 = take(T * B * P);
+    l.p1 = take(T * B * P);
+    l.ga = take(T * B * 4 * D);
+    l.gg = take(T * B * 4 * D);
+    l.ai = take((T + 1) * B * (M + D));
+    l.ca = take((T + 1) * B * D);
+    l.hg = take((T + 1) * B * D);
+    l.cg = take((T + 1) * B * D);
+    l.q = take(T * B * A);
+    l.cum = take((T + 1) * B * L);
+    l.memT = take(B * L * A);
+    l.fs = take(T * B * (N + 1));
+    l.wcat_att = take(4 * D * (M + D));
+    l.bsum_att = take(4 * D);
+    l.bsum_gen = take(4 * D);
+    l.wfs = take((N + 1) * (D + M));
+    l.bfs = take(N + 1);
+    l.ncell_blocks = cdiv(s.D, CELL_UNITS);
+    l.qpart = take((size_t)l.ncell_blocks * B * A);
+    l.split_att = pick_splitk(s.B, 4 * s.D, s.M + s.D);
+    l.split_gen = pick_splitk(s.B, 4 * s.D, s.D);
+    const int smax = l.split_att > l.split_gen ? l.split_att : l.split_gen;
+    l.part = take((size_t)smax * B * 4 * D);
+    l.total = off;
+    return l;
+}
+
+int validate_decoder_shape(const b200tts_decoder_shape& s);
+
+// ---- kernels shared between forward and backward translation units ----
+int launch_copy2d(float* dst, int ldd, const float* src, int lds, int rows, int cols, cudaStream_t st);
+int launch_add_vec(float* dst, const float* a, const float* b, int n, cudaStream_t st);
+int launch_fill(float* dst, float value, size_t n, cudaStream_t st);
+
+}  // namespace b200tts

@@ -1,0 +1,187 @@
+"""Host-side op layer: torch.autograd.Functions and thin wrappers that call the C ABI (libb200tts.so).
+
+PyTorch is plumbing here (device memory, streams, autograd glue between the fused ops); all arithmetic
+of the hot path happens inside the library.
+"""
+import ctypes
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DecoderShape, DecoderParams, DecoderInputs, DecoderOutputs, DecoderOutputGrads,
+                   DECODER_PARAM_FIELDS, check, ptr)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.B200TTSError('b200tts ops need CUDA tensors (there is no CPU fallback)')
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# generic GEMM
+# ------------------------------------------------------------------------------------------------
+def gemm(a, b, trans_a=False, trans_b=False, bias=None, out=None, beta=0.0, alpha=1.0, splitk=1):
+    """out = alpha * op(a) @ op(b) + beta * out + bias  on 2-D fp32 CUDA tensors (row-major, any row stride)."""
+    _require_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    K2, N = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    assert K == K2, (a.shape, b.shape, trans_a, trans_b)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    ws = torch.empty(splitk * M * N, device=a.device, dtype=torch.float32) if splitk > 1 else None
+    lib = _lib.load()
+    check(lib.b200tts_gemm_f32(int(trans_a), int(trans_b), M, N, K, float(alpha), ptr(a), a.stride(0), ptr(b), b.stride(0),
+                               float(beta), ptr(out), out.stride(0), ptr(bias), 1, 0, 0, 0, splitk, ptr(ws), _stream()),
+          'b200tts_gemm_f32')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# dropout keep-masks
+# ------------------------------------------------------------------------------------------------
+def fill_keep_mask(shape, rate, seed, stream_id, device):
+    """uint8 keep mask (1 = keep) with P(keep) = 1 - rate from the library's counter-based generator."""
+    mask = torch.empty(shape, dtype=torch.uint8, device=device)
+    check(_lib.load().b200tts_fill_keep_mask(ptr(mask), mask.numel(), float(rate), int(seed) & (2 ** 64 - 1), int(stream_id),
+                                            _stream()), 'b200tts_fill_keep_mask')
+    return mask
+
+
+# ------------------------------------------------------------------------------------------------
+# single attention step (module-level API of LocationSensitiveAttention)
+# ------------------------------------------------------------------------------------------------
+def attention_step(query, memory, memory_transform, text_lengths, w_query, w_location, w_loc_features, bias, w_energy,
+                   cum_weights):
+    """One LocationSensitiveAttention.forward (reference modules/attention.py:39-45, 67-86).
+
+    Updates `cum_weights` in place; returns (context [B, M], weights [B, L]).
+    """
+    _require_cuda(query, memory, memory_transform, cum_weights)
+    B, L, M = memory.shape
+    D = query.shape[1]
+    A = w_query.shape[0]
+    C, _, K = w_loc_features.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.b200tts_attention_step_workspace_elems(B, L, A), device=query.device, dtype=torch.float32)
+    ctx = torch.empty(B, M, device=query.device, dtype=torch.float32)
+    weights = torch.empty(B, L, device=query.device, dtype=torch.float32)
+    args = [_f32c(query), _f32c(memory), _f32c(memory_transform), text_lengths.to(torch.int32).contiguous(),
+            _f32c(w_query), _f32c(w_location), _f32c(w_loc_features), _f32c(bias), _f32c(w_energy)]
+    assert cum_weights.is_contiguous() and cum_weights.dtype == torch.float32
+    check(lib.b200tts_attention_step(B, L, M, D, A, C, K, *[ptr(t) for t in args], ptr(cum_weights), ptr(ctx),
+                                     ptr(weights), ptr(ws), _stream()), 'b200tts_attention_step')
+    return ctx, weights
+
+
+# ------------------------------------------------------------------------------------------------
+# fused decoder
+# ------------------------------------------------------------------------------------------------
+class DecoderConfig:
+    """Non-tensor arguments of one decode: shapes, regulariser settings, dropout masks, teacher-forcing coins."""
+
+    MASK_NAMES = ('prenet0', 'prenet1', 'att_h', 'att_c', 'gen_h', 'gen_c', 'step_prenet0', 'step_prenet1')
+
+    def __init__(self, cell_kind, training, rate_h, rate_c, prenet_rate, masks=None, teacher=None):
+        self.cell_kind = int(cell_kind)
+        self.training = bool(training)
+        self.rate_h, self.rate_c, self.prenet_rate = float(rate_h), float(rate_c), float(prenet_rate)
+        self.masks = dict(masks or {})       # name -> uint8 CUDA tensor, time-major ([T, B, P] / [T, B, D])
+        self.teacher = teacher               # None (all teacher forced) or host bool/uint8 array [T]
+
+
+def _decoder_structs(cfg, shape_dims, params, memory, text_lengths, target):
+    B, L, T, M, D, P, A, C, K, N = shape_dims
+    shape = DecoderShape(B, L, T, M, D, P, A, C, K, N, cfg.cell_kind, int(cfg.training), cfg.rate_h, cfg.rate_c,
+                         cfg.prenet_rate)
+    pstruct = DecoderParams(*[ptr(p) for p in params])
+    teacher_np = None
+    if cfg.teacher is not None:
+        teacher_np = np.ascontiguousarray(np.asarray(cfg.teacher).astype(np.uint8))
+        assert teacher_np.shape == (T,)
+    expect = {'prenet0': (T, B, P), 'prenet1': (T, B, P), 'step_prenet0': (T, B, P), 'step_prenet1': (T, B, P),
+              'att_h': (T, B, D), 'att_c': (T, B, D), 'gen_h': (T, B, D), 'gen_c': (T, B, D)}
+    mp = {}
+    for name in DecoderConfig.MASK_NAMES:
+        m = cfg.masks.get(name)
+        if m is not None:
+            assert m.dtype == torch.uint8 and m.is_cuda and m.is_contiguous() and tuple(m.shape) == expect[name], \
+                (name, m.dtype, tuple(m.shape), expect[name])
+        mp[name] = ptr(m)
+    inputs = DecoderInputs(ptr(memory), ptr(text_lengths), ptr(target),
+                           ctypes.c_void_p(teacher_np.ctypes.data) if teacher_np is not None else None,
+                           mp['prenet0'], mp['prenet1'], mp['att_h'], mp['att_c'], mp['gen_h'], mp['gen_c'],
+                           mp['step_prenet0'], mp['step_prenet1'])
+    return shape, pstruct, inputs, teacher_np
+
+
+class DecoderFunction(torch.autograd.Function):
+    """Decoder._decode (reference modules/tacotron2.py:148-209) as one fused op with a hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, cfg, memory, target, text_lengths, *params):
+        assert len(params) == len(DECODER_PARAM_FIELDS)
+        _require_cuda(memory, target, text_lengths, *params)
+        memory, target = _f32c(memory), _f32c(target)
+        params = [_f32c(p) for p in params]
+        text_lengths = text_lengths.to(torch.int32).contiguous()
+        byname = dict(zip(DECODER_PARAM_FIELDS, params))
+        B, L, M = memory.shape
+        N, T = target.shape[1], target.shape[2]
+        D = byname['att_w_hh'].shape[1]
+        P = byname['prenet_w1'].shape[0]
+        A = byname['attn_query'].shape[0]
+        C, K = byname['attn_loc_features'].shape[0], byname['attn_loc_features'].shape[-1]
+        assert byname['att_w_ih'].shape == (4 * D, P + M) and byname['gen_w_ih'].shape == (4 * D, D + M)
+        dims = (B, L, T, M, D, P, A, C, K, N)
+        shape, pstruct, inputs, teacher_np = _decoder_structs(cfg, dims, params, memory, text_lengths, target)
+        lib = _lib.load()
+        nbytes = lib.b200tts_decoder_workspace_bytes(ctypes.byref(shape))
+        if nbytes == 0:
+            raise _lib.B200TTSError('decoder shape rejected: ' + lib.b200tts_last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=memory.device)
+        spec = torch.empty(B, T, N, device=memory.device, dtype=torch.float32)
+        stop = torch.empty(B, T, device=memory.device, dtype=torch.float32)
+        align = torch.empty(B, T, L, device=memory.device, dtype=torch.float32)
+        outs = DecoderOutputs(ptr(spec), ptr(stop), ptr(align))
+        check(lib.b200tts_decoder_forward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
+                                          ctypes.byref(outs), ptr(ws), nbytes, _stream()), 'b200tts_decoder_forward')
+        ctx.cfg, ctx.dims, ctx.ws = cfg, dims, ws
+        ctx.save_for_backward(memory, target, text_lengths, align, *params)
+        ctx.set_materialize_grads(False)
+        return spec, stop, align
+
+    @staticmethod
+    def backward(ctx, d_spec, d_stop, d_align):
+        memory, target, text_lengths, align, *params = ctx.saved_tensors
+        cfg, dims = ctx.cfg, ctx.dims
+        shape, pstruct, inputs, teacher_np = _decoder_structs(cfg, dims, params, memory, text_lengths, target)
+        lib = _lib.load()
+        nbytes = lib.b200tts_decoder_bwd_workspace_bytes(ctypes.byref(shape))
+        bws = torch.empty(nbytes, dtype=torch.uint8, device=memory.device)
+        grads = [torch.zeros_like(p) for p in params]
+        gstruct = DecoderParams(*[ptr(g) for g in grads])
+        d_memory = torch.empty_like(memory) if ctx.needs_input_grad[1] else None
+        d_spec, d_stop, d_align = [None if t is None else _f32c(t) for t in (d_spec, d_stop, d_align)]
+        douts = DecoderOutputGrads(ptr(d_spec), ptr(d_stop), ptr(d_align))
+        fouts = DecoderOutputs(None, None, ptr(align))
+        check(lib.b200tts_decoder_backward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
+                                           ctypes.byref(fouts), ctypes.byref(douts), ptr(ctx.ws), ptr(bws), nbytes,
+                                           ctypes.byref(gstruct), ptr(d_memory), _stream()), 'b200tts_decoder_backward')
+        return (None, d_memory, None, None, *grads)
+
+
+def decoder_forward(cfg, memory, target, text_lengths, params):
+    """params: list of the 22 decoder parameter tensors in DECODER_PARAM_FIELDS order."""
+    return DecoderFunction.apply(cfg, memory, target, text_lengths, *params)

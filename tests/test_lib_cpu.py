@@ -1,0 +1,50 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/b200tts.h declares, sizes
+workspaces, and FAILS LOUDLY when asked to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from multilingual_text_to_speech_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    entry.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    header = open(os.path.join(ROOT, 'include', 'b200tts.h')).read()
+    declared = set(re.findall(r'\b(b200tts_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in include/b200tts.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_workspace_queries_are_host_only(lib):
+    shape = _lib.DecoderShape(64, 180, 900, 288, 1024, 256, 128, 32, 31, 80, 0, 1, 0.1, 0.0, 0.5)
+    fwd = lib.b200tts_decoder_workspace_bytes(ctypes.byref(shape))
+    bwd = lib.b200tts_decoder_bwd_workspace_bytes(ctypes.byref(shape))
+    assert 2e9 < fwd < 6e9 and 2e9 < bwd < 6e9, (fwd, bwd)
+    bad = _lib.DecoderShape(64, 180, 900, 288, 1024, 256, 129, 32, 31, 80, 0, 1, 0.1, 0.0, 0.5)
+    assert lib.b200tts_decoder_workspace_bytes(ctypes.byref(bad)) == 0
+    assert b'attention dimension' in lib.b200tts_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_compute_without_gpu_fails_loudly(lib):
+    a = torch.zeros(4, 4)
+    st = lib.b200tts_gemm_f32(0, 0, 4, 4, 4, 1.0, _lib.ptr(a), 4, _lib.ptr(a), 4, 0.0, _lib.ptr(a), 4, None, 1, 0, 0, 0, 1,
+                              None, None)
+    assert st != 0
+    assert b'no CPU fallback' in lib.b200tts_last_error() or b'CUDA' in lib.b200tts_last_error()
+    from multilingual_text_to_speech_b200 import functional as F
+    with pytest.raises(_lib.B200TTSError):
+        F.gemm(a, a)
