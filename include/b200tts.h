@@ -145,6 +145,69 @@ int b200tts_attention_step(int B, int L, int M, int D, int A, int C, int K, cons
                            const float* w_energy, float* cum_weights, float* context, float* weights,
                            float* workspace, void* stream);
 
+
+/* ---- convolution block: ConvBlock / HighwayConvBlock / ConvBlockGenerated / HighwayConvBlockGenerated ----
+ * modules/layers.py:50-178.  x [NB, G*Cin, L] -> pad((k-1)*dil/2) -> grouped Conv1d(no bias) -> BatchNorm1d
+ * (batch statistics over (NB, L) incl. padded positions when training) -> activation -> Dropout ->
+ * optional highway gate  out = h2 * sigmoid(h1) + x * (1 - sigmoid(h1)).
+ * weight [G*Cout, Cin, k] is either an nn.Conv1d weight or the output of b200tts_generator_forward.
+ * gamma / beta: element (g, o) at ptr[g*affine_gstride + o] (plain BN: stride Cout; generated BN:
+ * ptr = affine, affine + Cout with stride 2*Cout, modules/generated.py:83-84).                       */
+typedef struct {
+    int NB, G, Cin, Cout, L; /* Cout = per-group conv output channels (2*Cin for highway blocks) */
+    int k, dilation;
+    int activation;          /* 0 identity, 1 relu, 2 tanh */
+    int highway;
+    int training;
+    float eps, momentum, dropout;
+} b200tts_convblock_shape;
+
+size_t b200tts_convblock_saved_bytes(const b200tts_convblock_shape* shape);
+size_t b200tts_convblock_workspace_bytes(const b200tts_convblock_shape* shape);
+/* running_mean / running_var [G*Cout] are updated in place when training (may be NULL then). keep: uint8
+ * [NB, G*Cout, L] or NULL.  out [NB, G*Cf, L] with Cf = highway ? Cout/2 : Cout.                     */
+int b200tts_convblock_forward(const b200tts_convblock_shape* shape, const float* x, const float* weight,
+                              const float* gamma, const float* beta, int affine_gstride, float* running_mean,
+                              float* running_var, const uint8_t* keep, float* out, void* saved, void* workspace,
+                              void* stream);
+/* dx overwritten; dweight / dgamma / dbeta accumulated (+=).                                         */
+int b200tts_convblock_backward(const b200tts_convblock_shape* shape, const float* x, const float* weight,
+                               const float* gamma, const float* beta, int affine_gstride, const uint8_t* keep,
+                               const void* saved, const float* dout, float* dx, float* dweight, float* dgamma,
+                               float* dbeta, void* workspace, void* stream);
+
+/* ---- parameter generator: Conv1dGenerated / BatchNorm1dGenerated weight synthesis, modules/generated.py:38-39,81-82 ----
+ * out[g, :] = (e[g] . Wb^T + bb) . Wk^T + bk;   e [G, gd], Wb [bn, gd], Wk [R, bn]; eb [G, bn] is saved. */
+size_t b200tts_generator_workspace_bytes(int G, int bn);
+int b200tts_generator_forward(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* bb,
+                              const float* Wk, const float* bk, float* eb, float* out, void* stream);
+/* all gradients accumulated (+=). */
+int b200tts_generator_backward(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* Wk,
+                               const float* eb, const float* dout, float* de, float* dWb, float* dbb, float* dWk,
+                               float* dbk, void* workspace, void* stream);
+
+/* ---- embeddings: nn.Embedding gather (tacotron2.py:237-239,363; :121-124,143-146) ---- */
+/* out[t, 0:E] = table[ids[t], :] for ntok tokens, output row stride ldo (lets the caller write a column block). */
+int b200tts_embedding_forward(float* out, int ldo, const float* table, const int32_t* ids, long long ntok, int E, void* stream);
+/* dtable[v, :] += sum_{t: ids[t]==v} dout[t, 0:E]; rows equal to padding_idx (or -1 for none) are skipped. */
+int b200tts_embedding_backward(float* dtable, int V, const float* dout, int ldo, const int32_t* ids, long long ntok, int E,
+                               int padding_idx, void* stream);
+
+/* ---- packed bidirectional LSTM of the vanilla encoder: modules/encoder.py:33,41-44 ---- */
+typedef struct { int B, L, E, H; } b200tts_bilstm_shape;
+typedef struct {
+    float *w_ih, *w_hh, *b_ih, *b_hh;                                 /* _lstm.weight_ih_l0 [4H, E] ... */
+    float *w_ih_reverse, *w_hh_reverse, *b_ih_reverse, *b_hh_reverse; /* _lstm.*_l0_reverse */
+} b200tts_bilstm_params;
+size_t b200tts_bilstm_saved_bytes(const b200tts_bilstm_shape* shape);
+size_t b200tts_bilstm_workspace_bytes(const b200tts_bilstm_shape* shape);
+/* x [B, L, E], lengths [B] -> out [B, L, 2H] (zeros at positions >= length). */
+int b200tts_bilstm_forward(const b200tts_bilstm_shape* shape, const b200tts_bilstm_params* params, const float* x,
+                           const int32_t* lengths, float* out, void* saved, void* workspace, void* stream);
+int b200tts_bilstm_backward(const b200tts_bilstm_shape* shape, const b200tts_bilstm_params* params,
+                            const int32_t* lengths, const void* saved, const float* dout, float* dx,
+                            const b200tts_bilstm_params* d_params, void* workspace, void* stream);
+
 /* ---- dropout-mask generation (counter-based RNG; replaces the Philox draws inside F.dropout) ---- */
 int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream);
 

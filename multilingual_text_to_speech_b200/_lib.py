@@ -45,6 +45,22 @@ class DecoderOutputGrads(Structure):
     _fields_ = [(n, c_void_p) for n in ('d_spectrogram', 'd_stop', 'd_alignments')]
 
 
+class ConvBlockShape(Structure):
+    _fields_ = [(n, c_int) for n in ('NB', 'G', 'Cin', 'Cout', 'L', 'k', 'dilation', 'activation', 'highway', 'training')] + \
+               [('eps', c_float), ('momentum', c_float), ('dropout', c_float)]
+
+
+class BiLSTMShape(Structure):
+    _fields_ = [(n, c_int) for n in ('B', 'L', 'E', 'H')]
+
+
+BILSTM_PARAM_FIELDS = ('w_ih', 'w_hh', 'b_ih', 'b_hh', 'w_ih_reverse', 'w_hh_reverse', 'b_ih_reverse', 'b_hh_reverse')
+
+
+class BiLSTMParams(Structure):
+    _fields_ = [(n, c_void_p) for n in BILSTM_PARAM_FIELDS]
+
+
 # name -> (restype, argtypes); the "-m not gpu" suite checks every symbol of the header resolves
 SIGNATURES = {
     'b200tts_last_error': (c_char_p, []),
@@ -62,6 +78,23 @@ SIGNATURES = {
                                          c_size_t, POINTER(DecoderParams), c_void_p, c_void_p]),
     'b200tts_attention_step_workspace_elems': (c_size_t, [c_int, c_int, c_int]),
     'b200tts_attention_step': (c_int, [c_int] * 7 + [c_void_p] * 13),
+    'b200tts_convblock_saved_bytes': (c_size_t, [POINTER(ConvBlockShape)]),
+    'b200tts_convblock_workspace_bytes': (c_size_t, [POINTER(ConvBlockShape)]),
+    'b200tts_convblock_forward': (c_int, [POINTER(ConvBlockShape), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'b200tts_convblock_backward': (c_int, [POINTER(ConvBlockShape), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'b200tts_generator_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'b200tts_generator_forward': (c_int, [c_int, c_int, c_int, c_longlong] + [c_void_p] * 8),
+    'b200tts_generator_backward': (c_int, [c_int, c_int, c_int, c_longlong] + [c_void_p] * 12),
+    'b200tts_embedding_forward': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    'b200tts_embedding_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    'b200tts_bilstm_saved_bytes': (c_size_t, [POINTER(BiLSTMShape)]),
+    'b200tts_bilstm_workspace_bytes': (c_size_t, [POINTER(BiLSTMShape)]),
+    'b200tts_bilstm_forward': (c_int, [POINTER(BiLSTMShape), POINTER(BiLSTMParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p]),
+    'b200tts_bilstm_backward': (c_int, [POINTER(BiLSTMShape), POINTER(BiLSTMParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                        POINTER(BiLSTMParams), c_void_p, c_void_p]),
     'b200tts_fill_keep_mask': (c_int, [c_void_p, c_size_t, c_float, c_uint64, c_uint64, c_void_p]),
 }
 

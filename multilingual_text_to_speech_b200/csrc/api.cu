@@ -55,6 +55,30 @@ int attention_step_impl(int B, int L, int M, int D, int A, int C, int K, const f
                         const float* bias, const float* v, float* cum, float* ctx, float* weights, float* workspace,
                         cudaStream_t st);
 
+
+size_t convblock_saved_floats(const b200tts_convblock_shape& s);
+size_t convblock_workspace_floats(const b200tts_convblock_shape& s);
+int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, const float* weight, const float* gamma,
+                           const float* beta, int affine_gstride, float* running_mean, float* running_var, const uint8_t* keep,
+                           float* out, float* saved, float* ws, cudaStream_t st);
+int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, const float* weight, const float* gamma,
+                            const float* beta, int affine_gstride, const uint8_t* keep, const float* saved, const float* dout,
+                            float* dx, float* dweight, float* dgamma, float* dbeta, float* ws, cudaStream_t st);
+size_t generator_workspace_floats(int G, int bn);
+int generator_forward_impl(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* bb, const float* Wk,
+                           const float* bk, float* eb, float* out, cudaStream_t st);
+int generator_backward_impl(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* Wk, const float* eb,
+                            const float* dout, float* de, float* dWb, float* dbb, float* dWk, float* dbk, float* ws, cudaStream_t st);
+int embedding_forward_impl(float* out, int ldo, const float* table, const int* ids, long long ntok, int E, cudaStream_t st);
+int embedding_backward_impl(float* dtable, int V, const float* dout, int ldo, const int* ids, long long ntok, int E, int padding_idx,
+                            cudaStream_t st);
+size_t bilstm_saved_floats(const b200tts_bilstm_shape& s);
+size_t bilstm_workspace_floats(const b200tts_bilstm_shape& s);
+int bilstm_forward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_params& w, const float* x, const int* lengths, float* out,
+                        float* saved, float* ws, cudaStream_t st);
+int bilstm_backward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_params& w, const int* lengths, const float* saved,
+                         const float* dout, float* dx, const b200tts_bilstm_params& dw, float* ws, cudaStream_t st);
+
 namespace {
 // counter-based generator: splitmix64 finaliser over (seed, stream, index/4); 16 bits per decision
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
@@ -137,6 +161,76 @@ int b200tts_attention_step(int B, int L, int M, int D, int A, int C, int K, cons
                  "attention_step: null argument");
     return attention_step_impl(B, L, M, D, A, C, K, query, memory, memory_transform, text_lengths, w_query, w_location,
                                w_loc_features, bias, w_energy, cum_weights, context, weights, workspace, (cudaStream_t)stream);
+}
+
+size_t b200tts_convblock_saved_bytes(const b200tts_convblock_shape* s) { return s ? convblock_saved_floats(*s) * sizeof(float) : 0; }
+size_t b200tts_convblock_workspace_bytes(const b200tts_convblock_shape* s) { return s ? convblock_workspace_floats(*s) * sizeof(float) : 0; }
+
+int b200tts_convblock_forward(const b200tts_convblock_shape* shape, const float* x, const float* weight, const float* gamma,
+                              const float* beta, int affine_gstride, float* running_mean, float* running_var, const uint8_t* keep,
+                              float* out, void* saved, void* workspace, void* stream) {
+    B200_REQUIRE(shape && x && weight && gamma && beta && out && saved && workspace, "convblock_forward: null argument");
+    B200_TRY(require_device());
+    return convblock_forward_impl(*shape, x, weight, gamma, beta, affine_gstride, running_mean, running_var, keep, out, (float*)saved,
+                                  (float*)workspace, (cudaStream_t)stream);
+}
+
+int b200tts_convblock_backward(const b200tts_convblock_shape* shape, const float* x, const float* weight, const float* gamma,
+                               const float* beta, int affine_gstride, const uint8_t* keep, const void* saved, const float* dout,
+                               float* dx, float* dweight, float* dgamma, float* dbeta, void* workspace, void* stream) {
+    B200_REQUIRE(shape && x && weight && gamma && beta && saved && dout && workspace, "convblock_backward: null argument");
+    B200_REQUIRE(dx || !shape->highway, "convblock_backward: highway blocks need dx");
+    B200_TRY(require_device());
+    return convblock_backward_impl(*shape, x, weight, gamma, beta, affine_gstride, keep, (const float*)saved, dout, dx, dweight, dgamma,
+                                   dbeta, (float*)workspace, (cudaStream_t)stream);
+}
+
+size_t b200tts_generator_workspace_bytes(int G, int bn) { return generator_workspace_floats(G, bn) * sizeof(float); }
+
+int b200tts_generator_forward(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* bb, const float* Wk,
+                              const float* bk, float* eb, float* out, void* stream) {
+    B200_REQUIRE(e && Wb && bb && Wk && bk && eb && out, "generator_forward: null argument");
+    B200_TRY(require_device());
+    return generator_forward_impl(G, gd, bn, R, e, Wb, bb, Wk, bk, eb, out, (cudaStream_t)stream);
+}
+
+int b200tts_generator_backward(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* Wk, const float* eb,
+                               const float* dout, float* de, float* dWb, float* dbb, float* dWk, float* dbk, void* workspace,
+                               void* stream) {
+    B200_REQUIRE(e && Wb && Wk && eb && dout && de && dWb && dbb && dWk && dbk && workspace, "generator_backward: null argument");
+    B200_TRY(require_device());
+    return generator_backward_impl(G, gd, bn, R, e, Wb, Wk, eb, dout, de, dWb, dbb, dWk, dbk, (float*)workspace, (cudaStream_t)stream);
+}
+
+int b200tts_embedding_forward(float* out, int ldo, const float* table, const int32_t* ids, long long ntok, int E, void* stream) {
+    B200_REQUIRE(out && table && ids && ntok >= 0 && E > 0 && ldo >= E, "embedding_forward: bad argument");
+    B200_TRY(require_device());
+    return embedding_forward_impl(out, ldo, table, ids, ntok, E, (cudaStream_t)stream);
+}
+
+int b200tts_embedding_backward(float* dtable, int V, const float* dout, int ldo, const int32_t* ids, long long ntok, int E,
+                               int padding_idx, void* stream) {
+    B200_REQUIRE(dtable && dout && ids && V > 0 && E > 0 && ldo >= E, "embedding_backward: bad argument");
+    B200_TRY(require_device());
+    return embedding_backward_impl(dtable, V, dout, ldo, ids, ntok, E, padding_idx, (cudaStream_t)stream);
+}
+
+size_t b200tts_bilstm_saved_bytes(const b200tts_bilstm_shape* s) { return s ? bilstm_saved_floats(*s) * sizeof(float) : 0; }
+size_t b200tts_bilstm_workspace_bytes(const b200tts_bilstm_shape* s) { return s ? bilstm_workspace_floats(*s) * sizeof(float) : 0; }
+
+int b200tts_bilstm_forward(const b200tts_bilstm_shape* shape, const b200tts_bilstm_params* params, const float* x,
+                           const int32_t* lengths, float* out, void* saved, void* workspace, void* stream) {
+    B200_REQUIRE(shape && params && x && lengths && out && saved && workspace, "bilstm_forward: null argument");
+    B200_TRY(require_device());
+    return bilstm_forward_impl(*shape, *params, x, lengths, out, (float*)saved, (float*)workspace, (cudaStream_t)stream);
+}
+
+int b200tts_bilstm_backward(const b200tts_bilstm_shape* shape, const b200tts_bilstm_params* params, const int32_t* lengths,
+                            const void* saved, const float* dout, float* dx, const b200tts_bilstm_params* d_params, void* workspace,
+                            void* stream) {
+    B200_REQUIRE(shape && params && lengths && saved && dout && d_params && workspace, "bilstm_backward: null argument");
+    B200_TRY(require_device());
+    return bilstm_backward_impl(*shape, *params, lengths, (const float*)saved, dout, dx, *d_params, (float*)workspace, (cudaStream_t)stream);
 }
 
 int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream) {

@@ -35,6 +35,7 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -99,6 +100,7 @@ struct GemmDesc {
     float alpha = 1.f, beta = 0.f;
     int batch = 1;
     long long strideA = 0, strideB = 0, strideC = 0;
+    int a_batch_mod = 0;          // > 0: A advances by strideA * (batch_index % a_batch_mod)
     int splitk = 1;
     float* partial = nullptr;     // required when splitk > 1
     int keep_partials = 0;        // 1: leave the reduction to the consumer kernel (C untouched)
@@ -106,5 +108,6 @@ struct GemmDesc {
 
 int gemm_f32(const GemmDesc& d, cudaStream_t stream);
 size_t gemm_partial_elems(const GemmDesc& d);
+int gemm_f32_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream);
 
 }  // namespace b200tts

@@ -76,19 +76,6 @@ __global__ void relu_dropout_bwd_kernel(float* __restrict__ dz, const float* __r
 // ---------------------------------------------------------------------------------------------
 // LSTM cell backward (pointwise) -- one thread owns 8 utterances of one hidden unit
 // ---------------------------------------------------------------------------------------------
-struct CellBwdArgs {
-    const float* gates;                       // [B, 4D] activated i,f,g,o
-    const float* c_prev;                      // [B, D]
-    const float* dh_static; int ld_dhs;       // [B, ld] or null
-    const float* part; int nsplit; size_t part_stride; int ld_part; int part_col0;   // recurrent dh partials (null on the last step)
-    const float* dq; const float* Wq; int A;  // optional: dh += dq[b, :] . Wq[:, u]
-    float* dc_state;                          // [B, D] in: d c_out of this step; out: d c_out of the previous step
-    float* dhz_state;                         // [B, D] zoneout: direct d h_prev term (in/out); null for the dropout cell
-    const uint8_t* mask_h; const uint8_t* mask_c;
-    int kind, training; float rate_h, rate_c;
-    float* dgates;                            // [B, 4D] out (pre-activation gradients)
-    int B, D, last;                           // last = 1: step T-1, no incoming recurrent gradient
-};
 
 __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const CellBwdArgs p) {
     extern __shared__ __align__(16) float sm[];
@@ -131,12 +118,19 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const CellBwdArgs p)
             const size_t bu = (size_t)b * D + u, g0 = (size_t)b * 4 * D + u;
             float dh = dhq[j];
             if (p.dh_static) dh += p.dh_static[(size_t)b * p.ld_dhs + u];
-            float dc_in = 0.f;
+            float dc_in = 0.f, dh_rec = 0.f;
             if (!p.last) {
-                for (int s = 0; s < p.nsplit; ++s) dh += p.part[s * p.part_stride + (size_t)b * p.ld_part + p.part_col0 + u];
+                for (int s = 0; s < p.nsplit; ++s) dh_rec += p.part[s * p.part_stride + (size_t)b * p.ld_part + p.part_col0 + u];
                 dc_in = p.dc_state[bu];
-                if (p.dhz_state) dh += p.dhz_state[bu];
+                if (p.dhz_state) dh_rec += p.dhz_state[bu];
             }
+            if (p.lengths && p.step >= p.lengths[b]) {    // frozen step: gradients of the state pass straight through
+                p.dgates[g0] = 0.f; p.dgates[g0 + D] = 0.f; p.dgates[g0 + 2 * D] = 0.f; p.dgates[g0 + 3 * D] = 0.f;
+                p.dc_state[bu] = dc_in;
+                p.dhz_state[bu] = dh_rec;
+                continue;
+            }
+            dh += dh_rec;
             const float gi = p.gates[g0], gf = p.gates[g0 + D], gg = p.gates[g0 + 2 * D], go = p.gates[g0 + 3 * D];
             const float cp = p.c_prev[bu];
             const float tc = tanhf(gf * cp + gi * gg);
@@ -465,6 +459,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnBwdArgs
     }
 }
 
+}  // namespace
 int launch_cell_bwd(const CellBwdArgs& a, cudaStream_t st) {
     const int Bp = (a.B + 7) & ~7;
     const size_t smem = a.dq ? ((size_t)a.A * Bp + (size_t)a.A * (CELL_UNITS + 1)) * sizeof(float) : 0;
@@ -477,6 +472,7 @@ int launch_cell_bwd(const CellBwdArgs& a, cudaStream_t st) {
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
 }
+namespace {
 
 int pick_attn_bwd_chunk(int L, int M, int A, int C, int K) {
     const int Lp = (L + 3) & ~3;
@@ -550,20 +546,7 @@ int wgemm(cudaStream_t st, const BwdLayout& l, float* ws, int transA, int transB
     GemmDesc d;
     d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.transA = transA;
     d.transB = transB; d.beta = beta; d.batch = batch; d.strideA = sA; d.strideB = sB; d.strideC = sC;
-    const bool big = M > 64 && N > 64;
-    const int tiles = (big ? cdiv(M, 128) * cdiv(N, 128) : cdiv(M, 64) * cdiv(N, 64)) * batch;
-    int s = 1;
-    if (tiles < 148) {
-        s = (296 + tiles - 1) / tiles;
-        const int kmax = cdiv(K, 256);
-        if (s > kmax) s = kmax;
-        if (s > 32) s = 32;
-        if (s < 1) s = 1;
-        while (s > 1 && (size_t)s * batch * M * N > l.gpart_elems) --s;
-    }
-    d.splitk = s;
-    d.partial = ws + l.gpart;
-    return gemm_f32(d, st);
+    return gemm_f32_auto(d, ws + l.gpart, l.gpart_elems, st);
 }
 
 }  // namespace

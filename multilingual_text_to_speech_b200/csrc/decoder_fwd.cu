@@ -73,18 +73,6 @@ __global__ void split_frames_kernel(float* __restrict__ spec, float* __restrict_
 //   gates: xproj (time-batched input projection incl. both biases) + sum of split-K partials of the
 //   recurrent GEMM.  modules/layers.py:26-34 (zoneout), :44-47 (dropout), torch LSTMCell order i,f,g,o.
 // =============================================================================================
-struct CellFwdArgs {
-    const float* xproj; float* gates;                 // [B, 4D] (may alias)
-    const float* part; int nsplit; size_t part_stride;
-    const float* c_prev;                              // [B, D]
-    const float* h_prev; int ld_hprev;                // [B, ld]
-    float* c_out;                                     // [B, D]
-    float* h_out; int ld_hout;                        // [B, ld]
-    const uint8_t* mask_h; const uint8_t* mask_c;     // [B, D] or null
-    int kind, training; float rate_h, rate_c;
-    const float* Wq; int A; float* qpart;             // optional: qpart[blk, B, A] = h[:, blk units] . Wq[:, blk units]^T
-    int B, D;
-};
 
 __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const CellFwdArgs p) {
     extern __shared__ __align__(16) float sm[];
@@ -124,6 +112,11 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const CellFwdArgs p)
                 }
             } else if (p.training && p.mask_h) {
                 hn = hn * (float)p.mask_h[(size_t)b * D + u] * inv_h;
+            }
+            if (p.lengths) {                     // packed sequence: frozen state and zero output beyond the length
+                const bool valid = p.step < p.lengths[b];
+                if (p.y_out) p.y_out[(size_t)b * p.ld_y + u] = valid ? hn : 0.f;
+                if (!valid) { cn = cp; hn = p.h_prev[(size_t)b * p.ld_hprev + u]; }
             }
             p.c_out[(size_t)b * D + u] = cn;
             p.h_out[(size_t)b * p.ld_hout + u] = hn;
@@ -314,6 +307,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnFwdArgs
     }
 }
 
+}  // namespace
 int launch_cell_fwd(const CellFwdArgs& a, cudaStream_t st) {
     const int Bp = (a.B + 7) & ~7;
     const size_t smem = a.Wq ? ((size_t)CELL_UNITS * Bp + (size_t)a.A * (CELL_UNITS + 1)) * sizeof(float) : 0;
@@ -323,6 +317,7 @@ int launch_cell_fwd(const CellFwdArgs& a, cudaStream_t st) {
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
 }
+namespace {
 
 int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {
     const size_t smem = attn_fwd_smem_floats(a.L, a.M, a.A, a.C, a.K) * sizeof(float);

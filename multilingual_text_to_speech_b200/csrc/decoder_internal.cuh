@@ -80,6 +80,40 @@ static inline DecoderLayout decoder_layout(const b200tts_decoder_shape& s) {
 
 int validate_decoder_shape(const b200tts_decoder_shape& s);
 
+// ---- LSTM cell kernels (decoder_fwd.cu / decoder_bwd.cu), shared with the encoder bi-LSTM ----
+struct CellFwdArgs {
+    const float* xproj; float* gates;                 // [B, 4D] (may alias)
+    const float* part; int nsplit; size_t part_stride;
+    const float* c_prev;                              // [B, D]
+    const float* h_prev; int ld_hprev;                // [B, ld]
+    float* c_out;                                     // [B, D]
+    float* h_out; int ld_hout;                        // [B, ld]
+    const uint8_t* mask_h; const uint8_t* mask_c;     // [B, D] or null
+    int kind, training; float rate_h, rate_c;
+    const float* Wq; int A; float* qpart;             // optional: qpart[blk, B, A] = h[:, blk units] . Wq[:, blk units]^T
+    float* y_out; int ld_y;                            // optional: y[b, u] = valid ? h : 0 (packed-sequence output)
+    const int* lengths; int step;                     // optional: utterance b is valid at this step iff step < lengths[b]
+    int B, D;
+};
+
+struct CellBwdArgs {
+    const float* gates;                       // [B, 4D] activated i,f,g,o
+    const float* c_prev;                      // [B, D]
+    const float* dh_static; int ld_dhs;       // [B, ld] or null
+    const float* part; int nsplit; size_t part_stride; int ld_part; int part_col0;   // recurrent dh partials (null on the last step)
+    const float* dq; const float* Wq; int A;  // optional: dh += dq[b, :] . Wq[:, u]
+    float* dc_state;                          // [B, D] in: d c_out of this step; out: d c_out of the previous step
+    float* dhz_state;                         // [B, D] zoneout: direct d h_prev term (in/out); null for the dropout cell
+    const uint8_t* mask_h; const uint8_t* mask_c;
+    int kind, training; float rate_h, rate_c;
+    float* dgates;                            // [B, 4D] out (pre-activation gradients)
+    const int* lengths; int step;             // optional packed-sequence validity (see CellFwdArgs)
+    int B, D, last;                           // last = 1: step T-1, no incoming recurrent gradient
+};
+
+int launch_cell_fwd(const CellFwdArgs& a, cudaStream_t st);
+int launch_cell_bwd(const CellBwdArgs& a, cudaStream_t st);
+
 // ---- kernels shared between forward and backward translation units ----
 int launch_copy2d(float* dst, int ldd, const float* src, int lds, int rows, int cols, cudaStream_t st);
 int launch_add_vec(float* dst, const float* a, const float* b, int n, cudaStream_t st);

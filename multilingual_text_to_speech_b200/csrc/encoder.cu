@@ -1,0 +1,410 @@
+// Encoder-side ops: (grouped, dilated) 1-D convolution block with batch-norm / activation / dropout /
+// highway gate, the per-language parameter generator, and embedding gather / scatter.
+//   reference: modules/layers.py:50-178 (ConvBlock*, HighwayConvBlock*), modules/generated.py:7-96,
+//              modules/encoder.py:196-221, modules/tacotron2.py:237-239,363 (embedding), :143-146 (cond. embeddings)
+// Convolutions run as im2col + the batched fp32 GEMM (one GEMM per (sample-row, language) pair, the
+// generated per-language kernels shared across rows through GemmDesc::a_batch_mod).
+#include "common.cuh"
+
+namespace b200tts {
+
+namespace {
+
+inline int grid_for(size_t n) {
+    size_t g = (n + 255) / 256;
+    return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
+}
+
+// col[nb, i*k + t, l] = x[nb, i, l + t*dil - pad]  (zero outside)      nb runs over (row, group) pairs
+__global__ void im2col1d_kernel(float* __restrict__ col, const float* __restrict__ x, size_t NBG, int Cin, int L, int k, int dil, int pad) {
+    const size_t total = NBG * Cin * k * L;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int l = idx % L;
+        const int t = (idx / L) % k;
+        const size_t ni = idx / ((size_t)L * k);          // nb * Cin + i
+        const int ls = l + t * dil - pad;
+        col[idx] = (ls >= 0 && ls < L) ? x[ni * L + ls] : 0.f;
+    }
+}
+
+// dx[nb, i, l] (+)= sum_t dcol[nb, i*k + t, l - t*dil + pad]
+__global__ void col2im1d_kernel(float* __restrict__ dx, const float* __restrict__ dcol, size_t NBG, int Cin, int L, int k, int dil,
+                                int pad, int accumulate) {
+    const size_t total = NBG * Cin * L;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int l = idx % L;
+        const size_t ni = idx / L;
+        float acc = accumulate ? dx[idx] : 0.f;
+        for (int t = 0; t < k; ++t) {
+            const int lo = l - t * dil + pad;
+            if (lo >= 0 && lo < L) acc += dcol[(ni * k + t) * L + lo];
+        }
+        dx[idx] = acc;
+    }
+}
+
+// per-channel batch statistics over (NB, L); x [NB, Ct, L].  One CTA per channel, two passes (mean, then variance).
+__global__ void __launch_bounds__(128) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ invstd,
+                                                       float* __restrict__ running_mean, float* __restrict__ running_var, int NB,
+                                                       int Ct, int L, float eps, float momentum) {
+    __shared__ float red[64];
+    const int c = blockIdx.x;
+    const int n = NB * L;
+    float s = 0.f;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) s += x[((size_t)(idx / L) * Ct + c) * L + idx % L];
+    const float mu = block_sum(s, red) / (float)n;
+    float v = 0.f;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const float d = x[((size_t)(idx / L) * Ct + c) * L + idx % L] - mu;
+        v = fmaf(d, d, v);
+    }
+    const float var = block_sum(v, red) / (float)n;
+    if (threadIdx.x == 0) {
+        mean[c] = mu;
+        invstd[c] = 1.f / sqrtf(var + eps);
+        if (running_mean) {
+            const float unbiased = n > 1 ? var * ((float)n / (float)(n - 1)) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+    }
+}
+
+__global__ void bn_eval_stats_kernel(float* __restrict__ mean, float* __restrict__ invstd, const float* __restrict__ rm,
+                                     const float* __restrict__ rv, int Ct, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < Ct) { mean[c] = rm[c]; invstd[c] = 1.f / sqrtf(rv[c] + eps); }
+}
+
+__device__ __forceinline__ float act_fwd(int kind, float z) { return kind == 1 ? fmaxf(z, 0.f) : (kind == 2 ? tanhf(z) : z); }
+__device__ __forceinline__ float act_bwd(int kind, float z, float a) { return kind == 1 ? (z > 0.f ? 1.f : 0.f) : (kind == 2 ? 1.f - a * a : 1.f); }
+
+struct BlockArgs {
+    const float* conv;      // [NB, G*Cout, L] convolution output (pre batch-norm)
+    const float* mean; const float* invstd;   // [G*Cout]
+    const float* gamma; const float* beta; int affine_gstride;   // gamma[g*stride + o]
+    const uint8_t* keep; float keep_scale;    // [NB, G*Cout, L] or null
+    const float* xin;       // [NB, G*Cin, L] block input (highway only)
+    int NB, G, Cout, L, act, highway;
+};
+
+// y = dropout(act(bn(conv)));  highway: out[g, c] = y[g, C + c] * sigmoid(y[g, c]) + xin[g, c] * (1 - sigmoid(y[g, c]))
+__global__ void block_fwd_kernel(const BlockArgs p, float* __restrict__ out) {
+    const int Cf = p.highway ? p.Cout / 2 : p.Cout;
+    const size_t total = (size_t)p.NB * p.G * Cf * p.L;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int l = idx % p.L;
+        const int c = (idx / p.L) % Cf;
+        const int g = (idx / ((size_t)p.L * Cf)) % p.G;
+        const size_t nb = idx / ((size_t)p.L * Cf * p.G);
+        auto value = [&](int o) {
+            const int ch = g * p.Cout + o;
+            const size_t ci = (nb * p.G * p.Cout + ch) * p.L + l;
+            const float z = (p.conv[ci] - p.mean[ch]) * p.invstd[ch] * p.gamma[g * p.affine_gstride + o] + p.beta[g * p.affine_gstride + o];
+            float a = act_fwd(p.act, z);
+            if (p.keep) a = a * (float)p.keep[ci] * p.keep_scale;
+            return a;
+        };
+        if (p.highway) {
+            const float h1 = value(c), h2 = value(Cf + c);
+            const float s = sigmoidf_acc(h1);
+            out[idx] = h2 * s + p.xin[idx] * (1.f - s);
+        } else {
+            out[idx] = value(c);
+        }
+    }
+}
+
+// backward through highway / dropout / activation: dz [NB, G*Cout, L] (grad wrt the batch-norm output) and,
+// for highway blocks, the skip-path gradient dx = dout * (1 - sigmoid(h1)).
+__global__ void block_bwd_prep_kernel(const BlockArgs p, const float* __restrict__ dout, float* __restrict__ dz, float* __restrict__ dx_skip) {
+    const int Cf = p.highway ? p.Cout / 2 : p.Cout;
+    const size_t total = (size_t)p.NB * p.G * Cf * p.L;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int l = idx % p.L;
+        const int c = (idx / p.L) % Cf;
+        const int g = (idx / ((size_t)p.L * Cf)) % p.G;
+        const size_t nb = idx / ((size_t)p.L * Cf * p.G);
+        float zs[2], as[2], ks[2];
+        size_t cis[2];
+        const int nch = p.highway ? 2 : 1;
+        for (int j = 0; j < nch; ++j) {
+            const int o = c + j * Cf, ch = g * p.Cout + o;
+            cis[j] = (nb * p.G * p.Cout + ch) * p.L + l;
+            zs[j] = (p.conv[cis[j]] - p.mean[ch]) * p.invstd[ch] * p.gamma[g * p.affine_gstride + o] + p.beta[g * p.affine_gstride + o];
+            as[j] = act_fwd(p.act, zs[j]);
+            ks[j] = p.keep ? (float)p.keep[cis[j]] * p.keep_scale : 1.f;
+        }
+        const float go = dout[idx];
+        if (p.highway) {
+            const float h1 = as[0] * ks[0], h2 = as[1] * ks[1];
+            const float s = sigmoidf_acc(h1);
+            const float dh1 = go * (h2 - p.xin[idx]) * s * (1.f - s), dh2 = go * s;
+            dz[cis[0]] = dh1 * ks[0] * act_bwd(p.act, zs[0], as[0]);
+            dz[cis[1]] = dh2 * ks[1] * act_bwd(p.act, zs[1], as[1]);
+            dx_skip[idx] = go * (1.f - s);
+        } else {
+            dz[cis[0]] = go * ks[0] * act_bwd(p.act, zs[0], as[0]);
+        }
+    }
+}
+
+// per channel: s1 = sum dz, s2 = sum dz * xhat  -> dbeta += s1, dgamma += s2; keeps s1, s2 for the apply pass
+__global__ void __launch_bounds__(128) bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ conv,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            float* __restrict__ s1o, float* __restrict__ s2o, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int affine_gstride, int NB, int G, int Cout, int L) {
+    __shared__ float red[64];
+    const int ch = blockIdx.x, Ct = G * Cout, n = NB * L;
+    const float mu = mean[ch], is = invstd[ch];
+    float s1 = 0.f, s2 = 0.f;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const size_t ci = ((size_t)(idx / L) * Ct + ch) * L + idx % L;
+        const float d = dz[ci];
+        s1 += d;
+        s2 = fmaf(d, (conv[ci] - mu) * is, s2);
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        s1o[ch] = s1; s2o[ch] = s2;
+        const int g = ch / Cout, o = ch % Cout;
+        if (dbeta) dbeta[g * affine_gstride + o] += s1;
+        if (dgamma) dgamma[g * affine_gstride + o] += s2;
+    }
+}
+
+// dconv = gamma * invstd * (dz - s1/n - xhat * s2/n)   (training);  gamma * invstd * dz (eval).  In place on dz.
+__global__ void bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restrict__ conv, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma, int affine_gstride,
+                                    const float* __restrict__ s1, const float* __restrict__ s2, int NB, int G, int Cout, int L, int training) {
+    const int Ct = G * Cout;
+    const size_t total = (size_t)NB * Ct * L;
+    const float inv_n = 1.f / (float)(NB * L);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (idx / L) % Ct;
+        const float gm = gamma[(ch / Cout) * affine_gstride + ch % Cout] * invstd[ch];
+        float d = dz[idx];
+        if (training) d = d - s1[ch] * inv_n - (conv[idx] - mean[ch]) * invstd[ch] * s2[ch] * inv_n;
+        dz[idx] = gm * d;
+    }
+}
+
+// out[b, l, :] = table[ids[b, l], :]
+__global__ void embedding_fwd_kernel(float* __restrict__ out, int ldo, const float* __restrict__ table, const int* __restrict__ ids,
+                                     size_t ntok, int E) {
+    const size_t total = ntok * E;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = idx / E;
+        const int e = idx % E;
+        out[t * ldo + e] = table[(size_t)ids[t] * E + e];
+    }
+}
+
+// dtable[v, :] += sum over tokens with id v of dout[token, :]   (one CTA per vocabulary row: deterministic order)
+__global__ void __launch_bounds__(256) embedding_bwd_kernel(float* __restrict__ dtable, const float* __restrict__ dout, int ldo,
+                                                            const int* __restrict__ ids, int ntok, int E, int padding_idx) {
+    const int v = blockIdx.x;
+    if (v == padding_idx) return;
+    for (int e0 = 0; e0 < E; e0 += blockDim.x) {
+        const int e = e0 + threadIdx.x;
+        float acc = 0.f;
+        for (int t = 0; t < ntok; ++t)
+            if (ids[t] == v && e < E) acc += dout[(size_t)t * ldo + e];
+        if (e < E) dtable[(size_t)v * E + e] += acc;
+    }
+}
+
+__global__ void colsum_rows_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, size_t cols) {
+    for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < cols; c += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += src[(size_t)r * cols + c];
+        dst[c] += s;
+    }
+}
+
+struct BlockDims {
+    int NB, G, Cin, Cout, L, k, dil, pad, Cf;
+    size_t conv_elems, col_elems, Ct;
+};
+inline BlockDims block_dims(const b200tts_convblock_shape& s) {
+    BlockDims d;
+    d.NB = s.NB; d.G = s.G; d.Cin = s.Cin; d.Cout = s.Cout; d.L = s.L; d.k = s.k; d.dil = s.dilation;
+    d.pad = (s.k - 1) * s.dilation / 2;
+    d.Cf = s.highway ? s.Cout / 2 : s.Cout;
+    d.Ct = (size_t)s.G * s.Cout;
+    d.conv_elems = (size_t)s.NB * d.Ct * s.L;
+    d.col_elems = s.k > 1 ? (size_t)s.NB * s.G * s.Cin * s.k * s.L : 0;
+    return d;
+}
+constexpr size_t kGemmScratch = (size_t)4 * 1024 * 1024;
+
+int validate_block(const b200tts_convblock_shape& s) {
+    B200_REQUIRE(s.NB > 0 && s.G > 0 && s.Cin > 0 && s.Cout > 0 && s.L > 0 && s.k > 0 && s.dilation > 0, "convblock: non-positive dimension");
+    B200_REQUIRE(s.k % 2 == 1, "convblock: even kernel sizes are not supported (k=%d)", s.k);
+    B200_REQUIRE(!s.highway || s.Cout == 2 * s.Cin, "convblock: highway needs Cout == 2*Cin (got %d, %d)", s.Cout, s.Cin);
+    B200_REQUIRE(s.activation >= 0 && s.activation <= 2, "convblock: unknown activation %d", s.activation);
+    B200_REQUIRE(s.dropout >= 0.f && s.dropout < 1.f, "convblock: dropout must be in [0,1)");
+    return B200TTS_OK;
+}
+
+}  // namespace
+
+size_t convblock_saved_floats(const b200tts_convblock_shape& s) {
+    const BlockDims d = block_dims(s);
+    return align_up_sz(d.conv_elems, 64) + 2 * align_up_sz(d.Ct, 64);
+}
+size_t convblock_workspace_floats(const b200tts_convblock_shape& s) {
+    const BlockDims d = block_dims(s);
+    // forward: im2col.  backward: im2col + dz/dconv + dcol + s1/s2 + split-K scratch
+    return align_up_sz(d.col_elems, 64) * 2 + align_up_sz(d.conv_elems, 64) + 2 * align_up_sz(d.Ct, 64) + kGemmScratch;
+}
+
+int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, const float* weight, const float* gamma,
+                           const float* beta, int affine_gstride, float* running_mean, float* running_var, const uint8_t* keep,
+                           float* out, float* saved, float* ws, cudaStream_t st) {
+    B200_TRY(validate_block(s));
+    const BlockDims d = block_dims(s);
+    float* conv = saved;
+    float* mean = saved + align_up_sz(d.conv_elems, 64);
+    float* invstd = mean + align_up_sz(d.Ct, 64);
+    const float* col = x;
+    if (s.k > 1) {
+        im2col1d_kernel<<<grid_for(d.col_elems), 256, 0, st>>>(ws, x, (size_t)s.NB * s.G, s.Cin, s.L, s.k, s.dilation, d.pad);
+        B200_LAUNCH_CHECK();
+        col = ws;
+    }
+    GemmDesc g;
+    g.A = weight; g.lda = s.Cin * s.k; g.transA = 0; g.a_batch_mod = s.G; g.strideA = (long long)s.Cout * s.Cin * s.k;
+    g.B = col; g.ldb = s.L; g.transB = 0; g.strideB = (long long)s.Cin * s.k * s.L;
+    g.C = conv; g.ldc = s.L; g.strideC = (long long)s.Cout * s.L;
+    g.M = s.Cout; g.N = s.L; g.K = s.Cin * s.k; g.batch = s.NB * s.G;
+    B200_TRY(gemm_f32(g, st));
+    if (s.training) {
+        bn_stats_kernel<<<(int)d.Ct, 128, 0, st>>>(conv, mean, invstd, running_mean, running_var, s.NB, (int)d.Ct, s.L, s.eps, s.momentum);
+    } else {
+        B200_REQUIRE(running_mean && running_var, "convblock: eval mode needs running statistics");
+        bn_eval_stats_kernel<<<cdiv(d.Ct, 256), 256, 0, st>>>(mean, invstd, running_mean, running_var, (int)d.Ct, s.eps);
+    }
+    B200_LAUNCH_CHECK();
+    BlockArgs a{conv, mean, invstd, gamma, beta, affine_gstride, (s.training && s.dropout > 0.f) ? keep : nullptr,
+                1.f / (1.f - s.dropout), x, s.NB, s.G, s.Cout, s.L, s.activation, s.highway};
+    block_fwd_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, out);
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+
+int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, const float* weight, const float* gamma,
+                            const float* beta, int affine_gstride, const uint8_t* keep, const float* saved, const float* dout,
+                            float* dx, float* dweight, float* dgamma, float* dbeta, float* ws, cudaStream_t st) {
+    B200_TRY(validate_block(s));
+    const BlockDims d = block_dims(s);
+    const float* conv = saved;
+    const float* mean = saved + align_up_sz(d.conv_elems, 64);
+    const float* invstd = mean + align_up_sz(d.Ct, 64);
+    float* col = ws;
+    float* dcol = col + align_up_sz(d.col_elems, 64);
+    float* dz = dcol + align_up_sz(d.col_elems, 64);
+    float* s1 = dz + align_up_sz(d.conv_elems, 64);
+    float* s2 = s1 + align_up_sz(d.Ct, 64);
+    float* scratch = s2 + align_up_sz(d.Ct, 64);
+
+    BlockArgs a{conv, mean, invstd, gamma, beta, affine_gstride, (s.training && s.dropout > 0.f) ? keep : nullptr,
+                1.f / (1.f - s.dropout), x, s.NB, s.G, s.Cout, s.L, s.activation, s.highway};
+    block_bwd_prep_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, dout, dz, dx);
+    B200_LAUNCH_CHECK();
+    bn_bwd_reduce_kernel<<<(int)d.Ct, 128, 0, st>>>(dz, conv, mean, invstd, s1, s2, dgamma, dbeta, affine_gstride, s.NB, s.G, s.Cout, s.L);
+    B200_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<grid_for(d.conv_elems), 256, 0, st>>>(dz, conv, mean, invstd, gamma, affine_gstride, s1, s2, s.NB, s.G, s.Cout,
+                                                                s.L, s.training);
+    B200_LAUNCH_CHECK();
+    const float* colr = x;
+    if (s.k > 1) {
+        im2col1d_kernel<<<grid_for(d.col_elems), 256, 0, st>>>(col, x, (size_t)s.NB * s.G, s.Cin, s.L, s.k, s.dilation, d.pad);
+        B200_LAUNCH_CHECK();
+        colr = col;
+    }
+    const int R = s.Cin * s.k;
+    if (dweight) {
+        // dW[g] (+)= sum_rows dconv[row, g] . col[row, g]^T    (one batched GEMM per sample row, accumulating)
+        for (int q = 0; q < s.NB; ++q) {
+            GemmDesc g;
+            g.A = dz + (size_t)q * d.Ct * s.L; g.lda = s.L; g.transA = 0; g.strideA = (long long)s.Cout * s.L;
+            g.B = colr + (size_t)q * s.G * R * s.L; g.ldb = s.L; g.transB = 1; g.strideB = (long long)R * s.L;
+            g.C = dweight; g.ldc = R; g.strideC = (long long)s.Cout * R; g.beta = 1.f;
+            g.M = s.Cout; g.N = R; g.K = s.L; g.batch = s.G;
+            B200_TRY(gemm_f32(g, st));
+        }
+    }
+    if (dx) {
+        GemmDesc g;     // dcol[row, g] = W[g]^T . dconv[row, g]
+        g.A = weight; g.lda = R; g.transA = 1; g.a_batch_mod = s.G; g.strideA = (long long)s.Cout * R;
+        g.B = dz; g.ldb = s.L; g.transB = 0; g.strideB = (long long)s.Cout * s.L;
+        g.M = R; g.N = s.L; g.K = s.Cout; g.batch = s.NB * s.G;
+        if (s.k == 1) {
+            g.C = dx; g.ldc = s.L; g.strideC = (long long)s.Cin * s.L; g.beta = s.highway ? 1.f : 0.f;
+            B200_TRY(gemm_f32(g, st));
+        } else {
+            g.C = dcol; g.ldc = s.L; g.strideC = (long long)R * s.L;
+            B200_TRY(gemm_f32(g, st));
+            col2im1d_kernel<<<grid_for((size_t)s.NB * s.G * s.Cin * s.L), 256, 0, st>>>(dx, dcol, (size_t)s.NB * s.G, s.Cin, s.L, s.k,
+                                                                                       s.dilation, d.pad, s.highway);
+            B200_LAUNCH_CHECK();
+        }
+    }
+    (void)scratch; (void)beta;
+    return B200TTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameter generator: out[g, :] = (e[g] . Wb^T + bb) . Wk^T + bk        (modules/generated.py:38-39, 81-84)
+// ---------------------------------------------------------------------------------------------
+size_t generator_workspace_floats(int G, int bn) { return align_up_sz((size_t)G * bn, 64) + kGemmScratch; }
+
+int generator_forward_impl(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* bb, const float* Wk,
+                           const float* bk, float* eb, float* out, cudaStream_t st) {
+    B200_REQUIRE(G > 0 && gd > 0 && bn > 0 && R > 0 && R < (1ll << 31), "generator: bad dimensions");
+    GemmDesc a;
+    a.A = e; a.lda = gd; a.B = Wb; a.ldb = gd; a.transB = 1; a.C = eb; a.ldc = bn; a.bias = bb; a.M = G; a.N = bn; a.K = gd;
+    B200_TRY(gemm_f32(a, st));
+    GemmDesc b;
+    b.A = eb; b.lda = bn; b.B = Wk; b.ldb = bn; b.transB = 1; b.C = out; b.ldc = (int)R; b.bias = bk; b.M = G; b.N = (int)R; b.K = bn;
+    return gemm_f32(b, st);
+}
+
+int generator_backward_impl(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* Wk, const float* eb,
+                            const float* dout, float* de, float* dWb, float* dbb, float* dWk, float* dbk, float* ws, cudaStream_t st) {
+    float* deb = ws;
+    float* scratch = ws + align_up_sz((size_t)G * bn, 64);
+    GemmDesc a;     // dWk [R, bn] += dout^T . eb
+    a.A = dout; a.lda = (int)R; a.transA = 1; a.B = eb; a.ldb = bn; a.transB = 0; a.C = dWk; a.ldc = bn; a.beta = 1.f;
+    a.M = (int)R; a.N = bn; a.K = G;
+    B200_TRY(gemm_f32(a, st));
+    colsum_rows_add_kernel<<<grid_for((size_t)R), 256, 0, st>>>(dbk, dout, G, (size_t)R);
+    B200_LAUNCH_CHECK();
+    GemmDesc b;     // deb [G, bn] = dout . Wk   (long K: split)
+    b.A = dout; b.lda = (int)R; b.B = Wk; b.ldb = bn; b.transB = 0; b.C = deb; b.ldc = bn; b.M = G; b.N = bn; b.K = (int)R;
+    B200_TRY(gemm_f32_auto(b, scratch, kGemmScratch, st));
+    GemmDesc c;     // dWb [bn, gd] += deb^T . e
+    c.A = deb; c.lda = bn; c.transA = 1; c.B = e; c.ldb = gd; c.transB = 0; c.C = dWb; c.ldc = gd; c.beta = 1.f; c.M = bn; c.N = gd; c.K = G;
+    B200_TRY(gemm_f32(c, st));
+    colsum_rows_add_kernel<<<1, 256, 0, st>>>(dbb, deb, G, (size_t)bn);
+    B200_LAUNCH_CHECK();
+    GemmDesc dd;    // de [G, gd] += deb . Wb
+    dd.A = deb; dd.lda = bn; dd.B = Wb; dd.ldb = gd; dd.transB = 0; dd.C = de; dd.ldc = gd; dd.beta = 1.f; dd.M = G; dd.N = gd; dd.K = bn;
+    return gemm_f32(dd, st);
+}
+
+int embedding_forward_impl(float* out, int ldo, const float* table, const int* ids, long long ntok, int E, cudaStream_t st) {
+    embedding_fwd_kernel<<<grid_for((size_t)ntok * E), 256, 0, st>>>(out, ldo, table, ids, (size_t)ntok, E);
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+int embedding_backward_impl(float* dtable, int V, const float* dout, int ldo, const int* ids, long long ntok, int E, int padding_idx,
+                            cudaStream_t st) {
+    embedding_bwd_kernel<<<V, 256, 0, st>>>(dtable, dout, ldo, ids, (int)ntok, E, padding_idx);
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+
+}  // namespace b200tts

@@ -85,7 +85,7 @@ struct KernelArgs {
     int M, N, K, lda, ldb, ldc;
     int a_kcontig, b_kcontig, a_vec, b_vec;
     float alpha, beta;
-    int batch, splitk, kchunk;
+    int batch, splitk, kchunk, a_batch_mod;
     long long strideA, strideB, strideC;
 };
 
@@ -100,7 +100,7 @@ gemm_f32_kernel(const KernelArgs p) {
 
     const int z = blockIdx.z;
     const int bz = z / p.splitk, ks = z % p.splitk;
-    const float* A = p.A + (size_t)bz * p.strideA;
+    const float* A = p.A + (size_t)(p.a_batch_mod > 0 ? bz % p.a_batch_mod : bz) * p.strideA;
     const float* B = p.B + (size_t)bz * p.strideB;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int k_begin = ks * p.kchunk;
@@ -222,7 +222,7 @@ int gemm_f32(const GemmDesc& d, cudaStream_t stream) {
     p.M = d.M; p.N = d.N; p.K = d.K; p.lda = d.lda; p.ldb = d.ldb; p.ldc = d.ldc;
     p.a_kcontig = !d.transA; p.b_kcontig = d.transB;
     p.alpha = d.alpha; p.beta = d.beta; p.batch = d.batch; p.splitk = d.splitk;
-    p.strideA = d.strideA; p.strideB = d.strideB; p.strideC = d.strideC;
+    p.strideA = d.strideA; p.strideB = d.strideB; p.strideC = d.strideC; p.a_batch_mod = d.a_batch_mod;
     int kchunk = cdiv(d.K > 0 ? d.K : 1, d.splitk);
     kchunk = cdiv(kchunk, BK) * BK;
     p.kchunk = kchunk;
@@ -253,6 +253,27 @@ int gemm_f32(const GemmDesc& d, cudaStream_t stream) {
         B200_LAUNCH_CHECK();
     }
     return B200TTS_OK;
+}
+
+
+// Picks a split-K factor so that small-output / long-K products still fill the 148 SMs, bounded by the
+// scratch the caller provides for the partial sums.
+int gemm_f32_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream) {
+    const bool big = d.M > 64 && d.N > 64;
+    const long long tiles = (long long)(big ? cdiv(d.M, 128) * cdiv(d.N, 128) : cdiv(d.M, 64) * cdiv(d.N, 64)) * d.batch;
+    int s = 1;
+    if (tiles < 148 && scratch) {
+        s = (int)((296 + tiles - 1) / tiles);
+        const int kmax = cdiv(d.K, 128);
+        if (s > kmax) s = kmax;
+        if (s > 160) s = 160;
+        if (s < 1) s = 1;
+        while (s > 1 && (size_t)s * d.batch * d.M * d.N > scratch_elems) --s;
+    }
+    d.splitk = s;
+    d.partial = s > 1 ? scratch : nullptr;
+    d.keep_partials = 0;
+    return gemm_f32(d, stream);
 }
 
 }  // namespace b200tts

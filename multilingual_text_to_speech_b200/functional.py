@@ -185,3 +185,211 @@ class DecoderFunction(torch.autograd.Function):
 def decoder_forward(cfg, memory, target, text_lengths, params):
     """params: list of the 22 decoder parameter tensors in DECODER_PARAM_FIELDS order."""
     return DecoderFunction.apply(cfg, memory, target, text_lengths, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder-side ops
+# ------------------------------------------------------------------------------------------------
+ACTIVATIONS = {'identity': 0, 'relu': 1, 'tanh': 2}
+
+
+def _bytes(n, device):
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=device)
+
+
+class ConvBlockFunction(torch.autograd.Function):
+    """pad -> grouped conv -> batch norm -> activation -> dropout (-> highway) (reference modules/layers.py:50-178).
+
+    x [NB, G*Cin, L]; weight [G*Cout, Cin, k]; gamma/beta: flat tensors addressed (g, o) -> [g*gstride + o]
+    (a [G, 2*Cout] generated affine passes gamma = aff, beta = aff[:, Cout:] views with gstride = 2*Cout).
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, keep, meta):
+        (G, k, dilation, activation, highway, training, eps, momentum, dropout, gstride) = meta
+        _require_cuda(x, weight, gamma, beta)
+        x, weight = _f32c(x), _f32c(weight)
+        NB, GC, L = x.shape
+        Cin = GC // G
+        Cout = weight.shape[0] // G
+        assert weight.shape[1] == Cin and weight.shape[2] == k, (weight.shape, Cin, k)
+        assert gamma.stride(-1) == 1 and beta.stride(-1) == 1
+        shape = _lib.ConvBlockShape(NB, G, Cin, Cout, L, k, dilation, ACTIVATIONS[activation], int(highway), int(training),
+                                    eps, momentum, dropout)
+        lib = _lib.load()
+        saved = _bytes(lib.b200tts_convblock_saved_bytes(ctypes.byref(shape)), x.device)
+        ws = _bytes(lib.b200tts_convblock_workspace_bytes(ctypes.byref(shape)), x.device)
+        Cf = Cout // 2 if highway else Cout
+        out = torch.empty(NB, G * Cf, L, device=x.device, dtype=torch.float32)
+        if keep is not None:
+            assert keep.dtype == torch.uint8 and keep.is_contiguous() and tuple(keep.shape) == (NB, G * Cout, L)
+        check(lib.b200tts_convblock_forward(ctypes.byref(shape), ptr(x), ptr(weight), ptr(gamma), ptr(beta), gstride,
+                                            ptr(running_mean), ptr(running_var), ptr(keep), ptr(out), ptr(saved), ptr(ws), _stream()),
+              'b200tts_convblock_forward')
+        ctx.shape, ctx.gstride, ctx.saved_buf, ctx.keep = shape, gstride, saved, keep
+        ctx.save_for_backward(x, weight, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, gamma, beta = ctx.saved_tensors
+        shape = ctx.shape
+        lib = _lib.load()
+        ws = _bytes(lib.b200tts_convblock_workspace_bytes(ctypes.byref(shape)), x.device)
+        dout = _f32c(dout)
+        dx = torch.empty_like(x)
+        dweight = torch.zeros_like(weight)
+        # gamma / beta may be strided views of one generated-affine tensor: produce gradients in the same geometry
+        G, Cout, gs = shape.G, shape.Cout, ctx.gstride
+        dgb = torch.zeros(2 * G * Cout, device=x.device, dtype=torch.float32)
+        if gs == Cout:      # plain batch norm: separate dense gamma / beta
+            dgamma, dbeta = dgb[:G * Cout], dgb[G * Cout:]
+        else:               # generated affine [G, 2*Cout]: gamma = [:, :Cout], beta = [:, Cout:]
+            dgamma, dbeta = dgb, dgb[Cout:]
+        check(lib.b200tts_convblock_backward(ctypes.byref(shape), ptr(x), ptr(weight), ptr(gamma), ptr(beta), gs, ptr(ctx.keep),
+                                             ptr(ctx.saved_buf), ptr(dout), ptr(dx), ptr(dweight), ptr(dgamma), ptr(dbeta),
+                                             ptr(ws), _stream()), 'b200tts_convblock_backward')
+        if gs == Cout:
+            g_gamma, g_beta = dgamma.view_as(gamma), dbeta.view_as(beta)
+        else:
+            full = dgb.view(G, gs)
+            g_gamma, g_beta = full[:, :Cout], full[:, Cout:]
+        return dx, dweight, g_gamma, g_beta, None, None, None, None
+
+
+def conv_block(x, weight, gamma, beta, running_mean, running_var, keep, groups, kernel, dilation, activation, highway,
+               training, eps, momentum, dropout, gstride):
+    meta = (groups, kernel, dilation, activation, highway, training, eps, momentum, dropout, gstride)
+    return ConvBlockFunction.apply(x, weight, gamma, beta, running_mean, running_var, keep, meta)
+
+
+class GeneratorFunction(torch.autograd.Function):
+    """out[g] = (e[g] . Wb^T + bb) . Wk^T + bk   (reference modules/generated.py:38-39, 81-82)."""
+
+    @staticmethod
+    def forward(ctx, e, Wb, bb, Wk, bk):
+        _require_cuda(e, Wb, bb, Wk, bk)
+        e, Wb, bb, Wk, bk = [_f32c(t) for t in (e, Wb, bb, Wk, bk)]
+        G, gd = e.shape
+        bn, R = Wb.shape[0], Wk.shape[0]
+        eb = torch.empty(G, bn, device=e.device, dtype=torch.float32)
+        out = torch.empty(G, R, device=e.device, dtype=torch.float32)
+        check(_lib.load().b200tts_generator_forward(G, gd, bn, R, ptr(e), ptr(Wb), ptr(bb), ptr(Wk), ptr(bk), ptr(eb), ptr(out),
+                                                    _stream()), 'b200tts_generator_forward')
+        ctx.save_for_backward(e, Wb, Wk, eb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        e, Wb, Wk, eb = ctx.saved_tensors
+        G, gd = e.shape
+        bn, R = Wb.shape[0], Wk.shape[0]
+        lib = _lib.load()
+        dout = _f32c(dout)
+        de, dWb, dWk = torch.zeros_like(e), torch.zeros_like(Wb), torch.zeros_like(Wk)
+        dbb = torch.zeros(bn, device=e.device); dbk = torch.zeros(R, device=e.device)
+        ws = _bytes(lib.b200tts_generator_workspace_bytes(G, bn), e.device)
+        check(lib.b200tts_generator_backward(G, gd, bn, R, ptr(e), ptr(Wb), ptr(Wk), ptr(eb), ptr(dout), ptr(de), ptr(dWb),
+                                             ptr(dbb), ptr(dWk), ptr(dbk), ptr(ws), _stream()), 'b200tts_generator_backward')
+        return de, dWb, dbb, dWk, dbk
+
+
+class EmbeddingFunction(torch.autograd.Function):
+    """table[ids] with optional padding row (nn.Embedding, reference modules/tacotron2.py:237-239, 121-124)."""
+
+    @staticmethod
+    def forward(ctx, table, ids, padding_idx):
+        _require_cuda(table, ids)
+        table = _f32c(table)
+        ids32 = ids.to(torch.int32).contiguous()
+        E = table.shape[1]
+        out = torch.empty(*ids.shape, E, device=table.device, dtype=torch.float32)
+        check(_lib.load().b200tts_embedding_forward(ptr(out), E, ptr(table), ptr(ids32), ids32.numel(), E, _stream()),
+              'b200tts_embedding_forward')
+        ctx.save_for_backward(ids32)
+        ctx.V, ctx.E, ctx.padding_idx = table.shape[0], E, -1 if padding_idx is None else int(padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids32,) = ctx.saved_tensors
+        dout = _f32c(dout)
+        dtable = torch.zeros(ctx.V, ctx.E, device=dout.device, dtype=torch.float32)
+        check(_lib.load().b200tts_embedding_backward(ptr(dtable), ctx.V, ptr(dout), ctx.E, ptr(ids32), ids32.numel(), ctx.E,
+                                                     ctx.padding_idx, _stream()), 'b200tts_embedding_backward')
+        return dtable, None, None
+
+
+def embedding(table, ids, padding_idx=None):
+    return EmbeddingFunction.apply(table, ids, padding_idx)
+
+
+class BiLSTMFunction(torch.autograd.Function):
+    """Packed bidirectional LSTM (reference modules/encoder.py:41-44)."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, *params):
+        _require_cuda(x, lengths, *params)
+        x = _f32c(x)
+        params = [_f32c(p) for p in params]
+        lengths32 = lengths.to(torch.int32).contiguous()
+        B, L, E = x.shape
+        H = params[1].shape[1]
+        shape = _lib.BiLSTMShape(B, L, E, H)
+        lib = _lib.load()
+        saved = _bytes(lib.b200tts_bilstm_saved_bytes(ctypes.byref(shape)), x.device)
+        ws = _bytes(lib.b200tts_bilstm_workspace_bytes(ctypes.byref(shape)), x.device)
+        out = torch.empty(B, L, 2 * H, device=x.device, dtype=torch.float32)
+        pstruct = _lib.BiLSTMParams(*[ptr(p) for p in params])
+        check(lib.b200tts_bilstm_forward(ctypes.byref(shape), ctypes.byref(pstruct), ptr(x), ptr(lengths32), ptr(out), ptr(saved),
+                                         ptr(ws), _stream()), 'b200tts_bilstm_forward')
+        ctx.shape, ctx.saved_buf = shape, saved
+        ctx.save_for_backward(lengths32, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lengths32, *params = ctx.saved_tensors
+        shape = ctx.shape
+        lib = _lib.load()
+        dout = _f32c(dout)
+        ws = _bytes(lib.b200tts_bilstm_workspace_bytes(ctypes.byref(shape)), dout.device)
+        dx = torch.empty(shape.B, shape.L, shape.E, device=dout.device, dtype=torch.float32)
+        grads = [torch.zeros_like(p) for p in params]
+        pstruct = _lib.BiLSTMParams(*[ptr(p) for p in params])
+        gstruct = _lib.BiLSTMParams(*[ptr(g) for g in grads])
+        check(lib.b200tts_bilstm_backward(ctypes.byref(shape), ctypes.byref(pstruct), ptr(lengths32), ptr(ctx.saved_buf), ptr(dout),
+                                          ptr(dx), ctypes.byref(gstruct), ptr(ws), _stream()), 'b200tts_bilstm_backward')
+        return (dx, None, *grads)
+
+
+def bilstm(x, lengths, params):
+    """params: 8 tensors in _lib.BILSTM_PARAM_FIELDS order."""
+    return BiLSTMFunction.apply(x, lengths, *params)
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = x . W^T + b on the library GEMM (used by the small dense layers outside the fused decoder)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, weight)
+        x2 = _f32c(x).reshape(-1, x.shape[-1])
+        weight = _f32c(weight)
+        out = gemm(x2, weight, False, True, bias=None if bias is None else _f32c(bias))
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias, ctx.xshape = bias is not None, x.shape
+        return out.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, weight = ctx.saved_tensors
+        d2 = _f32c(dout).reshape(-1, weight.shape[0])
+        dx = gemm(d2, weight, False, False).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = gemm(d2, x2, True, False, splitk=8 if x2.shape[0] > 4096 else 1)
+        db = d2.sum(0) if ctx.has_bias else None
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    return LinearFunction.apply(x, weight, bias)

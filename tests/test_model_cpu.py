@@ -1,0 +1,44 @@
+"""Host-side (CPU) checks of the module surface: constructor / state_dict compatibility with the reference."""
+import pytest
+import torch
+
+from helpers import Golden, GOLDEN_CASES
+import model_cases
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_state_dict_names_and_shapes_match_reference(name):
+    g = Golden(name)
+    model = model_cases.build_model(g)            # strict load: raises on any missing / unexpected key or shape mismatch
+    own = model.state_dict()
+    assert list(own.keys()) == list(g.sd.keys())
+    for k, v in own.items():
+        assert tuple(v.shape) == tuple(g.sd[k].shape), k
+    # shared modules are registered twice, exactly like the reference
+    assert model._decoder._prenet is model._prenet and model._decoder._attention is model._attention
+    # the handles train.py reads (train.py:67,130,262-266)
+    for attr in ('_encoder', '_decoder', '_postnet', '_prenet', '_embedding', '_attention'):
+        assert len(list(getattr(model, attr).parameters())) > 0
+
+
+def test_params_surface():
+    from multilingual_text_to_speech_b200.params.params import Params as hp
+    hp.reset()
+    assert hp.symbols_count() == 70 and hp.decoder_dimension == 1024 and hp.attention_kernel_size == 31
+    sd = hp.state_dict()
+    assert 'batch_size' in sd and 'symbols_count' not in sd
+    hp.load_state_dict({'encoder_type': 'generated'})
+    assert hp.encoder_type == 'generated'
+    hp.reset()
+    assert hp.encoder_type == 'simple'
+
+
+def test_no_cpu_fallback():
+    from multilingual_text_to_speech_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip('checks the no-GPU failure mode')
+    g = Golden('lj_dropout')
+    model = model_cases.build_model(g)
+    i = g.inputs
+    with pytest.raises(_lib.B200TTSError):
+        model(i['text'], i['text_length'], i['target'], i['target_length'], None, None, 1.0)

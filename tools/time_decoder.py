@@ -1,0 +1,53 @@
+"""Time the fused decoder (forward + backward) alone at a given shape; prints per-phase CUDA-event times."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--B', type=int, default=64)
+    ap.add_argument('--L', type=int, default=180)
+    ap.add_argument('--T', type=int, default=900)
+    ap.add_argument('--M', type=int, default=288)
+    ap.add_argument('--kind', default='dropout')
+    ap.add_argument('--iters', type=int, default=3)
+    ap.add_argument('--fwd-only', action='store_true')
+    a = ap.parse_args()
+    import decoder_cases as dc
+    from multilingual_text_to_speech_b200 import functional as F, _lib
+    c = dc.full_dim_case(B=a.B, L=a.L, T=a.T, M=a.M, kind=a.kind, seed=1, ragged=False)
+    dev = torch.device('cuda:0')
+    cfg, params, memory = dc._cuda_inputs(c, dev)
+    target, lens = c.target.to(dev), c.lengths.to(dev)
+    for it in range(a.iters + 1):
+        n0 = _lib.launch_count()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        t0 = time.perf_counter()
+        e0.record()
+        spec, stop, align = F.decoder_forward(cfg, memory, target, lens, params)
+        e1.record()
+        if not a.fwd_only:
+            loss = spec.sum() + stop.sum() + (align * align).sum()
+            loss.backward()
+        e2.record()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f'iter {it}: fwd {e0.elapsed_time(e1):.2f} ms  bwd {e1.elapsed_time(e2):.2f} ms  host-enqueue {1e3 * (t1 - t0):.1f} ms '
+              f'wall {1e3 * (t2 - t0):.1f} ms  launches {_lib.launch_count() - n0}  '
+              f'frames/s {a.B * a.T / (t2 - t0):.0f}', flush=True)
+        for p in params:
+            p.grad = None
+        memory.grad = None
+
+
+if __name__ == '__main__':
+    main()
