@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the Tacotron-2 training hot path (forward + loss + backward) -- driver contract.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                    # this framework, 1 GPU
+    torchrun --nproc-per-node N ... bench.py --gpus N ...             # data parallel, one rank per GPU, NCCL all-reduce
+    python bench.py --impl reference --steps 2 --warmup 1             # CPU reference arm (oracle port, host cores)
+
+A "step" is one training step of the named configuration on one synthetic batch per GPU: embedding -> encoder ->
+fused decoder -> postnet -> TacotronLoss -> backward (-> gradient all-reduce when N > 1).  Optimizer, data loading
+and logging are excluded.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'mel-frames/sec (train fwd+bwd)'
+UNIT = 'mel-frames/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='generated_training')
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: 60 for grouped encoders, 64 otherwise)')
+    ap.add_argument('--text-len', type=int, default=180)
+    ap.add_argument('--frames', type=int, default=900)
+    ap.add_argument('--regularization', default='zoneout', choices=['zoneout', 'dropout'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload(a):
+    from multilingual_text_to_speech_b200 import configs
+    hp = configs.apply(a.config, decoder_regularization=a.regularization)
+    G = max(hp.language_number, 1)
+    grouped = hp.encoder_type in ('generated', 'convolutional')
+    B = a.batch or (60 if grouped else 64)      # 64 is not divisible by the 10 / 5 languages of the grouped encoders
+    if grouped and B % G:
+        raise SystemExit(f'batch {B} must be divisible by the {G} languages of the grouped encoder')
+    return hp, B, a.text_len, a.frames
+
+
+def synth_batch(hp, B, L, T, seed, device, pin=False):
+    """Synthetic batch of SURVEY section 8d: random symbols, randn mels, full lengths, language b % G, stop ones on the last frames."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    G = max(hp.language_number, 1)
+    batch = {
+        'text': torch.randint(1, hp.symbols_count() + 3, (B, L), generator=g),
+        'text_length': torch.full((B,), L, dtype=torch.long),
+        'target': torch.randn(B, hp.num_mels, T, generator=g),
+        'target_length': torch.full((B,), T, dtype=torch.long),
+        'stop_target': torch.zeros(B, T),
+    }
+    batch['stop_target'][:, T - hp.stop_frames:] = 1.0
+    if hp.multi_speaker:
+        batch['speakers'] = torch.randint(0, hp.speaker_number, (B,), generator=g)
+    if hp.multi_language:
+        batch['languages'] = torch.arange(B) % G
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device is not None:
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch
+
+
+# --------------------------------------------------------------------------------------------------
+# roofline bookkeeping (SURVEY.md section 8d formula: naive algorithmic bytes of one decoder step, forward)
+# --------------------------------------------------------------------------------------------------
+def bytes_fwd_step(B, L, M, D=1024, P=256, A=128, C=32, K=31, N=80, w=4, a=4):
+    W = (4 * D * (P + M) + 4 * D * D + 8 * D) + (4 * D * (D + M) + 4 * D * D + 8 * D) + (A * D + A * C + C * K + 2 * A) + \
+        (N * (D + M) + N + (D + M) + 1)
+    act = B * ((L * A + L * M + 2 * L + P + 4 * D) + (4 * D + N + 1 + 2 * L))
+    return w * W + a * act
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        if not sm:
+            return None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_frames_per_s(a, steps, warmup, sample_frames=100):
+    import torch
+    from multilingual_text_to_speech_b200 import configs
+    from multilingual_text_to_speech_b200.modules.tacotron2 import Tacotron
+    from oracle import tacotron_oracle as O
+    hp, B, L, _ = workload(a)
+    T = sample_frames
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = Tacotron()                       # parameter container only (construction needs no GPU)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    for k in list(sd):
+        if k.startswith('_decoder._prenet.') or k.startswith('_decoder._attention.'):
+            sd[k] = sd[k[len('_decoder.'):]]
+    ns = configs.as_namespace()
+    b = synth_batch(hp, B, L, T, 1234, None)
+    g = torch.Generator().manual_seed(7)
+    D, P = hp.decoder_dimension, hp.prenet_dimension
+    keep = lambda shape, p: (torch.rand(*shape, generator=g) >= p).float()   # noqa: E731
+    tape = {'teacher': torch.ones(T, dtype=torch.bool), 'prenet0': keep((B, T + 1, P), 0.5), 'prenet1': keep((B, T + 1, P), 0.5),
+            'att_h': keep((T, B, D), 0.1), 'gen_h': keep((T, B, D), 0.1), 'att_c': keep((T, B, D), 0.1), 'gen_c': keep((T, B, D), 0.1)}
+    times = []
+    for it in range(warmup + steps):
+        for v in sd.values():
+            if v.is_floating_point():
+                v.grad = None
+        t0 = time.perf_counter()
+        post, pre, stop, align, spk, enc = O.tacotron_forward(sd, ns, b['text'], b['text_length'], b['target'], b['target_length'],
+                                                              b.get('speakers'), b.get('languages'), tape, training=True)
+        loss, _ = O.tacotron_loss(ns, hp.guided_attention_toleration, b['text_length'], b['target_length'], pre, b['target'], post,
+                                  b['target'], stop, b['stop_target'], align, b.get('speakers'), spk)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    sample = f'oracle port (torch CPU fp32), {a.config} B={B} L={L}, first {T} of {a.frames} frames, fwd+loss+bwd, {steps} timed steps'
+    return B * T / med, med, cores, sample
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    fps, med, cores, sample = cpu_oracle_frames_per_s(a, a.steps, a.warmup)
+    hp, B, L, T = workload(a)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': {'workload': f'{a.config} train fwd+bwd, B={B} L={L} T={T} ({a.regularization} cells)'},
+            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# this framework
+# --------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    entry.build()
+    from multilingual_text_to_speech_b200 import _lib, functional as F
+    from multilingual_text_to_speech_b200.modules.tacotron2 import Tacotron, TacotronLoss
+    from multilingual_text_to_speech_b200.rng import MaskSource
+    from multilingual_text_to_speech_b200.distributed import GradBucket
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device: the hot path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    hp, B, L, T = workload(a)
+    torch.manual_seed(0)
+    model = Tacotron().to(dev).train()
+    crit = TacotronLoss(hp.guided_attention_steps, hp.guided_attention_toleration, hp.guided_attention_gain)
+    bucket = GradBucket(model, world)
+    MaskSource.manual_seed(1234 + rank)
+    host = synth_batch(hp, B, L, T, 1234 + rank, None, pin=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    F.PROFILE.clear()
+
+    def step(batch):
+        bucket.zero()
+        post, pre, stop, align, spk, enc = model(batch['text'], batch['text_length'], batch['target'], batch['target_length'],
+                                                 batch.get('speakers'), batch.get('languages'), hp.teacher_forcing)
+        loss, _ = crit(batch['text_length'], batch['target_length'], pre, batch['target'], post, batch['target'], stop,
+                       batch['stop_target'], align, batch.get('speakers'), spk, enc, None)
+        loss.backward()
+        bucket.allreduce()
+        return loss
+
+    def timed(n, from_host):
+        """n steps bracketed by barrier + synchronize; device time by CUDA events; returns (max-over-ranks ms, last loss)."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss_val = None
+        for _ in range(n):
+            batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if from_host else resident
+            loss = step(batch)
+            if from_host:
+                loss_val = float(loss)            # device -> host read of the step's result
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), loss_val
+
+    for _ in range(max(a.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    F.PROFILE.clear()
+    F.PROFILE['enabled'] = True
+    n0 = _lib.launch_count()
+    ms, _ = timed(a.steps, from_host=False)
+    launches = _lib.launch_count() - n0
+    F.PROFILE['enabled'] = False
+    torch.cuda.synchronize()
+    dec_ms = [s.elapsed_time(e) for s, e in F.PROFILE.get('decoder_fwd', [])]
+    ms_e2e, loss_val = timed(a.steps, from_host=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        frames = world * B * T * a.steps
+        value = frames / (ms * 1e-3)
+        M = hp.encoder_dimension + (hp.speaker_embedding_dimension if hp.multi_speaker else 0) + \
+            (hp.language_embedding_dimension if hp.multi_language else 0)
+        peak, peak_src = measured_peaks()
+        roof = None
+        if dec_ms:
+            alg = T * bytes_fwd_step(B, L, M)
+            dur = statistics.mean(dec_ms) * 1e-3
+            roof = {'bound': 'hbm', 'achieved': alg / dur / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': alg / dur / 1e9 / peak,
+                    'traffic': None, 'kernel': 'decoder forward (b200tts_decoder_forward: attention-LSTM + attention + generator-LSTM '
+                    'loop, all launches)', 'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': dur * 1e3, 'peak_source': peak_src}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
+                'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic',
+                'config': {'workload': f'{a.config} train fwd+bwd, B={B}/GPU L={L} T={T} ({a.regularization} cells), tf=1.0',
+                           'global_batch': world * B, 'parallelism': f'dp{world}',
+                           'l2': 'per-step working set (~5 GB of activations) >> 126 MB L2, no flush needed',
+                           'note': 'batch 64 is invalid for the 10-language grouped encoder (B % G == 0); shipped batch 60 used'},
+                'clocks': clocks, 'gpu_launches': int(launches),
+                'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
+                        'loss': loss_val},
+                'roofline': roof}
+        if world == 1 and not a.no_cpu_baseline:
+            fps, med, cores, sample = cpu_oracle_frames_per_s(a, 1, 0, sample_frames=40)
+            line['cpu_baseline'] = {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == '__main__':
+    main()

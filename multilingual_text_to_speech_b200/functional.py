@@ -12,6 +12,30 @@ from ._lib import (DecoderShape, DecoderParams, DecoderInputs, DecoderOutputs, D
                    DECODER_PARAM_FIELDS, check, ptr)
 
 
+# Optional in-band timing of the dominant ops (bench.py): when PROFILE['enabled'] is set, CUDA events are recorded on
+# the launching stream around the library call and appended as (start, end) pairs under the op's name.
+PROFILE = {}
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.on = bool(PROFILE.get('enabled'))
+        if self.on:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.end.record()
+            PROFILE.setdefault(self.name, []).append((self.start, self.end))
+        return False
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -155,8 +179,9 @@ class DecoderFunction(torch.autograd.Function):
         stop = torch.empty(B, T, device=memory.device, dtype=torch.float32)
         align = torch.empty(B, T, L, device=memory.device, dtype=torch.float32)
         outs = DecoderOutputs(ptr(spec), ptr(stop), ptr(align))
-        check(lib.b200tts_decoder_forward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
-                                          ctypes.byref(outs), ptr(ws), nbytes, _stream()), 'b200tts_decoder_forward')
+        with _Timed('decoder_fwd'):
+            check(lib.b200tts_decoder_forward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
+                                              ctypes.byref(outs), ptr(ws), nbytes, _stream()), 'b200tts_decoder_forward')
         ctx.cfg, ctx.dims, ctx.ws = cfg, dims, ws
         ctx.save_for_backward(memory, target, text_lengths, align, *params)
         ctx.set_materialize_grads(False)
@@ -176,9 +201,10 @@ class DecoderFunction(torch.autograd.Function):
         d_spec, d_stop, d_align = [None if t is None else _f32c(t) for t in (d_spec, d_stop, d_align)]
         douts = DecoderOutputGrads(ptr(d_spec), ptr(d_stop), ptr(d_align))
         fouts = DecoderOutputs(None, None, ptr(align))
-        check(lib.b200tts_decoder_backward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
-                                           ctypes.byref(fouts), ctypes.byref(douts), ptr(ctx.ws), ptr(bws), nbytes,
-                                           ctypes.byref(gstruct), ptr(d_memory), _stream()), 'b200tts_decoder_backward')
+        with _Timed('decoder_bwd'):
+            check(lib.b200tts_decoder_backward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
+                                               ctypes.byref(fouts), ctypes.byref(douts), ptr(ctx.ws), ptr(bws), nbytes,
+                                               ctypes.byref(gstruct), ptr(d_memory), _stream()), 'b200tts_decoder_backward')
         return (None, d_memory, None, None, *grads)
 
 
