@@ -42,6 +42,14 @@ int b200tts_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 unsigned long long b200tts_launch_count(void);
 
+/* Arithmetic mode of every contraction in the library.  FP32: exact fp32 FFMA kernels (parity gate rtol 1e-3 /
+ * atol 1e-4 against the reference).  BF16: operands rounded to bf16, fp32 accumulation on the tensor cores, fp32
+ * master weights / states / outputs (BASELINE.json configs[1] "bf16 fwd / fp32 master"; gate: mel L1 < 1e-3).     */
+#define B200TTS_PRECISION_FP32 0
+#define B200TTS_PRECISION_BF16 1
+int b200tts_set_precision(int mode);
+int b200tts_get_precision(void);
+
 /* ---- generic dense contraction (the time-batched GEMMs of the path) ----------------------- */
 /* C = alpha * op(A) . op(B) + beta * C + bias[n];  op(A)(m,k) = transA ? A[k*lda+m] : A[m*lda+k],
  * op(B)(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n].  Replaces the torch.nn.Linear / cuBLAS call sites

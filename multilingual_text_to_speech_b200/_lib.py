@@ -66,6 +66,8 @@ SIGNATURES = {
     'b200tts_last_error': (c_char_p, []),
     'b200tts_version': (c_int, []),
     'b200tts_launch_count': (c_ulonglong, []),
+    'b200tts_set_precision': (c_int, [c_int]),
+    'b200tts_get_precision': (c_int, []),
     'b200tts_gemm_f32': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float,
                                  c_void_p, c_int, c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_int, c_void_p,
                                  c_void_p]),
@@ -129,6 +131,17 @@ def check(status, what):
 def ptr(t):
     """Device/host pointer of a torch tensor (None -> NULL)."""
     return None if t is None else c_void_p(t.data_ptr())
+
+
+PRECISIONS = {'fp32': 0, 'bf16': 1}
+
+
+def set_precision(name):
+    check(load().b200tts_set_precision(PRECISIONS[name]), 'b200tts_set_precision')
+
+
+def get_precision():
+    return {v: k for k, v in PRECISIONS.items()}[load().b200tts_get_precision()]
 
 
 def launch_count():

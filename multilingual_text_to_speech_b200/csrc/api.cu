@@ -108,6 +108,12 @@ extern "C" {
 const char* b200tts_last_error(void) { return g_error; }
 int b200tts_version(void) { return 100; }
 unsigned long long b200tts_launch_count(void) { return g_launches.load(); }
+int b200tts_set_precision(int mode) {
+    if (mode != B200TTS_PRECISION_FP32 && mode != B200TTS_PRECISION_BF16) { set_last_error("set_precision: unknown mode %d", mode); return B200TTS_ERR_INVALID; }
+    set_precision_mode(mode);
+    return B200TTS_OK;
+}
+int b200tts_get_precision(void) { return precision_mode(); }
 
 int b200tts_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                      int ldb, float beta, float* C, int ldc, const float* bias, int batch, long long strideA,
@@ -117,7 +123,7 @@ int b200tts_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, c
     d.A = A; d.B = B; d.C = C; d.bias = bias; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
     d.transA = transA; d.transB = transB; d.alpha = alpha; d.beta = beta; d.batch = batch < 1 ? 1 : batch;
     d.strideA = strideA; d.strideB = strideB; d.strideC = strideC; d.splitk = splitk < 1 ? 1 : splitk; d.partial = workspace;
-    return gemm_f32(d, (cudaStream_t)stream);
+    return gemm_run(d, (cudaStream_t)stream);
 }
 
 size_t b200tts_decoder_workspace_bytes(const b200tts_decoder_shape* shape) {

@@ -107,6 +107,13 @@ struct GemmDesc {
 };
 
 int gemm_f32(const GemmDesc& d, cudaStream_t stream);
+int gemm_bf16(const GemmDesc& d, cudaStream_t stream);
+// Precision mode of the library (b200tts_set_precision): 0 = fp32-exact (parity mode), 1 = bf16 tensor-core operands.
+int precision_mode();
+void set_precision_mode(int mode);
+// Dispatch on the precision mode.
+int gemm_run(const GemmDesc& d, cudaStream_t stream);
+int gemm_run_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream);
 size_t gemm_partial_elems(const GemmDesc& d);
 int gemm_f32_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream);
 

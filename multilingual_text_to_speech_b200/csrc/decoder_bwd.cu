@@ -500,7 +500,7 @@ int launch_attn_bwd(AttnBwdArgs a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 struct BwdLayout {
     size_t dfs, dhgd, dctxs, dgg, dhas, dga, dq, dctxt, dcum, dc, dhz, dmemT, dWloc_acc, dWc_acc, dv_acc, dp1, dp0, dwfs,
-        part, gpart, total;
+        part, gpart, pextra, total;
     int split_gen, split_att;
     size_t gpart_elems;
 };
@@ -535,6 +535,7 @@ BwdLayout bwd_layout(const b200tts_decoder_shape& s) {
     // scratch for the split-K partials of the long-K weight-gradient GEMMs (only small outputs are split)
     l.gpart_elems = (size_t)6 * 1024 * 1024;
     l.gpart = take(l.gpart_elems);
+    l.pextra = take(persist_bwd_gen_extra_bytes(s) / sizeof(float) + 64);
     l.total = off;
     return l;
 }
@@ -546,7 +547,7 @@ int wgemm(cudaStream_t st, const BwdLayout& l, float* ws, int transA, int transB
     GemmDesc d;
     d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.transA = transA;
     d.transB = transB; d.beta = beta; d.batch = batch; d.strideA = sA; d.strideB = sB; d.strideC = sC;
-    return gemm_f32_auto(d, ws + l.gpart, l.gpart_elems, st);
+    return gemm_run_auto(d, ws + l.gpart, l.gpart_elems, st);
 }
 
 }  // namespace
@@ -600,25 +601,30 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
 
     // ---- 2. generator LSTM reverse loop ----
     const bool zone = s.cell_kind == B200TTS_CELL_ZONEOUT;
+    if (precision_mode() == B200TTS_PRECISION_BF16 && persist_bwd_supported(s)) {
+        // bf16 perf mode: one cooperative weight-stationary kernel for the whole reverse recurrence
+        B200_TRY(persist_gen_bwd_loop(s, w, in, fl, fws, W(l.dhgd), W(l.dgg), reinterpret_cast<unsigned char*>(W(l.pextra)), st));
+    } else {
     for (int i = T - 1; i >= 0; --i) {
-        CellBwdArgs ca{};
-        ca.gates = F(fl.gg) + (size_t)i * B4D;
-        ca.c_prev = F(fl.cg) + (size_t)i * BD;
-        ca.dh_static = W(l.dhgd) + (size_t)i * BD; ca.ld_dhs = D;
-        ca.part = W(l.part); ca.nsplit = l.split_gen; ca.part_stride = BD; ca.ld_part = D; ca.part_col0 = 0;
-        ca.dq = nullptr; ca.Wq = nullptr; ca.A = 0;
-        ca.dc_state = W(l.dc); ca.dhz_state = zone ? W(l.dhz) : nullptr;
-        ca.mask_h = in.mask_gen_h ? in.mask_gen_h + (size_t)i * BD : nullptr;
-        ca.mask_c = in.mask_gen_c ? in.mask_gen_c + (size_t)i * BD : nullptr;
-        ca.kind = s.cell_kind; ca.training = s.training; ca.rate_h = s.rate_h; ca.rate_c = s.rate_c;
-        ca.dgates = W(l.dgg) + (size_t)i * B4D; ca.B = B; ca.D = D; ca.last = (i == T - 1);
-        B200_TRY(launch_cell_bwd(ca, st));
-        if (i > 0) {
-            GemmDesc d;      // d h_gen_{i-1} (recurrent) = dgates_i . W_hh
-            d.A = ca.dgates; d.lda = 4 * D; d.B = w.gen_w_hh; d.ldb = D; d.transB = 0; d.M = B; d.N = D; d.K = 4 * D;
-            d.splitk = l.split_gen; d.partial = W(l.part); d.keep_partials = 1;
-            if (d.splitk == 1) { d.C = W(l.part); d.ldc = D; d.keep_partials = 0; d.partial = nullptr; }
-            B200_TRY(gemm_f32(d, st));
+            CellBwdArgs ca{};
+            ca.gates = F(fl.gg) + (size_t)i * B4D;
+            ca.c_prev = F(fl.cg) + (size_t)i * BD;
+            ca.dh_static = W(l.dhgd) + (size_t)i * BD; ca.ld_dhs = D;
+            ca.part = W(l.part); ca.nsplit = l.split_gen; ca.part_stride = BD; ca.ld_part = D; ca.part_col0 = 0;
+            ca.dq = nullptr; ca.Wq = nullptr; ca.A = 0;
+            ca.dc_state = W(l.dc); ca.dhz_state = zone ? W(l.dhz) : nullptr;
+            ca.mask_h = in.mask_gen_h ? in.mask_gen_h + (size_t)i * BD : nullptr;
+            ca.mask_c = in.mask_gen_c ? in.mask_gen_c + (size_t)i * BD : nullptr;
+            ca.kind = s.cell_kind; ca.training = s.training; ca.rate_h = s.rate_h; ca.rate_c = s.rate_c;
+            ca.dgates = W(l.dgg) + (size_t)i * B4D; ca.B = B; ca.D = D; ca.last = (i == T - 1);
+            B200_TRY(launch_cell_bwd(ca, st));
+            if (i > 0) {
+                GemmDesc d;      // d h_gen_{i-1} (recurrent) = dgates_i . W_hh
+                d.A = ca.dgates; d.lda = 4 * D; d.B = w.gen_w_hh; d.ldb = D; d.transB = 0; d.M = B; d.N = D; d.K = 4 * D;
+                d.splitk = l.split_gen; d.partial = W(l.part); d.keep_partials = 1;
+                if (d.splitk == 1) { d.C = W(l.part); d.ldc = D; d.keep_partials = 0; d.partial = nullptr; }
+                B200_TRY(gemm_run(d, st));
+            }
         }
     }
     // time-batched generator gradients
@@ -673,7 +679,7 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
             d.A = ca.dgates; d.lda = 4 * D; d.B = F(fl.wcat_att); d.ldb = MD; d.transB = 0; d.M = B; d.N = MD; d.K = 4 * D;
             d.splitk = l.split_att; d.partial = W(l.part); d.keep_partials = 1;
             if (d.splitk == 1) { d.C = W(l.part); d.ldc = MD; d.keep_partials = 0; d.partial = nullptr; }
-            B200_TRY(gemm_f32(d, st));
+            B200_TRY(gemm_run(d, st));
         }
     }
 

@@ -393,7 +393,7 @@ int run_gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, cons
     if (keep && splitk == 1) {          // single split: the "partial" buffer simply receives the product
         d.C = partial; d.ldc = N; d.keep_partials = 0; d.partial = nullptr;
     }
-    return gemm_f32(d, st);
+    return gemm_run(d, st);
 }
 
 // prenet of one block of rows (time-batched or a single free-running step)
@@ -524,7 +524,15 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
     B200_TRY(launch_fill(c.at(l.cg), 0.f, BD, st));
     B200_TRY(launch_fill(c.at(l.cum), 0.f, (size_t)B * s.L, st));
 
-    if (!sequential) {
+    const bool persistent = !sequential && precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s);
+    if (persistent) {
+        // bf16 perf mode: one cooperative, weight-stationary kernel per recurrence (decoder_persist.cu)
+        unsigned char* pws = reinterpret_cast<unsigned char*>(c.at(l.persist));
+        B200_TRY(persist_att_loop(s, w, in, l, ws, pws, out.alignments, st));
+        B200_TRY(gen_input_proj(c, 0, T));
+        B200_TRY(persist_gen_loop(s, w, in, l, ws, pws, st));
+        B200_TRY(frame_proj(c, 0, T));
+    } else if (!sequential) {
         for (int i = 0; i < T; ++i) B200_TRY(att_step(c, i, out.alignments));
         B200_TRY(gen_input_proj(c, 0, T));
         for (int i = 0; i < T; ++i) B200_TRY(gen_step(c, i));

@@ -20,6 +20,20 @@ static inline int pick_splitk(int M, int N, int K) {
     return s;
 }
 
+// Extras of the persistent bf16 kernels (decoder_persist.cu); offsets in BYTES from the region base.
+struct PersistLayout {
+    int Kp_att, Kp_gen, ldm;
+    size_t aib;      // bf16 [T+1, B, Kp_att]  [ctx | h_att] operands
+    size_t hgb;      // bf16 [T+1, B, Kp_gen]  h_gen operands
+    size_t memTb;    // bf16 [B, L, A]
+    size_t memb;     // bf16 [B, L, ldm]
+    size_t wcombT;   // f32  [K, A]
+    size_t barrier;  // grid-barrier counter (+ abort flag at +128 B)
+    size_t total;
+};
+PersistLayout persist_layout(const b200tts_decoder_shape& s);
+bool persist_supported(const b200tts_decoder_shape& s);
+
 // All offsets are in floats from the workspace base.
 struct DecoderLayout {
     // saved for backward
@@ -39,8 +53,9 @@ struct DecoderLayout {
     size_t wfs;      // [N+1, D+M] = [frame_w ; stop_w]
     size_t bfs;      // [N+1]
     // scratch
-    size_t qpart;    // [ncell_blocks, B, A]
+    size_t qpart;    // [max(ncell_blocks, D/16), B, A]
     size_t part;     // split-K partials
+    size_t persist;  // byte-addressed extras of the persistent bf16 kernels (PersistLayout), stored as floats
     size_t total;
     int split_att, split_gen, ncell_blocks;
 };
@@ -69,16 +84,26 @@ static inline DecoderLayout decoder_layout(const b200tts_decoder_shape& s) {
     l.wfs = take((N + 1) * (D + M));
     l.bfs = take(N + 1);
     l.ncell_blocks = cdiv(s.D, CELL_UNITS);
-    l.qpart = take((size_t)l.ncell_blocks * B * A);
+    l.qpart = take((size_t)cdiv(s.D, 16) * B * A);
     l.split_att = pick_splitk(s.B, 4 * s.D, s.M + s.D);
     l.split_gen = pick_splitk(s.B, 4 * s.D, s.D);
     const int smax = l.split_att > l.split_gen ? l.split_att : l.split_gen;
     l.part = take((size_t)smax * B * 4 * D);
+    l.persist = take(persist_layout(s).total / sizeof(float) + 64);
     l.total = off;
     return l;
 }
 
 int validate_decoder_shape(const b200tts_decoder_shape& s);
+int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                     const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st);
+bool persist_bwd_supported(const b200tts_decoder_shape& s);
+size_t persist_bwd_gen_extra_bytes(const b200tts_decoder_shape& s);
+int persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                         const DecoderLayout& fl, const float* fws, const float* dh_static, float* dgates, unsigned char* extra,
+                         cudaStream_t st);
+int persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                     const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st);
 
 // ---- LSTM cell kernels (decoder_fwd.cu / decoder_bwd.cu), shared with the encoder bi-LSTM ----
 struct CellFwdArgs {

@@ -1,0 +1,539 @@
+// Persistent recurrent kernels of the bf16 perf mode (forward): ONE cooperative launch per LSTM loop.
+//
+//   * weight-stationary: CTA (rb, bh) keeps the bf16 slice [64 gate rows = 16 hidden units x {i,f,g,o}] x K of the
+//     recurrent weight matrix in shared memory for the whole sequence (169 KB for K = 1312) and owns a batch
+//     half of 32 utterances -> 64 x 2 = 128 CTAs, one per SM;
+//   * per step the bf16 activation operand [32 x K] streams L2 -> shared memory with cp.async in 256-column chunks
+//     (double buffered); the 8 warps split K inside a chunk and feed mma.sync.m16n8k16 from ldmatrix fragments;
+//     a tree reduction over the warps is followed by the LSTM cell / regulariser epilogue in registers;
+//   * attention loop only: after a grid barrier the first B CTAs run the location-sensitive attention of one
+//     utterance each (query from the per-CTA partial projections, warp-shuffle softmax, context), second barrier;
+//   * grid barriers are monotonic counters in global memory (acquire/release, L2-only loads for exchanged data)
+//     with a clock64 watchdog so a protocol bug can never hang the GPU.
+// fp32 state (c, h, gates, cumulative weights, context, alignments) is written exactly where the per-step (v1)
+// path writes it, so the backward pass and the fp32 parity path are unaffected.
+// Reference semantics: modules/tacotron2.py:180-198, modules/layers.py:18-47, modules/attention.py:39-86.
+#include <cuda_bf16.h>
+#include <cooperative_groups.h>
+#include "decoder_internal.cuh"
+
+namespace b200tts {
+
+namespace {
+
+constexpr int PT = 256;             // threads per CTA
+constexpr int UNITS = 16;           // hidden units per CTA
+constexpr int ROWS = 4 * UNITS;     // gate rows per CTA
+constexpr int BT = 32;              // utterances per CTA
+constexpr int CHUNK = 256;          // activation columns per cp.async stage
+constexpr int ALD = CHUNK + 8;      // bf16 row stride of an activation stage
+
+struct LoopArgs {
+    int B, T, D, K, Kp, RB, NBH;
+    const float* W; int ldw;                  // recurrent weights fp32 [4D, ldw]
+    __nv_bfloat16* actb;                      // [T+1, B, Kp] bf16 operand of step i in row i
+    float* actf; int ldf; int hcol;           // fp32 mirror ([T+1, B, ldf]); h lives at column hcol
+    float* gates;                             // [T, B, 4D] in: input projection (+biases); out: activated gates
+    float* cstate;                            // [T+1, B, D]
+    const uint8_t* mask_h; const uint8_t* mask_c;   // [T, B, D] or null
+    int kind, training; float rate_h, rate_c;
+    // attention (ATT instantiation only)
+    int L, M, A, KC;
+    const float* Wq;                          // [A, D]
+    float* qpart;                             // [RB, B, A]
+    float* qsave;                             // [T, B, A]
+    const float* WcombT;                      // [KC, A]  (Wloc . Wc)^T
+    const float* bias; const float* v;        // [A]
+    const __nv_bfloat16* memTb;               // [B, L, A]
+    const __nv_bfloat16* memb; int ldm;       // [B, L, ldm]
+    const int* lengths;
+    float* cum;                               // [T+1, B, L]
+    float* align; long long align_bstride;    // [B, T, L]
+    unsigned* barrier; int* abort_flag;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Monotonic-counter grid barrier.  Returns false if the watchdog fired (caller must leave the loop).
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag) {
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        int ok = 1;
+        const long long t0 = clock64();
+        while (ld_acquire(counter) < target) {
+            if (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag)) { ok = 0; *abort_flag = 1; break; }
+        }
+        __threadfence();
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+struct Smem {
+    __nv_bfloat16* W;      // [ROWS][Kp + 8]
+    __nv_bfloat16* act;    // [2][BT][ALD]   (aliased by the reduction scratch and the attention scratch)
+    float* wq;             // [A][UNITS + 1]
+    float* hs;             // [BT][UNITS + 1]
+    float* sum;            // [BT][ROWS + 1]
+};
+
+template <bool ATT>
+__global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const int rb = cta % p.RB, bh = cta / p.RB;
+    const int u0 = rb * UNITS, b0 = bh * BT;
+    const int Kp = p.Kp, WLD = Kp + 8, D = p.D, B = p.B;
+    const unsigned nblocks = gridDim.x;
+
+    Smem s;
+    size_t off = 0;
+    s.W = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += (size_t)ROWS * WLD * 2;
+    s.act = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += (size_t)2 * BT * ALD * 2;
+    s.sum = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (ROWS + 1) * 4;
+    s.hs = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (UNITS + 1) * 4;
+    s.wq = reinterpret_cast<float*>(smem_raw + off);
+    float* scratch = reinterpret_cast<float*>(s.act);          // 2*BT*ALD*2 B = 33,792 B = 8448 floats
+
+    // ---- one-time: resident weight slice (fp32 -> bf16), query-projection slice ----
+    for (int idx = tid; idx < ROWS * Kp; idx += PT) {
+        const int r = idx / Kp, k = idx % Kp;
+        const int g = r / UNITS, u = r % UNITS;
+        float w = 0.f;
+        if (k < p.K && u0 + u < D) w = p.W[(size_t)(g * D + u0 + u) * p.ldw + k];
+        s.W[r * WLD + k] = __float2bfloat16_rn(w);
+    }
+    if (ATT) {
+        for (int idx = tid; idx < p.A * UNITS; idx += PT) {
+            const int a = idx / UNITS, u = idx % UNITS;
+            s.wq[a * (UNITS + 1) + u] = (u0 + u < D) ? p.Wq[(size_t)a * D + u0 + u] : 0.f;
+        }
+    }
+    __syncthreads();
+
+    const int nchunks = (Kp + CHUNK - 1) / CHUNK;
+    const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
+    unsigned target = 0;
+
+    for (int i = 0; i < p.T; ++i) {
+        // =================== gate GEMM: acc[b, r] = sum_k act[b, k] * W[r, k] ===================
+        float acc[2][8][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+
+        const __nv_bfloat16* arow = p.actb + ((size_t)i * B + b0) * Kp;
+        auto issue = [&](int c) {
+            __nv_bfloat16* dst = s.act + (size_t)(c & 1) * BT * ALD;
+            const int kbase = c * CHUNK;
+            const int segs = min(CHUNK, Kp - kbase) / 8;            // 16-byte segments per row in this chunk
+            for (int idx = tid; idx < BT * segs; idx += PT) {
+                const int r = idx / segs, sg = idx % segs;
+                __nv_bfloat16* d = dst + r * ALD + sg * 8;
+                if (b0 + r < B) cp_async16(d, arow + (size_t)r * Kp + kbase + sg * 8);
+                else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        if (nchunks > 1) issue(1);
+        for (int c = 0; c < nchunks; ++c) {
+            if (c + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();
+            const __nv_bfloat16* ab = s.act + (size_t)(c & 1) * BT * ALD;
+            const int kbase = c * CHUNK;
+            const int ksteps = min(CHUNK, Kp - kbase) / 16;
+            for (int ks = warp; ks < ksteps; ks += 8) {
+                const int kk = ks * 16;
+                uint32_t af[2][4], bf[4][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+                    ldmatrix_x4(af[mt][0], af[mt][1], af[mt][2], af[mt][3], ab + (mt * 16 + (lane & 15)) * ALD + kk + (lane >> 4) * 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    ldmatrix_x4(bf[j][0], bf[j][1], bf[j][2], bf[j][3],
+                                s.W + (size_t)(j * 16 + (lane & 7) + ((lane >> 4) << 3)) * WLD + kbase + kk + ((lane >> 3) & 1) * 8);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) mma_bf16(acc[mt][nt], af[mt], bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
+            }
+            __syncthreads();
+            if (c + 2 < nchunks) issue(c + 2);
+        }
+
+        // =================== tree reduction over the 8 warps (K split) ===================
+        // accumulator element (mt, nt, e): b = mt*16 + g + 8*(e>>1), r = nt*8 + 2*tq + (e&1)
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int half = 4; half >= 1; half >>= 1) {
+            if (warp >= half && warp < 2 * half) {
+                float* dst = scratch + (size_t)(warp - half) * (BT * ROWS);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) dst[((mt * 8 + nt) * 4 + e) * 32 + lane] = acc[mt][nt][e];
+            }
+            __syncthreads();
+            if (warp < half) {
+                const float* src = scratch + (size_t)warp * (BT * ROWS);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[mt][nt][e] += src[((mt * 8 + nt) * 4 + e) * 32 + lane];
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        s.sum[(mt * 16 + g + 8 * (e >> 1)) * (ROWS + 1) + nt * 8 + 2 * tq + (e & 1)] = acc[mt][nt][e];
+        }
+        __syncthreads();
+
+        // =================== LSTM cell + regulariser (2 (b, u) pairs per thread) ===================
+        for (int idx = tid; idx < BT * UNITS; idx += PT) {
+            const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
+            float hs = 0.f;
+            if (b < B && u < D) {
+                const size_t g0 = ((size_t)i * B + b) * 4 * D + u;
+                const float zi = p.gates[g0] + s.sum[bl * (ROWS + 1) + uu];
+                const float zf = p.gates[g0 + D] + s.sum[bl * (ROWS + 1) + UNITS + uu];
+                const float zg = p.gates[g0 + 2 * D] + s.sum[bl * (ROWS + 1) + 2 * UNITS + uu];
+                const float zo = p.gates[g0 + 3 * D] + s.sum[bl * (ROWS + 1) + 3 * UNITS + uu];
+                const float gi = sigmoidf_acc(zi), gf = sigmoidf_acc(zf), gg = tanhf(zg), go = sigmoidf_acc(zo);
+                const size_t bu = (size_t)b * D + u;
+                const float cp = p.cstate[(size_t)i * B * D + bu];
+                float cn = gf * cp + gi * gg;
+                float hn = go * tanhf(cn);
+                p.gates[g0] = gi; p.gates[g0 + D] = gf; p.gates[g0 + 2 * D] = gg; p.gates[g0 + 3 * D] = go;
+                const size_t mi = (size_t)i * B * D + bu;
+                if (p.kind == B200TTS_CELL_ZONEOUT) {
+                    const float hp = p.actf[((size_t)i * B + b) * p.ldf + p.hcol + u];
+                    if (p.training) {
+                        float dh = hn - hp, dc = cn - cp;
+                        if (p.mask_h) dh = dh * (float)p.mask_h[mi] * inv_h;
+                        if (p.mask_c) dc = dc * (float)p.mask_c[mi] * inv_c;
+                        hn = (1.f - p.rate_h) * dh + hp;
+                        cn = (1.f - p.rate_c) * dc + cp;
+                    } else {
+                        hn = p.rate_h * hp + (1.f - p.rate_h) * hn;
+                        cn = p.rate_c * cp + (1.f - p.rate_c) * cn;
+                    }
+                } else if (p.training && p.mask_h) {
+                    hn = hn * (float)p.mask_h[mi] * inv_h;
+                }
+                p.cstate[(size_t)(i + 1) * B * D + bu] = cn;
+                p.actf[((size_t)(i + 1) * B + b) * p.ldf + p.hcol + u] = hn;
+                p.actb[((size_t)(i + 1) * B + b) * Kp + p.hcol + u] = __float2bfloat16_rn(hn);
+                hs = hn;
+            }
+            if (ATT) s.hs[bl * (UNITS + 1) + uu] = hs;
+        }
+
+        if (ATT) {
+            __syncthreads();
+            // partial query projection of this CTA's 16 hidden units: qpart[rb, b, a]
+            for (int idx = tid; idx < BT * p.A; idx += PT) {
+                const int bl = idx / p.A, a = idx % p.A;
+                if (b0 + bl < B) {
+                    float q = 0.f;
+#pragma unroll
+                    for (int uu = 0; uu < UNITS; ++uu) q = fmaf(s.hs[bl * (UNITS + 1) + uu], s.wq[a * (UNITS + 1) + uu], q);
+                    p.qpart[((size_t)rb * B + b0 + bl) * p.A + a] = q;
+                }
+            }
+        }
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+
+        if (ATT) {
+            // =================== attention of utterance `cta` (CTAs 0 .. B-1) ===================
+            if (cta < B) {
+                const int b = cta, L = p.L, A = p.A, M = p.M, KC = p.KC, half = (KC - 1) / 2;
+                float* qb = scratch;                       // [A]
+                float* vv = qb + A;                        // [A]
+                float* cump = vv + A;                      // [L + KC - 1] (+3)
+                float* WcT = cump + ((L + KC - 1 + 3) & ~3);   // [KC][A]
+                float* e = WcT + KC * A;                   // [L] (+3)
+                float* red = e + ((L + 3) & ~3);           // [64]
+                float* cred = red + 64;                    // [8][M]
+                int len = p.lengths[b];
+                len = len < 0 ? 0 : (len > L ? L : len);
+                for (int a = tid; a < A; a += PT) {
+                    float q = 0.f;
+                    for (int r = 0; r < p.RB; ++r) q += __ldcg(p.qpart + ((size_t)r * B + b) * A + a);
+                    p.qsave[((size_t)i * B + b) * A + a] = q;
+                    qb[a] = q + p.bias[a];
+                    vv[a] = p.v[a];
+                }
+                const float* cum_prev = p.cum + ((size_t)i * B + b) * L;
+                for (int j = tid; j < L + KC - 1; j += PT) {
+                    const int l = j - half;
+                    cump[j] = (l >= 0 && l < L) ? __ldcg(cum_prev + l) : 0.f;
+                }
+                for (int idx = tid; idx < KC * A; idx += PT) WcT[idx] = p.WcombT[idx];
+                __syncthreads();
+                // energies: warp = 4 consecutive positions, lane = attention dims lane + 32 j
+                for (int l0 = warp * 4; l0 < len; l0 += 32) {
+                    float sacc[4][4];
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sacc[ii][j] = 0.f;
+                    float c0 = cump[l0], c1 = cump[l0 + 1], c2 = cump[l0 + 2];
+                    for (int k = 0; k < KC; ++k) {
+                        const float c3 = cump[min(l0 + k + 3, L + KC - 2)];
+                        float w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) w[j] = (lane + 32 * j < A) ? WcT[k * A + lane + 32 * j] : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            sacc[0][j] = fmaf(c0, w[j], sacc[0][j]); sacc[1][j] = fmaf(c1, w[j], sacc[1][j]);
+                            sacc[2][j] = fmaf(c2, w[j], sacc[2][j]); sacc[3][j] = fmaf(c3, w[j], sacc[3][j]);
+                        }
+                        c0 = c1; c1 = c2; c2 = c3;
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int l = l0 + ii;
+                        if (l < len) {
+                            float ep = 0.f;
+                            const __nv_bfloat16* mt = p.memTb + ((size_t)b * L + l) * A;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int a = lane + 32 * j;
+                                if (a < A) ep = fmaf(vv[a], tanhf(sacc[ii][j] + qb[a] + __bfloat162float(mt[a])), ep);
+                            }
+                            ep = warp_sum(ep);
+                            if (lane == 0) e[l] = ep;
+                        }
+                    }
+                }
+                __syncthreads();
+                float mx = -INFINITY;
+                for (int l = tid; l < len; l += PT) mx = fmaxf(mx, e[l]);
+                mx = block_max(mx, red);
+                float sum = 0.f;
+                for (int l = tid; l < len; l += PT) { const float ex = expf(e[l] - mx); e[l] = ex; sum += ex; }
+                sum = block_sum(sum, red);
+                float* cum_next = p.cum + ((size_t)(i + 1) * B + b) * L;
+                for (int l = tid; l < L; l += PT) {
+                    const float w = l < len ? e[l] / sum : 0.f;
+                    e[l] = w;
+                    p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
+                    cum_next[l] = cump[l + half] + w;
+                }
+                __syncthreads();
+                // context: warp per position, lanes over pairs of memory columns
+                float cacc[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cacc[j] = 0.f;
+                for (int l = warp; l < len; l += 8) {
+                    const float w = e[l];
+                    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + l) * p.ldm);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int m2 = lane + 32 * j;
+                        if (2 * m2 < M) {
+                            const float2 v2 = __bfloat1622float2(row[m2]);
+                            cacc[2 * j] = fmaf(w, v2.x, cacc[2 * j]);
+                            cacc[2 * j + 1] = fmaf(w, v2.y, cacc[2 * j + 1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m2 = lane + 32 * j;
+                    if (2 * m2 < M) { cred[warp * M + 2 * m2] = cacc[2 * j]; if (2 * m2 + 1 < M) cred[warp * M + 2 * m2 + 1] = cacc[2 * j + 1]; }
+                }
+                __syncthreads();
+                for (int m = tid; m < M; m += PT) {
+                    float sctx = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) sctx += cred[w8 * M + m];
+                    p.actf[((size_t)(i + 1) * B + b) * p.ldf + m] = sctx;
+                    p.actb[((size_t)(i + 1) * B + b) * Kp + m] = __float2bfloat16_rn(sctx);
+                }
+            }
+            if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        }
+    }
+}
+
+size_t loop_smem_bytes(int Kp, int A, bool att, int L, int M, int KC) {
+    size_t b = (size_t)ROWS * (Kp + 8) * 2 + (size_t)2 * BT * ALD * 2 + (size_t)BT * (ROWS + 1) * 4 + (size_t)BT * (UNITS + 1) * 4;
+    if (att) {
+        b += (size_t)A * (UNITS + 1) * 4;
+        // the attention scratch aliases the activation stages; it must fit there
+        const size_t need = ((size_t)2 * A + ((L + KC - 1 + 3) & ~3) + (size_t)KC * A + ((L + 3) & ~3) + 64 + (size_t)8 * M) * 4;
+        if (need > (size_t)2 * BT * ALD * 2) return 0;
+    }
+    return b;
+}
+
+__global__ void f32_to_bf16_rows_kernel(__nv_bfloat16* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, size_t rows,
+                                        int cols) {
+    const size_t total = rows * ldd;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / ldd;
+        const int c = idx % ldd;
+        dst[idx] = __float2bfloat16_rn(c < cols ? src[r * lds + c] : 0.f);
+    }
+}
+
+// WcombT[k, a] = sum_c Wloc[a, c] * Wc[c, k]
+__global__ void wcomb_kernel(float* __restrict__ WcombT, const float* __restrict__ Wloc, const float* __restrict__ Wc, int A, int C, int K) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * A) return;
+    const int k = idx / A, a = idx % A;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(Wloc[a * C + c], Wc[c * K + k], s);
+    WcombT[idx] = s;
+}
+
+inline int grid_for(size_t n) {
+    size_t g = (n + 255) / 256;
+    return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+PersistLayout persist_layout(const b200tts_decoder_shape& s) {
+    PersistLayout l;
+    size_t off = 0;     // in bytes, 256-aligned regions
+    auto take = [&](size_t n) { size_t o = off; off = (off + n + 255) / 256 * 256; return o; };
+    const size_t T = s.T, B = s.B;
+    l.Kp_att = (s.M + s.D + 15) / 16 * 16;
+    l.Kp_gen = (s.D + 15) / 16 * 16;
+    l.ldm = (s.M + 7) / 8 * 8;
+    l.aib = take((T + 1) * B * l.Kp_att * 2);
+    l.hgb = take((T + 1) * B * l.Kp_gen * 2);
+    l.memTb = take(B * (size_t)s.L * s.A * 2);
+    l.memb = take(B * (size_t)s.L * l.ldm * 2);
+    l.wcombT = take((size_t)s.K * s.A * 4);
+    l.barrier = take(256);
+    l.total = off;
+    return l;
+}
+
+bool persist_supported(const b200tts_decoder_shape& s) {
+    if (s.D % UNITS != 0) return false;
+    const int RB = s.D / UNITS, NBH = (s.B + BT - 1) / BT;
+    if (RB * NBH > 148 || s.B > RB * NBH) return false;
+    const PersistLayout l = persist_layout(s);
+    const size_t a = loop_smem_bytes(l.Kp_att, s.A, true, s.L, s.M, s.K), g = loop_smem_bytes(l.Kp_gen, s.A, false, 0, 0, 0);
+    return a != 0 && a <= 227 * 1024 && g <= 227 * 1024;
+}
+
+static int launch_loop(bool att, const LoopArgs& a, size_t smem, cudaStream_t st) {
+    void* fn = att ? (void*)lstm_loop_kernel<true> : (void*)lstm_loop_kernel<false>;
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
+    int dev = 0, sms = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = a.RB * a.NBH;
+    B200_REQUIRE(per_sm * sms >= grid, "persistent loop: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, sms);
+    LoopArgs args = a;
+    void* params[] = {&args};
+    B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+
+// Attention-LSTM + attention loop (all T steps).  Expects: ga = input projection, ai row 0 = 0, ca row 0 = 0, cum row 0 = 0.
+int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                     const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st) {
+    const PersistLayout l = persist_layout(s);
+    const int B = s.B, T = s.T, D = s.D, M = s.M, MD = M + D;
+    __nv_bfloat16* aib = reinterpret_cast<__nv_bfloat16*>(pws + l.aib);
+    __nv_bfloat16* memTb = reinterpret_cast<__nv_bfloat16*>(pws + l.memTb);
+    __nv_bfloat16* memb = reinterpret_cast<__nv_bfloat16*>(pws + l.memb);
+    float* wcombT = reinterpret_cast<float*>(pws + l.wcombT);
+    unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
+    B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)B * l.Kp_att * 2, st));                 // operand of step 0
+    B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
+    f32_to_bf16_rows_kernel<<<grid_for((size_t)B * s.L * s.A), 256, 0, st>>>(memTb, s.A, ws + fl.memT, s.A, (size_t)B * s.L, s.A);
+    B200_LAUNCH_CHECK();
+    f32_to_bf16_rows_kernel<<<grid_for((size_t)B * s.L * l.ldm), 256, 0, st>>>(memb, l.ldm, in.memory, M, (size_t)B * s.L, M);
+    B200_LAUNCH_CHECK();
+    wcomb_kernel<<<cdiv(s.K * s.A, 256), 256, 0, st>>>(wcombT, w.attn_location, w.attn_loc_features, s.A, s.C, s.K);
+    B200_LAUNCH_CHECK();
+    // padding columns [MD, Kp) of every operand row must be zero (weights there are zero too, but NaN * 0 would poison)
+    if (l.Kp_att != MD) B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)(T + 1) * B * l.Kp_att * 2, st));
+    LoopArgs a{};
+    a.B = B; a.T = T; a.D = D; a.K = MD; a.Kp = l.Kp_att; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
+    a.W = ws + fl.wcat_att; a.ldw = MD;
+    a.actb = aib; a.actf = ws + fl.ai; a.ldf = MD; a.hcol = M;
+    a.gates = ws + fl.ga; a.cstate = ws + fl.ca;
+    a.mask_h = in.mask_att_h; a.mask_c = in.mask_att_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
+    a.L = s.L; a.M = M; a.A = s.A; a.KC = s.K;
+    a.Wq = w.attn_query; a.qpart = ws + fl.qpart; a.qsave = ws + fl.q; a.WcombT = wcombT; a.bias = w.attn_bias; a.v = w.attn_energy;
+    a.memTb = memTb; a.memb = memb; a.ldm = l.ldm; a.lengths = in.text_lengths; a.cum = ws + fl.cum;
+    a.align = align; a.align_bstride = (long long)T * s.L;
+    a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
+    return launch_loop(true, a, loop_smem_bytes(l.Kp_att, s.A, true, s.L, M, s.K), st);
+}
+
+// Generator-LSTM loop.  Expects: gg = input projection, hg row 0 = 0, cg row 0 = 0.
+int persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                     const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st) {
+    const PersistLayout l = persist_layout(s);
+    const int B = s.B, T = s.T, D = s.D;
+    __nv_bfloat16* hgb = reinterpret_cast<__nv_bfloat16*>(pws + l.hgb);
+    unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
+    B200_CUDA(cudaMemsetAsync(hgb, 0, (size_t)(l.Kp_gen != D ? (size_t)(T + 1) : 1) * B * l.Kp_gen * 2, st));
+    B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
+    LoopArgs a{};
+    a.B = B; a.T = T; a.D = D; a.K = D; a.Kp = l.Kp_gen; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
+    a.W = w.gen_w_hh; a.ldw = D;
+    a.actb = hgb; a.actf = ws + fl.hg; a.ldf = D; a.hcol = 0;
+    a.gates = ws + fl.gg; a.cstate = ws + fl.cg;
+    a.mask_h = in.mask_gen_h; a.mask_c = in.mask_gen_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
+    a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
+    return launch_loop(false, a, loop_smem_bytes(l.Kp_gen, s.A, false, 0, 0, 0), st);
+}
+
+}  // namespace b200tts

@@ -279,7 +279,7 @@ int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, con
     g.B = col; g.ldb = s.L; g.transB = 0; g.strideB = (long long)s.Cin * s.k * s.L;
     g.C = conv; g.ldc = s.L; g.strideC = (long long)s.Cout * s.L;
     g.M = s.Cout; g.N = s.L; g.K = s.Cin * s.k; g.batch = s.NB * s.G;
-    B200_TRY(gemm_f32(g, st));
+    B200_TRY(gemm_run(g, st));
     if (s.training) {
         bn_stats_kernel<<<(int)d.Ct, 128, 0, st>>>(conv, mean, invstd, running_mean, running_var, s.NB, (int)d.Ct, s.L, s.eps, s.momentum);
     } else {
@@ -333,7 +333,7 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
             g.B = colr + (size_t)q * s.G * R * s.L; g.ldb = s.L; g.transB = 1; g.strideB = (long long)R * s.L;
             g.C = dweight; g.ldc = R; g.strideC = (long long)s.Cout * R; g.beta = 1.f;
             g.M = s.Cout; g.N = R; g.K = s.L; g.batch = s.G;
-            B200_TRY(gemm_f32(g, st));
+            B200_TRY(gemm_run(g, st));
         }
     }
     if (dx) {
@@ -343,10 +343,10 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
         g.M = R; g.N = s.L; g.K = s.Cout; g.batch = s.NB * s.G;
         if (s.k == 1) {
             g.C = dx; g.ldc = s.L; g.strideC = (long long)s.Cin * s.L; g.beta = s.highway ? 1.f : 0.f;
-            B200_TRY(gemm_f32(g, st));
+            B200_TRY(gemm_run(g, st));
         } else {
             g.C = dcol; g.ldc = s.L; g.strideC = (long long)R * s.L;
-            B200_TRY(gemm_f32(g, st));
+            B200_TRY(gemm_run(g, st));
             col2im1d_kernel<<<grid_for((size_t)s.NB * s.G * s.Cin * s.L), 256, 0, st>>>(dx, dcol, (size_t)s.NB * s.G, s.Cin, s.L, s.k,
                                                                                        s.dilation, d.pad, s.highway);
             B200_LAUNCH_CHECK();

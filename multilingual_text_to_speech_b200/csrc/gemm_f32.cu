@@ -256,10 +256,23 @@ int gemm_f32(const GemmDesc& d, cudaStream_t stream) {
 }
 
 
+static int g_precision = 0;
+int precision_mode() { return g_precision; }
+void set_precision_mode(int mode) { g_precision = mode ? 1 : 0; }
+int gemm_run(const GemmDesc& d, cudaStream_t stream) { return g_precision ? gemm_bf16(d, stream) : gemm_f32(d, stream); }
+
+static int gemm_auto_impl(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream, bool bf16);
+int gemm_f32_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream) {
+    return gemm_auto_impl(d, scratch, scratch_elems, stream, false);
+}
+int gemm_run_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream) {
+    return gemm_auto_impl(d, scratch, scratch_elems, stream, g_precision != 0);
+}
+
 // Picks a split-K factor so that small-output / long-K products still fill the 148 SMs, bounded by the
 // scratch the caller provides for the partial sums.
-int gemm_f32_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream) {
-    const bool big = d.M > 64 && d.N > 64;
+static int gemm_auto_impl(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream, bool bf16) {
+    const bool big = bf16 || (d.M > 64 && d.N > 64);
     const long long tiles = (long long)(big ? cdiv(d.M, 128) * cdiv(d.N, 128) : cdiv(d.M, 64) * cdiv(d.N, 64)) * d.batch;
     int s = 1;
     if (tiles < 148 && scratch) {
@@ -273,7 +286,7 @@ int gemm_f32_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t
     d.splitk = s;
     d.partial = s > 1 ? scratch : nullptr;
     d.keep_partials = 0;
-    return gemm_f32(d, stream);
+    return bf16 ? gemm_bf16(d, stream) : gemm_f32(d, stream);
 }
 
 }  // namespace b200tts

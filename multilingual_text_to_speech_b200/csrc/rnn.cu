@@ -102,7 +102,7 @@ int bilstm_forward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_para
         GemmDesc g;
         g.A = saved + l.xp + (size_t)dir * L * B * E; g.lda = E; g.B = w_ih; g.ldb = E; g.transB = 1; g.C = gates; g.ldc = 4 * H;
         g.bias = bsum; g.M = L * B; g.N = 4 * H; g.K = E;
-        B200_TRY(gemm_f32(g, st));
+        B200_TRY(gemm_run(g, st));
         B200_TRY(launch_fill(hs, 0.f, BH, st));
         B200_TRY(launch_fill(cs, 0.f, BH, st));
         for (int j = 0; j < L; ++j) {
@@ -111,7 +111,7 @@ int bilstm_forward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_para
             r.A = hs + (size_t)j * BH; r.lda = H; r.B = w_hh; r.ldb = H; r.transB = 1; r.M = B; r.N = 4 * H; r.K = H;
             r.splitk = l.split; r.partial = ws + l.part; r.keep_partials = 1;
             if (r.splitk == 1) { r.C = ws + l.part; r.ldc = 4 * H; r.keep_partials = 0; r.partial = nullptr; }
-            B200_TRY(gemm_f32(r, st));
+            B200_TRY(gemm_run(r, st));
             CellFwdArgs ca{};
             ca.xproj = gates + (size_t)j * B4H; ca.gates = gates + (size_t)j * B4H;
             ca.part = ws + l.part; ca.nsplit = l.split; ca.part_stride = B4H;
@@ -154,23 +154,23 @@ int bilstm_backward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_par
                 r.A = ca.dgates; r.lda = 4 * H; r.B = w_hh; r.ldb = H; r.transB = 0; r.M = B; r.N = H; r.K = 4 * H;
                 r.splitk = l.split_b; r.partial = ws + l.part; r.keep_partials = 1;
                 if (r.splitk == 1) { r.C = ws + l.part; r.ldc = H; r.keep_partials = 0; r.partial = nullptr; }
-                B200_TRY(gemm_f32(r, st));
+                B200_TRY(gemm_run(r, st));
             }
         }
         const float* xp = saved + l.xp + (size_t)dir * L * B * E;
         GemmDesc a;   // dW_ih += dg^T . x
         a.A = dg; a.lda = 4 * H; a.transA = 1; a.B = xp; a.ldb = E; a.C = dw_ih; a.ldc = E; a.beta = 1.f; a.M = 4 * H; a.N = E; a.K = L * B;
-        B200_TRY(gemm_f32_auto(a, ws + l.scratch, (size_t)2 * 1024 * 1024, st));
+        B200_TRY(gemm_run_auto(a, ws + l.scratch, (size_t)2 * 1024 * 1024, st));
         GemmDesc b;   // dW_hh += dg^T . h_prev
         b.A = dg; b.lda = 4 * H; b.transA = 1; b.B = hs; b.ldb = H; b.C = dw_hh; b.ldc = H; b.beta = 1.f; b.M = 4 * H; b.N = H; b.K = L * B;
-        B200_TRY(gemm_f32_auto(b, ws + l.scratch, (size_t)2 * 1024 * 1024, st));
+        B200_TRY(gemm_run_auto(b, ws + l.scratch, (size_t)2 * 1024 * 1024, st));
         dim3 blk(32, 8);
         colsum_add2_kernel<<<cdiv(4 * H, 32), blk, 0, st>>>(db_ih, db_hh, dg, (size_t)L * B, 4 * H);
         B200_LAUNCH_CHECK();
         GemmDesc c;   // dx (processing order) = dg . W_ih
         c.A = dg; c.lda = 4 * H; c.B = w_ih; c.ldb = E; c.transB = 0; c.C = ws + l.dxp + (size_t)dir * L * B * E; c.ldc = E;
         c.M = L * B; c.N = E; c.K = 4 * H;
-        B200_TRY(gemm_f32(c, st));
+        B200_TRY(gemm_run(c, st));
     }
     if (dx) {
         from_processing_order_kernel<<<grid_for((size_t)L * B * E), 256, 0, st>>>(dx, ws + l.dxp, B, L, E);

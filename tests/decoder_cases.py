@@ -138,6 +138,49 @@ def _cuda_inputs(c, device):
     return cfg, params, memory
 
 
+def run_case_bf16(c, check_grads=True, verbose=False):
+    """bf16 perf mode (tensor-core operands, fp32 state): gate = mel L1 < 1e-3 against the fp64 oracle (north_star)."""
+    from multilingual_text_to_speech_b200 import functional as F, _lib
+    device = torch.device('cuda:0')
+    cfg, params, memory = _cuda_inputs(c, device)
+    _lib.set_precision('bf16')
+    try:
+        spec, stop, align = F.decoder_forward(cfg, memory, c.target.to(device), c.lengths.to(device), params)
+        torch.cuda.synchronize()
+        with_grad = check_grads and bool(c.tape['teacher'].all())
+        sd, mem_o, spec_o, stop_o, align_o = _oracle_run(c, torch.float64, with_grad)
+        report = {}
+        for name, got, ref in (('spec', spec, spec_o), ('stop', stop, stop_o), ('align', align, align_o)):
+            d = (got.detach().cpu().double() - ref.detach()).abs()
+            report[name + '_l1'], report[name + '_max'] = float(d.mean()), float(d.max())
+        assert torch.isfinite(spec).all() and torch.isfinite(align).all()
+        assert report['spec_l1'] < 1e-3, report
+        assert report['align_l1'] < 1e-3, report
+        agree = float((align.detach().cpu().argmax(2) == align_o.detach().argmax(2)).float().mean())
+        report['argmax_agree'] = agree
+        assert agree > 0.97, report
+        if with_grad:
+            g = torch.Generator().manual_seed(99)
+            r_spec = torch.randn(spec_o.shape, generator=g, dtype=torch.float64)
+            r_stop = torch.randn(stop_o.shape, generator=g, dtype=torch.float64)
+            r_align = torch.randn(align_o.shape, generator=g, dtype=torch.float64)
+            ((spec_o * r_spec).sum() + (stop_o * r_stop).sum() + (align_o * r_align).sum()).backward()
+            ((spec * r_spec.float().to(device)).sum() + (stop * r_stop.float().to(device)).sum() +
+             (align * r_align.float().to(device)).sum()).backward()
+            torch.cuda.synchronize()
+            pairs = [('memory', memory.grad, mem_o.grad)] + [(f, p.grad, sd[k].grad) for (f, k), p in zip(PARAM_KEYS, params)]
+            for name, got, ref in pairs:
+                ref = ref if ref is not None else torch.zeros_like(got.cpu().double())
+                rel = float((got.detach().cpu().double() - ref).norm() / (ref.norm() + 1e-12))
+                report['d_' + name] = rel
+                assert rel < 0.08, (c.name, name, rel)
+    finally:
+        _lib.set_precision('fp32')
+    if verbose:
+        print(c.name, '[bf16]', {k: f'{v:.2e}' for k, v in report.items()})
+    return report
+
+
 def run_case(c, check_grads=True, verbose=False, rtol=1e-3, atol=1e-4):
     """Run the CUDA decoder on `c`, compare with the fp64 oracle.  Returns a dict of max abs differences."""
     from multilingual_text_to_speech_b200 import functional as F

@@ -110,3 +110,36 @@ def test_decoder_baseline_shape_properties():
     with torch.no_grad():
         s3, _, a3 = F.decoder_forward(cfg, memory, tgt.to(dev), c.lengths.to(dev), params)
     assert torch.equal(s1[:, :60], s3[:, :60]) and torch.equal(a1[:, :60], a3[:, :60])
+
+
+@pytest.mark.parametrize('M,N,K,ta,tb,splitk', [
+    (300, 260, 513, False, True, 1), (256, 4096, 1312, False, True, 1), (81, 1024, 2000, True, False, 4),
+    (4096, 288, 640, True, False, 3), (65, 65, 65, False, False, 2), (130, 77, 40, True, True, 1), (1, 7, 3, False, True, 1),
+])
+def test_gemm_bf16_mode(M, N, K, ta, tb, splitk):
+    """bf16 tensor-core mode: exact up to fp32 accumulation order once the operands are rounded to bf16."""
+    from multilingual_text_to_speech_b200 import functional as F, _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ar, br = a.bfloat16().double(), b.bfloat16().double()
+    ref = (ar.t() if ta else ar) @ (br.t() if tb else br) + bias.double()
+    _lib.set_precision('bf16')
+    try:
+        # route through the library's dispatching GEMM entry (same C ABI call; the mode selects the kernel)
+        out = F.gemm(a.cuda(), b.cuda(), ta, tb, bias=bias.cuda(), splitk=splitk)
+    finally:
+        _lib.set_precision('fp32')
+    assert_close(out, ref, 1e-4, 2e-4 * (K ** 0.5), f'bf16 gemm {M}x{N}x{K}')
+
+
+@pytest.mark.parametrize('kw', [
+    dict(B=8, L=40, T=30, kind='dropout'),
+    dict(B=40, L=64, T=24, kind='zoneout', seed=1),
+    dict(B=5, L=33, T=21, M=292, kind='dropout', seed=2),
+    dict(B=60, L=180, T=16, kind='zoneout', seed=6),
+])
+def test_decoder_bf16_perf_mode(kw):
+    """Persistent weight-stationary bf16 kernels (decoder_persist.cu) + bf16 tensor-core GEMMs."""
+    dc.run_case_bf16(dc.full_dim_case(**kw), check_grads=True, verbose=True)
