@@ -500,7 +500,7 @@ int launch_attn_bwd(AttnBwdArgs a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 struct BwdLayout {
     size_t dfs, dhgd, dctxs, dgg, dhas, dga, dq, dctxt, dcum, dc, dhz, dmemT, dWloc_acc, dWc_acc, dv_acc, dp1, dp0, dwfs,
-        part, gpart, pextra, total;
+        part, gpart, pextra, pextra2, total;
     int split_gen, split_att;
     size_t gpart_elems;
 };
@@ -536,6 +536,7 @@ BwdLayout bwd_layout(const b200tts_decoder_shape& s) {
     l.gpart_elems = (size_t)6 * 1024 * 1024;
     l.gpart = take(l.gpart_elems);
     l.pextra = take(persist_bwd_gen_extra_bytes(s) / sizeof(float) + 64);
+    l.pextra2 = take(att_bwd_extra(s).total / sizeof(float) + 64);
     l.total = off;
     return l;
 }
@@ -643,43 +644,52 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, M, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih + D, D + M, W(l.dctxs), M, 1.f));
 
     // ---- 3. attention LSTM + attention reverse loop ----
+    const bool persist_att = precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s) && persist_att_bwd_supported(s);
+    if (persist_att) {
+        // bf16 perf mode: cooperative weight-stationary kernel (tensor-core attention backward inside), then a parallel post pass
+        const PersistLayout pl = persist_layout(s);
+        B200_TRY(persist_att_bwd_loop(s, w, in, fl, fws, pl, reinterpret_cast<const unsigned char*>(F(fl.persist)), fwd_out.alignments,
+                                      dout.d_alignments, W(l.dhas), W(l.dctxs), W(l.dga), W(l.dq), W(l.dctxt), W(l.dmemT),
+                                      reinterpret_cast<unsigned char*>(W(l.pextra2)), dw, st));
+    } else {
     B200_TRY(launch_fill(W(l.dmemT), 0.f, (size_t)B * L * A, st));
-    B200_TRY(launch_fill(W(l.dWloc_acc), 0.f, (size_t)B * A * C, st));
-    B200_TRY(launch_fill(W(l.dWc_acc), 0.f, (size_t)B * C * K, st));
-    B200_TRY(launch_fill(W(l.dv_acc), 0.f, (size_t)B * A, st));
-    for (int i = T - 1; i >= 0; --i) {
-        const int last = (i == T - 1);
-        AttnBwdArgs aa{};
-        aa.q = F(fl.q) + (size_t)i * B * A; aa.memT = F(fl.memT); aa.memory = in.memory; aa.lengths = in.text_lengths;
-        aa.Wc = w.attn_loc_features; aa.Wloc = w.attn_location; aa.bias = w.attn_bias; aa.v = w.attn_energy;
-        aa.cum_prev = F(fl.cum) + (size_t)i * B * L;
-        aa.w = fwd_out.alignments + (size_t)i * L; aa.w_bstride = (long long)T * L;
-        aa.dalign = dout.d_alignments ? dout.d_alignments + (size_t)i * L : nullptr; aa.dalign_bstride = (long long)T * L;
-        aa.dctx_static = W(l.dctxs) + (size_t)i * B * M;
-        aa.part = W(l.part); aa.nsplit = l.split_att; aa.part_stride = (size_t)B * MD; aa.ld_part = MD;
-        aa.dcum = W(l.dcum); aa.dctx_tot = W(l.dctxt) + (size_t)i * B * M; aa.dq = W(l.dq) + (size_t)i * B * A;
-        aa.dmemT = W(l.dmemT); aa.dWloc_acc = W(l.dWloc_acc); aa.dWc_acc = W(l.dWc_acc); aa.dv_acc = W(l.dv_acc);
-        aa.B = B; aa.L = L; aa.M = M; aa.A = A; aa.C = C; aa.K = K; aa.last = last;
-        B200_TRY(launch_attn_bwd(aa, st));
+        B200_TRY(launch_fill(W(l.dWloc_acc), 0.f, (size_t)B * A * C, st));
+        B200_TRY(launch_fill(W(l.dWc_acc), 0.f, (size_t)B * C * K, st));
+        B200_TRY(launch_fill(W(l.dv_acc), 0.f, (size_t)B * A, st));
+        for (int i = T - 1; i >= 0; --i) {
+            const int last = (i == T - 1);
+            AttnBwdArgs aa{};
+            aa.q = F(fl.q) + (size_t)i * B * A; aa.memT = F(fl.memT); aa.memory = in.memory; aa.lengths = in.text_lengths;
+            aa.Wc = w.attn_loc_features; aa.Wloc = w.attn_location; aa.bias = w.attn_bias; aa.v = w.attn_energy;
+            aa.cum_prev = F(fl.cum) + (size_t)i * B * L;
+            aa.w = fwd_out.alignments + (size_t)i * L; aa.w_bstride = (long long)T * L;
+            aa.dalign = dout.d_alignments ? dout.d_alignments + (size_t)i * L : nullptr; aa.dalign_bstride = (long long)T * L;
+            aa.dctx_static = W(l.dctxs) + (size_t)i * B * M;
+            aa.part = W(l.part); aa.nsplit = l.split_att; aa.part_stride = (size_t)B * MD; aa.ld_part = MD;
+            aa.dcum = W(l.dcum); aa.dctx_tot = W(l.dctxt) + (size_t)i * B * M; aa.dq = W(l.dq) + (size_t)i * B * A;
+            aa.dmemT = W(l.dmemT); aa.dWloc_acc = W(l.dWloc_acc); aa.dWc_acc = W(l.dWc_acc); aa.dv_acc = W(l.dv_acc);
+            aa.B = B; aa.L = L; aa.M = M; aa.A = A; aa.C = C; aa.K = K; aa.last = last;
+            B200_TRY(launch_attn_bwd(aa, st));
 
-        CellBwdArgs ca{};
-        ca.gates = F(fl.ga) + (size_t)i * B4D;
-        ca.c_prev = F(fl.ca) + (size_t)i * BD;
-        ca.dh_static = W(l.dhas) + (size_t)i * BD; ca.ld_dhs = D;
-        ca.part = W(l.part); ca.nsplit = l.split_att; ca.part_stride = (size_t)B * MD; ca.ld_part = MD; ca.part_col0 = M;
-        ca.dq = aa.dq; ca.Wq = w.attn_query; ca.A = A;
-        ca.dc_state = W(l.dc); ca.dhz_state = zone ? W(l.dhz) : nullptr;
-        ca.mask_h = in.mask_att_h ? in.mask_att_h + (size_t)i * BD : nullptr;
-        ca.mask_c = in.mask_att_c ? in.mask_att_c + (size_t)i * BD : nullptr;
-        ca.kind = s.cell_kind; ca.training = s.training; ca.rate_h = s.rate_h; ca.rate_c = s.rate_c;
-        ca.dgates = W(l.dga) + (size_t)i * B4D; ca.B = B; ca.D = D; ca.last = last;
-        B200_TRY(launch_cell_bwd(ca, st));
-        if (i > 0) {
-            GemmDesc d;      // [d ctx_{i-1} | d h_att_{i-1}] (recurrent) = dgates_i . [W_ih[:, P:] | W_hh]
-            d.A = ca.dgates; d.lda = 4 * D; d.B = F(fl.wcat_att); d.ldb = MD; d.transB = 0; d.M = B; d.N = MD; d.K = 4 * D;
-            d.splitk = l.split_att; d.partial = W(l.part); d.keep_partials = 1;
-            if (d.splitk == 1) { d.C = W(l.part); d.ldc = MD; d.keep_partials = 0; d.partial = nullptr; }
-            B200_TRY(gemm_run(d, st));
+            CellBwdArgs ca{};
+            ca.gates = F(fl.ga) + (size_t)i * B4D;
+            ca.c_prev = F(fl.ca) + (size_t)i * BD;
+            ca.dh_static = W(l.dhas) + (size_t)i * BD; ca.ld_dhs = D;
+            ca.part = W(l.part); ca.nsplit = l.split_att; ca.part_stride = (size_t)B * MD; ca.ld_part = MD; ca.part_col0 = M;
+            ca.dq = aa.dq; ca.Wq = w.attn_query; ca.A = A;
+            ca.dc_state = W(l.dc); ca.dhz_state = zone ? W(l.dhz) : nullptr;
+            ca.mask_h = in.mask_att_h ? in.mask_att_h + (size_t)i * BD : nullptr;
+            ca.mask_c = in.mask_att_c ? in.mask_att_c + (size_t)i * BD : nullptr;
+            ca.kind = s.cell_kind; ca.training = s.training; ca.rate_h = s.rate_h; ca.rate_c = s.rate_c;
+            ca.dgates = W(l.dga) + (size_t)i * B4D; ca.B = B; ca.D = D; ca.last = last;
+            B200_TRY(launch_cell_bwd(ca, st));
+            if (i > 0) {
+                GemmDesc d;      // [d ctx_{i-1} | d h_att_{i-1}] (recurrent) = dgates_i . [W_ih[:, P:] | W_hh]
+                d.A = ca.dgates; d.lda = 4 * D; d.B = F(fl.wcat_att); d.ldb = MD; d.transB = 0; d.M = B; d.N = MD; d.K = 4 * D;
+                d.splitk = l.split_att; d.partial = W(l.part); d.keep_partials = 1;
+                if (d.splitk == 1) { d.C = W(l.part); d.ldc = MD; d.keep_partials = 0; d.partial = nullptr; }
+                B200_TRY(gemm_run(d, st));
+            }
         }
     }
 
@@ -698,12 +708,14 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     }
     // d Wq = dQ^T . h_att
     B200_TRY(wgemm(st, l, bws, 1, 0, A, D, (int)TB, W(l.dq), A, ai1 + M, MD, dw.attn_query, D, 1.f));
-    batchsum_add_kernel<<<grid_for((size_t)A * C), 256, 0, st>>>(dw.attn_location, W(l.dWloc_acc), B, (size_t)A * C);
-    B200_LAUNCH_CHECK();
-    batchsum_add_kernel<<<grid_for((size_t)C * K), 256, 0, st>>>(dw.attn_loc_features, W(l.dWc_acc), B, (size_t)C * K);
-    B200_LAUNCH_CHECK();
-    batchsum_add_kernel<<<1, 256, 0, st>>>(dw.attn_energy, W(l.dv_acc), B, (size_t)A);
-    B200_LAUNCH_CHECK();
+    if (!persist_att) {
+        batchsum_add_kernel<<<grid_for((size_t)A * C), 256, 0, st>>>(dw.attn_location, W(l.dWloc_acc), B, (size_t)A * C);
+        B200_LAUNCH_CHECK();
+        batchsum_add_kernel<<<grid_for((size_t)C * K), 256, 0, st>>>(dw.attn_loc_features, W(l.dWc_acc), B, (size_t)C * K);
+        B200_LAUNCH_CHECK();
+        batchsum_add_kernel<<<1, 256, 0, st>>>(dw.attn_energy, W(l.dv_acc), B, (size_t)A);
+        B200_LAUNCH_CHECK();
+    }
     // d Wm = dmemT^T . memory ; d memory = align^T . dctx (per utterance) + dmemT . Wm
     B200_TRY(wgemm(st, l, bws, 1, 0, A, M, B * L, W(l.dmemT), A, in.memory, M, dw.attn_memory, M, 1.f));
     if (d_memory) {

@@ -97,6 +97,14 @@ static inline DecoderLayout decoder_layout(const b200tts_decoder_shape& s) {
 int validate_decoder_shape(const b200tts_decoder_shape& s);
 int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                      const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st);
+struct AttBwdExtra { int MT; size_t dgb, part, wcb, wcb2, memTf, de, dwpart, dvpart, barrier, total; };
+AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s);
+bool persist_att_bwd_supported(const b200tts_decoder_shape& s);
+int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                         const DecoderLayout& fl, const float* fws, const PersistLayout& pl, const unsigned char* pws,
+                         const float* align, const float* dalign, const float* dh_static, const float* dctx_static, float* dgates,
+                         float* dq, float* dctx_tot, float* dmemT, unsigned char* extra, const b200tts_decoder_params& dw,
+                         cudaStream_t st);
 bool persist_bwd_supported(const b200tts_decoder_shape& s);
 size_t persist_bwd_gen_extra_bytes(const b200tts_decoder_shape& s);
 int persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,

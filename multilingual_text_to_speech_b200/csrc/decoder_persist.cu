@@ -117,10 +117,11 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
     size_t off = 0;
     s.W = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += (size_t)ROWS * WLD * 2;
     s.act = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += (size_t)2 * BT * ALD * 2;
-    s.sum = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (ROWS + 1) * 4;
     s.hs = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (UNITS + 1) * 4;
-    s.wq = reinterpret_cast<float*>(smem_raw + off);
+    s.wq = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)p.A * (UNITS + 1) * 4 : 0;
+    float* WcT = reinterpret_cast<float*>(smem_raw + off);     // [KC][A] resident (ATT only)
     float* scratch = reinterpret_cast<float*>(s.act);          // 2*BT*ALD*2 B = 33,792 B = 8448 floats
+    s.sum = scratch + 4096;                                    // [BT][ROWS+1] = 2080 floats, past the last reduction round's reads
 
     // ---- one-time: resident weight slice (fp32 -> bf16), query-projection slice ----
     for (int idx = tid; idx < ROWS * Kp; idx += PT) {
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
             const int a = idx / UNITS, u = idx % UNITS;
             s.wq[a * (UNITS + 1) + u] = (u0 + u < D) ? p.Wq[(size_t)a * D + u0 + u] : 0.f;
         }
+        for (int idx = tid; idx < p.KC * p.A; idx += PT) WcT[idx] = p.WcombT[idx];
     }
     __syncthreads();
 
@@ -291,25 +293,40 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                 float* qb = scratch;                       // [A]
                 float* vv = qb + A;                        // [A]
                 float* cump = vv + A;                      // [L + KC - 1] (+3)
-                float* WcT = cump + ((L + KC - 1 + 3) & ~3);   // [KC][A]
-                float* e = WcT + KC * A;                   // [L] (+3)
+                float* e = cump + ((L + KC - 1 + 3) & ~3); // [L] (+3)
                 float* red = e + ((L + 3) & ~3);           // [64]
-                float* cred = red + 64;                    // [8][M]
+                float* cred = red + 64;                    // [8][M]  (first used as [PT/A][A] query partials)
                 int len = p.lengths[b];
                 len = len < 0 ? 0 : (len > L ? L : len);
-                for (int a = tid; a < A; a += PT) {
-                    float q = 0.f;
-                    for (int r = 0; r < p.RB; ++r) q += __ldcg(p.qpart + ((size_t)r * B + b) * A + a);
-                    p.qsave[((size_t)i * B + b) * A + a] = q;
-                    qb[a] = q + p.bias[a];
-                    vv[a] = p.v[a];
+                {   // q[a] = sum over the RB per-CTA partial projections; 8 independent loads in flight per thread
+                    const int nsl = PT / A > 0 ? PT / A : 1;            // slices of the RB range (2 for A = 128)
+                    const int a = tid % A, sl = tid / A;
+                    if (sl < nsl) {
+                        float qs[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) qs[j] = 0.f;
+                        const int per = (p.RB + nsl - 1) / nsl, r0 = sl * per, r1 = min(p.RB, r0 + per);
+                        for (int r = r0; r < r1; r += 8) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (r + j < r1) qs[j] += __ldcg(p.qpart + ((size_t)(r + j) * B + b) * A + a);
+                        }
+                        cred[sl * A + a] = ((qs[0] + qs[1]) + (qs[2] + qs[3])) + ((qs[4] + qs[5]) + (qs[6] + qs[7]));
+                    }
+                    __syncthreads();
+                    for (int a2 = tid; a2 < A; a2 += PT) {
+                        float q = 0.f;
+                        for (int sl2 = 0; sl2 < nsl; ++sl2) q += cred[sl2 * A + a2];
+                        p.qsave[((size_t)i * B + b) * A + a2] = q;
+                        qb[a2] = q + p.bias[a2];
+                        vv[a2] = p.v[a2];
+                    }
                 }
                 const float* cum_prev = p.cum + ((size_t)i * B + b) * L;
                 for (int j = tid; j < L + KC - 1; j += PT) {
                     const int l = j - half;
                     cump[j] = (l >= 0 && l < L) ? __ldcg(cum_prev + l) : 0.f;
                 }
-                for (int idx = tid; idx < KC * A; idx += PT) WcT[idx] = p.WcombT[idx];
                 __syncthreads();
                 // energies: warp = 4 consecutive positions, lane = attention dims lane + 32 j
                 for (int l0 = warp * 4; l0 < len; l0 += 32) {
@@ -366,6 +383,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                 float cacc[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) cacc[j] = 0.f;
+#pragma unroll 4
                 for (int l = warp; l < len; l += 8) {
                     const float w = e[l];
                     const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + l) * p.ldm);
@@ -399,12 +417,12 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
 }
 
 size_t loop_smem_bytes(int Kp, int A, bool att, int L, int M, int KC) {
-    size_t b = (size_t)ROWS * (Kp + 8) * 2 + (size_t)2 * BT * ALD * 2 + (size_t)BT * (ROWS + 1) * 4 + (size_t)BT * (UNITS + 1) * 4;
+    size_t b = (size_t)ROWS * (Kp + 8) * 2 + (size_t)2 * BT * ALD * 2 + (size_t)BT * (UNITS + 1) * 4;
     if (att) {
-        b += (size_t)A * (UNITS + 1) * 4;
+        b += (size_t)A * (UNITS + 1) * 4 + (size_t)KC * A * 4;
         // the attention scratch aliases the activation stages; it must fit there
-        const size_t need = ((size_t)2 * A + ((L + KC - 1 + 3) & ~3) + (size_t)KC * A + ((L + 3) & ~3) + 64 + (size_t)8 * M) * 4;
-        if (need > (size_t)2 * BT * ALD * 2) return 0;
+        const size_t need = ((size_t)2 * A + ((L + KC - 1 + 3) & ~3) + ((L + 3) & ~3) + 64 + (size_t)8 * M) * 4;
+        if (need > (size_t)2 * BT * ALD * 2 || PT % A != 0) return 0;
     }
     return b;
 }

@@ -212,6 +212,582 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_kernel(const BwdLoopArgs 
     }
 }
 
+
+// =================================================================================================
+// Attention-LSTM + attention reverse loop
+// =================================================================================================
+constexpr int KBA = 8;            // K-blocks of the attention-loop product (over hidden units)
+constexpr int NBA = 9;            // N-blocks over the M + D output columns  -> 8 x 9 x 2 = 144 CTAs
+constexpr int GLD = 33;           // row stride of the G tile buffer (floats)
+
+struct AttBwdArgs {
+    int B, T, D, M, L, A, KC, NOUT, UK, UN, NBH, MT;      // NOUT = M + D, MT = ceil(L / 16)
+    const float* W; int ldw;                              // wcat_att fp32 [4D, M + D]
+    const float* gates; const float* cstate;              // forward saves
+    const float* dh_static;                               // [T, B, D]   (from the generator input projection)
+    const float* dctx_static;                             // [T, B, M]
+    const uint8_t* mask_h; const uint8_t* mask_c;
+    int kind, training; float rate_h, rate_c;
+    float* dgates; __nv_bfloat16* dgb; float* part;       // as in BwdLoopArgs; part [KBA, B, NOUT]
+    // attention
+    const float* q; const float* cum; const float* align; long long align_bstride;
+    const float* dalign; long long dalign_bstride;        // may be null
+    const float* bias; const float* v; const float* Wq;   // [A], [A], [A, D]
+    const __nv_bfloat16* WcB;                             // [A][40]   Wcomb[a][k], k contiguous (k >= KC zero)
+    const __nv_bfloat16* WcB2;                            // [32][A+8] Wcomb^T[k][a], a contiguous
+    const __nv_bfloat16* memTf;                           // [B][MT][32 lanes][64] fragment-major memory projection
+    const __nv_bfloat16* memb; int ldm;                   // [B, L, ldm]
+    const int* lengths;
+    float* dctx_tot;                                      // [T, B, M] out
+    float* dq;                                            // [T, B, A] out
+    float* de;                                            // [T, B, L] out (softmax-backward energies, consumed by the post pass)
+    unsigned* barrier; int* abort_flag;
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Build the Toeplitz pair arrays of the zero-padded cumulative weights: Ph[x] = (hi[x], hi[x+1]), Pl likewise, where
+// cumpad[j] = cum[j - half] and cum = hi + lo with hi, lo in bf16 (16 mantissa bits in total).
+__device__ __forceinline__ void build_pairs(uint32_t* Ph, uint32_t* Pl, const float* cum, int L, int half, int n, int tid, int nthreads) {
+    for (int x = tid; x < n; x += nthreads) {
+        float c0 = 0.f, c1 = 0.f;
+        const int l0 = x - half, l1 = x + 1 - half;
+        if (l0 >= 0 && l0 < L) c0 = __ldcg(cum + l0);
+        if (l1 >= 0 && l1 < L) c1 = __ldcg(cum + l1);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
+        const float r0 = c0 - __bfloat162float(h0), r1 = c1 - __bfloat162float(h1);
+        __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
+        Ph[x] = *reinterpret_cast<uint32_t*>(&hp);
+        Pl[x] = pack2(r0, r1);
+    }
+}
+
+__global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const int kb = cta % KBA, nb = (cta / KBA) % NBA, bh = cta / (KBA * NBA);
+    const int B = p.B, D = p.D, UK = p.UK, UN = p.UN, KROWS = 4 * UK, M = p.M, L = p.L, A = p.A;
+    const int WLD = UN + 8, ALD = KROWS + 8;
+    const int b0 = bh * BT, n0 = nb * UN;
+    __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem_raw);                 // [KROWS][WLD]
+    __nv_bfloat16* As = Ws + (size_t)KROWS * WLD;                                    // [BT][ALD]  (aliased by the attention scratch)
+    unsigned char* extra = reinterpret_cast<unsigned char*>(As + (size_t)BT * ALD);
+    __nv_bfloat16* sWcB = reinterpret_cast<__nv_bfloat16*>(extra);                   // [A][40]
+    __nv_bfloat16* sWcB2 = sWcB + (size_t)A * 40;                                    // [32][A+8]
+    float* dcum = reinterpret_cast<float*>(sWcB2 + (size_t)32 * (A + 8));            // [L16 + 32] persistent d cum
+    float* wq8 = dcum + (p.MT * 16 + 32);                                            // [A][8 + 1] query weights of this CTA's 8 units
+    const unsigned nblocks = gridDim.x;
+    const int L16 = p.MT * 16;
+
+    for (int idx = tid; idx < KROWS * UN; idx += PT) {
+        const int r = idx / UN, n = idx % UN;
+        const int g = r / UK, uk = r % UK;
+        float w = 0.f;
+        if (n0 + n < p.NOUT) w = p.W[(size_t)(g * D + kb * UK + uk) * p.ldw + n0 + n];
+        Ws[r * WLD + n] = __float2bfloat16_rn(w);
+    }
+    for (int idx = tid; idx < A * 40; idx += PT) sWcB[idx] = p.WcB[idx];
+    for (int idx = tid; idx < 32 * (A + 8); idx += PT) sWcB2[idx] = p.WcB2[idx];
+    for (int idx = tid; idx < L16 + 32; idx += PT) dcum[idx] = 0.f;
+    // cell-backward ownership: CTA c < D/8 owns hidden units [8c, 8c+8) for every utterance
+    const int UOWN = 8;
+    const bool owner = cta * UOWN < D;
+    const int uo0 = cta * UOWN;
+    if (owner)
+        for (int idx = tid; idx < A * UOWN; idx += PT) wq8[(idx / UOWN) * (UOWN + 1) + idx % UOWN] = p.Wq[(size_t)(idx / UOWN) * D + uo0 + idx % UOWN];
+    __syncthreads();
+
+    const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
+    constexpr int MAXE = 3;               // (b, u) pairs per thread: B * 8 / 256 <= 3 for B <= 64... (B <= 96)
+    float dc_reg[MAXE], dhz_reg[MAXE];
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) { dc_reg[e] = 0.f; dhz_reg[e] = 0.f; }
+    unsigned target = 0;
+
+    // attention scratch (aliases As): floats
+    float* scr = reinterpret_cast<float*>(As);
+    float* s_dctx = scr;                                  // [M (+3)]
+    float* s_w = s_dctx + ((M + 3) & ~3);                 // [L16]
+    float* s_de = s_w + L16;                              // [L16]
+    float* s_qb = s_de + L16;                             // [A]
+    float* s_vv = s_qb + A;                               // [A]
+    uint32_t* s_Ph = reinterpret_cast<uint32_t*>(s_vv + A);   // [L16 + 48]
+    uint32_t* s_Pl = s_Ph + (L16 + 48);
+    float* s_red = reinterpret_cast<float*>(s_Pl + (L16 + 48));   // [64]
+    float* s_G = s_red + 64;                              // [L16][GLD]
+    float* s_dqp = scr;                                   // [8][A]: aliases s_dctx .. s_Ph once the tile loop is done
+    float* s_stage = reinterpret_cast<float*>(s_Pl);      // [L16]: d cum staging (Pl is dead by then)
+
+    for (int i = p.T - 1; i >= 0; --i) {
+        const bool last = (i == p.T - 1);
+        // =========================== PA: attention backward of utterance `cta` ===========================
+        if (cta < B) {
+            const int b = cta, half = (p.KC - 1) / 2;
+            int len = p.lengths[b];
+            len = len < 0 ? 0 : (len > L ? L : len);
+            const int mtiles = (len + 15) / 16;
+            for (int m = tid; m < M; m += PT) {
+                float g = p.dctx_static[((size_t)i * B + b) * M + m];
+                if (!last)
+                    for (int k2 = 0; k2 < KBA; ++k2) g += __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + m);
+                s_dctx[m] = g;
+                p.dctx_tot[((size_t)i * B + b) * M + m] = g;
+            }
+            for (int l = tid; l < L16; l += PT) s_w[l] = l < L ? p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] : 0.f;
+            for (int a = tid; a < A; a += PT) { s_qb[a] = p.q[((size_t)i * B + b) * A + a] + p.bias[a]; s_vv[a] = p.v[a]; }
+            build_pairs(s_Ph, s_Pl, p.cum + ((size_t)i * B + b) * L, L, half, L16 + 48, tid, PT);
+            __syncthreads();
+            // dw[l] = dalign + dcum + <dctx, memory[l]>
+            for (int l = warp; l < L16; l += 8) {
+                float acc = 0.f;
+                if (l < len) {
+                    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + l) * p.ldm);
+                    for (int m2 = lane; 2 * m2 < M; m2 += 32) {
+                        const float2 v2 = __bfloat1622float2(row[m2]);
+                        acc = fmaf(s_dctx[2 * m2], v2.x, acc);
+                        if (2 * m2 + 1 < M) acc = fmaf(s_dctx[2 * m2 + 1], v2.y, acc);
+                    }
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    float g = 0.f;
+                    if (l < len) {
+                        g = acc + (last ? 0.f : dcum[l]);
+                        if (p.dalign) g += p.dalign[(size_t)b * p.dalign_bstride + (size_t)i * L + l];
+                    }
+                    s_de[l] = g;
+                }
+            }
+            __syncthreads();
+            float dot = 0.f;
+            for (int l = tid; l < len; l += PT) dot = fmaf(s_w[l], s_de[l], dot);
+            dot = block_sum(dot, s_red);
+            for (int l = tid; l < L16; l += PT) {
+                const float d = l < len ? s_w[l] * (s_de[l] - dot) : 0.f;
+                s_de[l] = d;
+                if (l < L) p.de[((size_t)i * B + b) * L + l] = d;
+            }
+            __syncthreads();
+            // energies backward on the tensor cores; warp owns position tiles {warp, warp + 8}
+            float dqacc[16][2];
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) { dqacc[nt][0] = 0.f; dqacc[nt][1] = 0.f; }
+            const int g = lane >> 2, tq = lane & 3;
+            for (int mt = warp; mt < mtiles; mt += 8) {
+                const int l0 = mt * 16;
+                float sacc[16][4];
+#pragma unroll
+                for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const int x = l0 + ks * 16 + g + 2 * tq;       // cumpad index of (row g, col 2t) of this k-step
+                    uint32_t ah[4], al[4];
+                    ah[0] = s_Ph[x]; ah[1] = s_Ph[x + 8]; ah[2] = s_Ph[x + 8]; ah[3] = s_Ph[x + 16];
+                    al[0] = s_Pl[x]; al[1] = s_Pl[x + 8]; al[2] = s_Pl[x + 8]; al[3] = s_Pl[x + 16];
+#pragma unroll
+                    for (int np = 0; np < 8; ++np) {
+                        uint32_t bf[4];
+                        ldmatrix_x4(bf[0], bf[1], bf[2], bf[3], sWcB + (size_t)(np * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
+                        mma_bf16(sacc[2 * np], ah, bf[0], bf[1]);
+                        mma_bf16(sacc[2 * np], al, bf[0], bf[1]);
+                        mma_bf16(sacc[2 * np + 1], ah, bf[2], bf[3]);
+                        mma_bf16(sacc[2 * np + 1], al, bf[2], bf[3]);
+                    }
+                }
+                // ds = de[l] * v[a] * (1 - tanh^2(S + q + bias + memT)); fragment-major memory projection: 64 bf16 per lane
+                const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + mt) * 32 + lane) * 64);
+                const float de0 = s_de[l0 + g], de1 = s_de[l0 + g + 8];
+                uint32_t dsA[16][2];
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const uint4 raw = mf[c4];                      // n-tiles 2*c4, 2*c4+1; 4 values each
+                    const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int nt = 2 * c4 + hf;
+                        const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf]));
+                        const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf + 1]));
+                        const int a0 = nt * 8 + 2 * tq;
+                        const float t0 = tanh_fast(sacc[nt][0] + s_qb[a0] + m01.x), t1 = tanh_fast(sacc[nt][1] + s_qb[a0 + 1] + m01.y);
+                        const float t2 = tanh_fast(sacc[nt][2] + s_qb[a0] + m23.x), t3 = tanh_fast(sacc[nt][3] + s_qb[a0 + 1] + m23.y);
+                        const float d0 = de0 * s_vv[a0] * (1.f - t0 * t0), d1 = de0 * s_vv[a0 + 1] * (1.f - t1 * t1);
+                        const float d2 = de1 * s_vv[a0] * (1.f - t2 * t2), d3 = de1 * s_vv[a0 + 1] * (1.f - t3 * t3);
+                        dqacc[nt][0] += d0 + d2; dqacc[nt][1] += d1 + d3;
+                        dsA[nt][0] = pack2(d0, d1); dsA[nt][1] = pack2(d2, d3);
+                    }
+                }
+                // G[l, tap] = sum_a ds[l, a] * Wcomb[a, tap]   (C fragments of ds reused as A fragments)
+                float gacc[4][4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) gacc[nt][e] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t af[4] = {dsA[2 * j][0], dsA[2 * j][1], dsA[2 * j + 1][0], dsA[2 * j + 1][1]};
+#pragma unroll
+                    for (int np = 0; np < 2; ++np) {
+                        uint32_t bf[4];
+                        ldmatrix_x4(bf[0], bf[1], bf[2], bf[3], sWcB2 + (size_t)(np * 16 + (lane & 7) + ((lane >> 4) << 3)) * (A + 8) + j * 16 + ((lane >> 3) & 1) * 8);
+                        mma_bf16(gacc[2 * np], af, bf[0], bf[1]);
+                        mma_bf16(gacc[2 * np + 1], af, bf[2], bf[3]);
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) s_G[(l0 + g + 8 * (e >> 1)) * GLD + nt * 8 + 2 * tq + (e & 1)] = gacc[nt][e];
+            }
+            // dq[a] = sum_l ds[l, a]: reduce over the 8 row lanes, then over warps
+            __syncthreads();                               // every warp is done with s_de / s_qb / s_vv / Ph / Pl
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float v = dqacc[nt][c];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (g == 0) s_dqp[warp * A + nt * 8 + 2 * tq + c] = v;
+                }
+            __syncthreads();
+            for (int a = tid; a < A; a += PT) {
+                float sdq = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) sdq += s_dqp[w8 * A + a];
+                p.dq[((size_t)i * B + b) * A + a] = sdq;
+            }
+            // d cum_{i-1}[j] = d cum_i[j] + sum_k G[j + half - k, k]
+            for (int j = tid; j < L; j += PT) {
+                float acc = last ? 0.f : dcum[j];
+                for (int k = 0; k < p.KC; ++k) {
+                    const int l = j + half - k;
+                    if (l >= 0 && l < mtiles * 16) acc += s_G[l * GLD + k];
+                }
+                s_stage[j] = acc;                           // staged: dcum is still being read by other threads
+            }
+            __syncthreads();
+            for (int j = tid; j < L; j += PT) dcum[j] = s_stage[j];
+        }
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+
+        // =========================== PB: attention-LSTM cell backward ===========================
+        if (owner) {
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) {
+                const int idx = tid + e * PT;
+                if (idx < B * UOWN) {
+                    const int b = idx / UOWN, uu = idx % UOWN, u = uo0 + uu;
+                    const size_t bu = (size_t)b * D + u, g0 = ((size_t)i * B + b) * 4 * D + u;
+                    float dh = p.dh_static[(size_t)i * B * D + bu];
+                    const float* dqr = p.dq + ((size_t)i * B + b) * A;
+                    float dhq = 0.f;
+                    for (int a = 0; a < A; a += 4) {
+                        const float4 d4 = __ldcg(reinterpret_cast<const float4*>(dqr + a));
+                        dhq = fmaf(d4.x, wq8[a * (UOWN + 1) + uu], dhq); dhq = fmaf(d4.y, wq8[(a + 1) * (UOWN + 1) + uu], dhq);
+                        dhq = fmaf(d4.z, wq8[(a + 2) * (UOWN + 1) + uu], dhq); dhq = fmaf(d4.w, wq8[(a + 3) * (UOWN + 1) + uu], dhq);
+                    }
+                    dh += dhq;
+                    float dc_in = 0.f;
+                    if (!last) {
+                        float rec = 0.f;
+                        for (int k2 = 0; k2 < KBA; ++k2) rec += __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
+                        dh += rec + dhz_reg[e];
+                        dc_in = dc_reg[e];
+                    }
+                    const float gi = p.gates[g0], gf = p.gates[g0 + D], gg = p.gates[g0 + 2 * D], go = p.gates[g0 + 3 * D];
+                    const float cp = p.cstate[(size_t)i * B * D + bu];
+                    const float tc = tanhf(gf * cp + gi * gg);
+                    const size_t mi = (size_t)i * B * D + bu;
+                    float dhn, dcn, dc_prev_direct = 0.f, dh_prev_direct = 0.f;
+                    if (p.kind == B200TTS_CELL_ZONEOUT) {
+                        float kh, kc;
+                        if (p.training) {
+                            kh = (1.f - p.rate_h) * (p.mask_h ? (float)p.mask_h[mi] * inv_h : 1.f);
+                            kc = (1.f - p.rate_c) * (p.mask_c ? (float)p.mask_c[mi] * inv_c : 1.f);
+                        } else { kh = 1.f - p.rate_h; kc = 1.f - p.rate_c; }
+                        dhn = dh * kh; dh_prev_direct = dh - dhn;
+                        dcn = dc_in * kc + dhn * go * (1.f - tc * tc);
+                        dc_prev_direct = dc_in - dc_in * kc;
+                    } else {
+                        dhn = (p.training && p.mask_h) ? dh * (float)p.mask_h[mi] * inv_h : dh;
+                        dcn = dc_in + dhn * go * (1.f - tc * tc);
+                    }
+                    const float di = dcn * gg * gi * (1.f - gi), df = dcn * cp * gf * (1.f - gf);
+                    const float dg = dcn * gi * (1.f - gg * gg), dO = dhn * tc * go * (1.f - go);
+                    p.dgates[g0] = di; p.dgates[g0 + D] = df; p.dgates[g0 + 2 * D] = dg; p.dgates[g0 + 3 * D] = dO;
+                    __nv_bfloat16* db = p.dgb + (size_t)b * 4 * D + u;
+                    db[0] = __float2bfloat16_rn(di); db[D] = __float2bfloat16_rn(df);
+                    db[2 * D] = __float2bfloat16_rn(dg); db[3 * D] = __float2bfloat16_rn(dO);
+                    dc_reg[e] = dcn * gf + dc_prev_direct;
+                    dhz_reg[e] = dh_prev_direct;
+                }
+            }
+        }
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        if (i == 0) break;
+
+        // =========================== P2: [d ctx | d h](i-1) partial = dgates_i[:, kb] . W[kb, nb] ===========================
+        {
+            const int segs = UK / 8;
+            for (int idx = tid; idx < BT * 4 * segs; idx += PT) {
+                const int r = idx / (4 * segs), rem = idx % (4 * segs), g = rem / segs, sg = rem % segs;
+                __nv_bfloat16* d = As + r * ALD + g * UK + sg * 8;
+                if (b0 + r < B) cp_async16(d, p.dgb + (size_t)(b0 + r) * 4 * D + g * D + kb * UK + sg * 8);
+                else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            cp_async_commit_wait();
+            __syncthreads();
+            const int npairs = UN / 16;
+            for (int np = warp; np < npairs; np += 8) {
+                float acc[2][2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+                for (int kk = 0; kk < KROWS; kk += 16) {
+                    uint32_t af[2][4], bf[4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        ldmatrix_x4(af[mt][0], af[mt][1], af[mt][2], af[mt][3], As + (mt * 16 + (lane & 15)) * ALD + kk + (lane >> 4) * 8);
+                    ldmatrix_x4_trans(bf[0], bf[1], bf[2], bf[3],
+                                      Ws + (size_t)(kk + (lane & 7) + ((lane >> 3) & 1) * 8) * WLD + np * 16 + (lane >> 4) * 8);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        mma_bf16(acc[mt][0], af[mt], bf[0], bf[1]);
+                        mma_bf16(acc[mt][1], af[mt], bf[2], bf[3]);
+                    }
+                }
+                const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int b = b0 + mt * 16 + g + 8 * (e >> 1);
+                            const int n = n0 + np * 16 + nt * 8 + 2 * tq + (e & 1);
+                            if (b < B && n < p.NOUT) p.part[((size_t)kb * B + b) * p.NOUT + n] = acc[mt][nt][e];
+                        }
+            }
+        }
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Post pass (fully parallel): accumulate what the recurrence does not need -- d memT, d Wcomb, d v.
+// CTA = (utterance b, position tile mt); warp w owns the attention dims [16w, 16w+16); loops over all T steps
+// recomputing S^T = Wcomb . T^T on the tensor cores from the saved query / cumulative weights / de.
+// -------------------------------------------------------------------------------------------------
+struct AttPostArgs {
+    int B, T, L, A, KC, MT;
+    const float* q; const float* cum; const float* de; const float* bias; const float* v;
+    const __nv_bfloat16* WcB;          // [A][40]
+    const float* memT;                 // [B, L, A] fp32
+    const int* lengths;
+    float* dmemT;                      // [B, L, A] out (each element written exactly once)
+    float* dWcomb_part;                // [B*MT][A][32]
+    float* dv_part;                    // [B*MT][A]
+};
+
+__global__ void __launch_bounds__(PT) att_post_kernel(const AttPostArgs p) {
+    __shared__ uint32_t Ph[2][64], Pl[2][64];
+    __shared__ float s_de[2][16], s_q[2][128];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / p.MT, mt = blockIdx.x % p.MT;
+    const int L = p.L, A = p.A, half = (p.KC - 1) / 2, l0 = mt * 16;
+    const int g = lane >> 2, tq = lane & 3;
+    int len = p.lengths[b];
+    len = len < 0 ? 0 : (len > L ? L : len);
+    const int a_base = warp * 16;                       // requires A <= 128 (8 warps x 16)
+    const bool active = a_base < A && l0 < len;
+    // A fragments of Wcomb (rows a, cols k): constant over the whole loop
+    uint32_t wa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const __nv_bfloat16* base = p.WcB + (size_t)(a_base + g) * 40 + ks * 16 + 2 * tq;
+        wa[ks][0] = *reinterpret_cast<const uint32_t*>(base);
+        wa[ks][1] = *reinterpret_cast<const uint32_t*>(base + 8 * 40);
+        wa[ks][2] = *reinterpret_cast<const uint32_t*>(base + 8);
+        wa[ks][3] = *reinterpret_cast<const uint32_t*>(base + 8 * 40 + 8);
+    }
+    // memT values of this thread's S^T fragment: rows a = a_base + g (+8), cols l = l0 + nt*8 + 2t (+1)
+    float mT[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int a = a_base + g + 8 * (e >> 1), l = l0 + nt * 8 + 2 * tq + (e & 1);
+            // rounded through bf16 exactly like the operand the forward / in-loop kernels consumed
+            mT[nt][e] = (a < A && l < L) ? __bfloat162float(__float2bfloat16_rn(p.memT[((size_t)b * L + l) * A + a])) : 0.f;
+        }
+    const float bias0 = a_base + g < A ? p.bias[a_base + g] : 0.f, bias1 = a_base + g + 8 < A ? p.bias[a_base + g + 8] : 0.f;
+    const float v0 = a_base + g < A ? p.v[a_base + g] : 0.f, v1 = a_base + g + 8 < A ? p.v[a_base + g + 8] : 0.f;
+    float dmacc[2][4], dwacc[4][4], dvacc[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dmacc[nt][e] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dwacc[nt][e] = 0.f;
+
+    auto stage = [&](int i, int buf) {
+        // window of cumpad needed by this tile: x in [l0, l0 + 16 + 32)
+        if (tid < 64) {
+            const float* cum = p.cum + ((size_t)i * p.B + b) * L;
+            const int x = l0 + tid;
+            float c0 = 0.f, c1 = 0.f;
+            const int la = x - half, lb = x + 1 - half;
+            if (la >= 0 && la < L) c0 = cum[la];
+            if (lb >= 0 && lb < L) c1 = cum[lb];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
+            __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
+            Ph[buf][tid] = *reinterpret_cast<uint32_t*>(&hp);
+            Pl[buf][tid] = pack2(c0 - __bfloat162float(h0), c1 - __bfloat162float(h1));
+        } else if (tid < 80) {
+            const int l = l0 + tid - 64;
+            s_de[buf][tid - 64] = l < L ? p.de[((size_t)i * p.B + b) * L + l] : 0.f;
+        } else if (tid >= 128 && tid < 128 + A) {
+            s_q[buf][tid - 128] = p.q[((size_t)i * p.B + b) * A + tid - 128];
+        }
+    };
+    if (l0 < len) stage(0, 0);
+    __syncthreads();
+    for (int i = 0; i < p.T && l0 < len; ++i) {
+        const int buf = i & 1;
+        if (i + 1 < p.T) stage(i + 1, buf ^ 1);
+        if (active) {
+            // S^T[a, l] = sum_k Wcomb[a, k] * cumpad[l + k]
+            float sacc[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    // B fragment (k rows, l cols): (k = ks*16 + 2t (+1) (+8), l = nt*8 + g) -> cumpad[l + k]
+                    const int x = nt * 8 + g + ks * 16 + 2 * tq;
+                    mma_bf16(sacc[nt], wa[ks], Ph[buf][x], Ph[buf][x + 8]);
+                    mma_bf16(sacc[nt], wa[ks], Pl[buf][x], Pl[buf][x + 8]);
+                }
+            const float q0 = s_q[buf][a_base + g] + bias0, q1 = s_q[buf][a_base + g + 8] + bias1;
+            uint32_t dsA[2][2];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float dea = s_de[buf][nt * 8 + 2 * tq], deb = s_de[buf][nt * 8 + 2 * tq + 1];
+                const float t0 = tanh_fast(sacc[nt][0] + q0 + mT[nt][0]), t1 = tanh_fast(sacc[nt][1] + q0 + mT[nt][1]);
+                const float t2 = tanh_fast(sacc[nt][2] + q1 + mT[nt][2]), t3 = tanh_fast(sacc[nt][3] + q1 + mT[nt][3]);
+                const float d0 = dea * v0 * (1.f - t0 * t0), d1 = deb * v0 * (1.f - t1 * t1);
+                const float d2 = dea * v1 * (1.f - t2 * t2), d3 = deb * v1 * (1.f - t3 * t3);
+                dmacc[nt][0] += d0; dmacc[nt][1] += d1; dmacc[nt][2] += d2; dmacc[nt][3] += d3;
+                dvacc[0] += dea * t0 + deb * t1; dvacc[1] += dea * t2 + deb * t3;
+                dsA[nt][0] = pack2(d0, d1); dsA[nt][1] = pack2(d2, d3);
+            }
+            // d Wcomb[a, k] += sum_l ds^T[a, l] * cumpad[l + k]   (A = ds^T chained; B fragment (l rows, k cols) = cumpad[l + k])
+            const uint32_t af[4] = {dsA[0][0], dsA[0][1], dsA[1][0], dsA[1][1]};
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int x = 2 * tq + nt * 8 + g;                  // l = 2t (+1) (+8), k = nt*8 + g
+                mma_bf16(dwacc[nt], af, Ph[buf][x], Ph[buf][x + 8]);
+            }
+        }
+        __syncthreads();
+    }
+    if (a_base < A) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int a = a_base + g + 8 * (e >> 1), l = l0 + nt * 8 + 2 * tq + (e & 1);
+                if (a < A && l < L) p.dmemT[((size_t)b * L + l) * A + a] = dmacc[nt][e];
+            }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int a = a_base + g + 8 * (e >> 1), k = nt * 8 + 2 * tq + (e & 1);
+                if (a < A) p.dWcomb_part[((size_t)blockIdx.x * A + a) * 32 + k] = dwacc[nt][e];
+            }
+        float d0 = dvacc[0], d1 = dvacc[1];
+        d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+        if (tq == 0) {
+            if (a_base + g < A) p.dv_part[(size_t)blockIdx.x * A + a_base + g] = d0;
+            if (a_base + g + 8 < A) p.dv_part[(size_t)blockIdx.x * A + a_base + g + 8] = d1;
+        }
+    }
+}
+
+// prep: bf16 copies of Wcomb in the two operand layouts, fragment-major memT
+__global__ void att_bwd_prep_kernel(__nv_bfloat16* __restrict__ WcB, __nv_bfloat16* __restrict__ WcB2, __nv_bfloat16* __restrict__ memTf,
+                                    const float* __restrict__ WcombT, const float* __restrict__ memT, int B, int L, int A, int KC, int MT) {
+    const size_t n1 = (size_t)A * 40, n2 = (size_t)32 * (A + 8), n3 = (size_t)B * MT * 32 * 64;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n1 + n2 + n3; idx += (size_t)gridDim.x * blockDim.x) {
+        if (idx < n1) {
+            const int a = idx / 40, k = idx % 40;
+            WcB[idx] = __float2bfloat16_rn(k < KC ? WcombT[(size_t)k * A + a] : 0.f);
+        } else if (idx < n1 + n2) {
+            const size_t j = idx - n1;
+            const int k = j / (A + 8), a = j % (A + 8);
+            WcB2[j] = __float2bfloat16_rn((k < KC && a < A) ? WcombT[(size_t)k * A + a] : 0.f);
+        } else {
+            const size_t j = idx - n1 - n2;
+            const int v = j % 64, lane = (j / 64) % 32, mt = (j / (64 * 32)) % MT, b = j / ((size_t)64 * 32 * MT);
+            const int nt = v / 4, e = v % 4, g = lane >> 2, tq = lane & 3;
+            const int l = mt * 16 + g + 8 * (e >> 1), a = nt * 8 + 2 * tq + (e & 1);
+            memTf[j] = __float2bfloat16_rn((l < L && a < A) ? memT[((size_t)b * L + l) * A + a] : 0.f);
+        }
+    }
+}
+
+// dWloc[a, c] += sum_k dWcomb[a, k] * Wc[c, k];  dWc[c, k] += sum_a Wloc[a, c] * dWcomb[a, k];  dv += sum parts
+__global__ void att_bwd_finish_kernel(float* __restrict__ dWloc, float* __restrict__ dWc, float* __restrict__ dv,
+                                      const float* __restrict__ dWcomb_part, const float* __restrict__ dv_part,
+                                      const float* __restrict__ Wloc, const float* __restrict__ Wc, int nparts, int A, int C, int KC) {
+    extern __shared__ float dW[];        // [A][32] reduced dWcomb
+    for (int idx = threadIdx.x; idx < A * 32; idx += blockDim.x) {
+        float s = 0.f;
+        for (int p2 = 0; p2 < nparts; ++p2) s += dWcomb_part[(size_t)p2 * A * 32 + idx];
+        dW[idx] = s;
+    }
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        float s = 0.f;
+        for (int p2 = 0; p2 < nparts; ++p2) s += dv_part[(size_t)p2 * A + a];
+        dv[a] += s;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < A * C; idx += blockDim.x) {
+        const int a = idx / C, c = idx % C;
+        float s = 0.f;
+        for (int k = 0; k < KC; ++k) s = fmaf(dW[a * 32 + k], Wc[c * KC + k], s);
+        dWloc[idx] += s;
+    }
+    for (int idx = threadIdx.x; idx < C * KC; idx += blockDim.x) {
+        const int c = idx / KC, k = idx % KC;
+        float s = 0.f;
+        for (int a = 0; a < A; ++a) s = fmaf(Wloc[a * C + c], dW[a * 32 + k], s);
+        dWc[idx] += s;
+    }
+}
+
 }  // namespace
 
 bool persist_bwd_supported(const b200tts_decoder_shape& s) {
@@ -219,6 +795,101 @@ bool persist_bwd_supported(const b200tts_decoder_shape& s) {
     const int UK = s.D / KB;
     if (UK / NBK > 32 || (UK % NBK) != 0) return false;
     return true;
+}
+
+// -------------------------------------------------------------------------------------------------
+// attention loop, host side
+// -------------------------------------------------------------------------------------------------
+AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s) {
+    AttBwdExtra x;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off = (off + n + 255) / 256 * 256; return o; };
+    x.MT = (s.L + 15) / 16;
+    x.dgb = take((size_t)s.B * 4 * s.D * 2);
+    x.part = take((size_t)KBA * s.B * (s.M + s.D) * 4);
+    x.wcb = take((size_t)s.A * 40 * 2);
+    x.wcb2 = take((size_t)32 * (s.A + 8) * 2);
+    x.memTf = take((size_t)s.B * x.MT * 32 * 64 * 2);
+    x.de = take((size_t)s.T * s.B * s.L * 4);
+    x.dwpart = take((size_t)s.B * x.MT * s.A * 32 * 4);
+    x.dvpart = take((size_t)s.B * x.MT * s.A * 4);
+    x.barrier = take(256);
+    x.total = off;
+    return x;
+}
+
+bool persist_att_bwd_supported(const b200tts_decoder_shape& s) {
+    if (!persist_bwd_supported(s)) return false;
+    if (s.A != 128 || s.K > 32 || s.B > 2 * BT || s.B * 8 > 3 * PT || s.D / 8 > KBA * NBA * ((s.B + BT - 1) / BT)) return false;
+    const int UK = s.D / KBA, UN = (cdiv(s.M + s.D, NBA) + 15) / 16 * 16;
+    const int MT = (s.L + 15) / 16, L16 = MT * 16;
+    const size_t fixed = ((size_t)4 * UK * (UN + 8) + (size_t)BT * (4 * UK + 8)) * 2 + (size_t)s.A * 40 * 2 + (size_t)32 * (s.A + 8) * 2 +
+                         (size_t)(L16 + 32) * 4 + (size_t)s.A * 9 * 4;
+    const size_t head = (size_t)((s.M + 3) & ~3) + 2 * L16 + 2 * s.A;          // s_dctx, s_w, s_de, s_qb, s_vv
+    const size_t scratch = (head + 2 * (L16 + 48) + 64 + (size_t)L16 * GLD) * 4;
+    if ((size_t)8 * s.A > head + (L16 + 48)) return false;                       // dq partials must end before Pl (staging)
+    return fixed <= 227 * 1024 && scratch <= (size_t)BT * (4 * UK + 8) * 2;
+}
+
+int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                         const DecoderLayout& fl, const float* fws, const PersistLayout& pl, const unsigned char* pws,
+                         const float* align, const float* dalign, const float* dh_static, const float* dctx_static, float* dgates,
+                         float* dq, float* dctx_tot, float* dmemT, unsigned char* extra, const b200tts_decoder_params& dw,
+                         cudaStream_t st) {
+    const AttBwdExtra x = att_bwd_extra(s);
+    const int B = s.B, D = s.D, M = s.M, T = s.T, L = s.L, A = s.A;
+    AttBwdArgs a{};
+    a.B = B; a.T = T; a.D = D; a.M = M; a.L = L; a.A = A; a.KC = s.K; a.NOUT = M + D; a.UK = D / KBA;
+    a.UN = (cdiv(M + D, NBA) + 15) / 16 * 16; a.NBH = (B + BT - 1) / BT; a.MT = x.MT;
+    a.W = fws + fl.wcat_att; a.ldw = M + D;
+    a.gates = fws + fl.ga; a.cstate = fws + fl.ca; a.dh_static = dh_static; a.dctx_static = dctx_static;
+    a.mask_h = in.mask_att_h; a.mask_c = in.mask_att_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
+    a.dgates = dgates;
+    a.dgb = reinterpret_cast<__nv_bfloat16*>(extra + x.dgb);
+    a.part = reinterpret_cast<float*>(extra + x.part);
+    a.q = fws + fl.q; a.cum = fws + fl.cum; a.align = align; a.align_bstride = (long long)T * L;
+    a.dalign = dalign; a.dalign_bstride = (long long)T * L;
+    a.bias = w.attn_bias; a.v = w.attn_energy; a.Wq = w.attn_query;
+    __nv_bfloat16* wcb = reinterpret_cast<__nv_bfloat16*>(extra + x.wcb);
+    __nv_bfloat16* wcb2 = reinterpret_cast<__nv_bfloat16*>(extra + x.wcb2);
+    __nv_bfloat16* memTf = reinterpret_cast<__nv_bfloat16*>(extra + x.memTf);
+    a.WcB = wcb; a.WcB2 = wcb2; a.memTf = memTf;
+    a.memb = reinterpret_cast<const __nv_bfloat16*>(pws + pl.memb); a.ldm = pl.ldm;
+    a.lengths = in.text_lengths; a.dctx_tot = dctx_tot; a.dq = dq; a.de = reinterpret_cast<float*>(extra + x.de);
+    a.barrier = reinterpret_cast<unsigned*>(extra + x.barrier); a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);
+    const float* wcombT = reinterpret_cast<const float*>(pws + pl.wcombT);
+    B200_CUDA(cudaMemsetAsync(a.barrier, 0, 256, st));
+    att_bwd_prep_kernel<<<148 * 4, 256, 0, st>>>(wcb, wcb2, memTf, wcombT, fws + fl.memT, B, L, A, s.K, x.MT);
+    B200_LAUNCH_CHECK();
+    const int L16 = x.MT * 16;
+    const size_t smem = ((size_t)4 * a.UK * (a.UN + 8) + (size_t)BT * (4 * a.UK + 8)) * 2 + (size_t)A * 40 * 2 + (size_t)32 * (A + 8) * 2 +
+                        (size_t)(L16 + 32) * 4 + (size_t)A * 9 * 4;
+    void* fn = (void*)att_bwd_loop_kernel;
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = KBA * NBA * a.NBH;
+    int per_sm = 0, dev = 0, sms = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B200_REQUIRE(per_sm * sms >= grid && grid >= B, "persistent attention backward: %d CTAs cannot be co-resident", grid);
+    void* params[] = {&a};
+    B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
+    B200_LAUNCH_CHECK();
+    // parallel post pass
+    AttPostArgs pp{};
+    pp.B = B; pp.T = T; pp.L = L; pp.A = A; pp.KC = s.K; pp.MT = x.MT;
+    pp.q = a.q; pp.cum = a.cum; pp.de = a.de; pp.bias = w.attn_bias; pp.v = w.attn_energy; pp.WcB = wcb; pp.memT = fws + fl.memT;
+    pp.lengths = in.text_lengths; pp.dmemT = dmemT;
+    pp.dWcomb_part = reinterpret_cast<float*>(extra + x.dwpart); pp.dv_part = reinterpret_cast<float*>(extra + x.dvpart);
+    B200_CUDA(cudaMemsetAsync(dmemT, 0, (size_t)B * L * A * 4, st));
+    B200_CUDA(cudaMemsetAsync(pp.dWcomb_part, 0, (size_t)B * x.MT * A * 32 * 4, st));
+    B200_CUDA(cudaMemsetAsync(pp.dv_part, 0, (size_t)B * x.MT * A * 4, st));
+    att_post_kernel<<<B * x.MT, PT, 0, st>>>(pp);
+    B200_LAUNCH_CHECK();
+    att_bwd_finish_kernel<<<1, 512, (size_t)A * 32 * 4, st>>>(dw.attn_location, dw.attn_loc_features, dw.attn_energy, pp.dWcomb_part,
+                                                             pp.dv_part, w.attn_location, w.attn_loc_features, B * x.MT, A, s.C, s.K);
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
 }
 
 size_t persist_bwd_gen_extra_bytes(const b200tts_decoder_shape& s) {

@@ -44,8 +44,21 @@ def _sigmoid(x):
     return 1.0 / (1.0 + torch.exp(-x))
 
 
+# Optional operand quantiser used to model the library's bf16 perf mode (operands rounded to bf16, fp32+ accumulate):
+# tests set QUANT = bf16_round so that the comparison isolates kernel bugs from the (expected) bf16 rounding.
+QUANT = None
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def _q(x):
+    return x if QUANT is None else QUANT(x)
+
+
 def _linear(x, w, b=None):
-    y = x @ w.transpose(0, 1)
+    y = _q(x) @ _q(w).transpose(0, 1)
     return y if b is None else y + b
 
 
@@ -153,7 +166,7 @@ def prenet(sd, prefix, x, p, keep0=None, keep1=None):
 def attention_reset(sd, prefix, memory):
     """AttentionBase.reset: memT = memory . Wm^T; cum = 0; ctx = 0."""
     B, L, M = memory.shape
-    memT = memory @ sd[f'{prefix}._memory.weight'].transpose(0, 1)
+    memT = _q(_linear(memory, sd[f'{prefix}._memory.weight']))     # the perf mode also stores the projection in bf16
     cum = torch.zeros(B, L, dtype=memory.dtype)
     ctx = torch.zeros(B, M, dtype=memory.dtype)
     return memT, cum, ctx
@@ -169,7 +182,7 @@ def attention_step(sd, prefix, query, memory, memT, cum, mask):
     B, L = cum.shape
     C, _, K = Wc.shape
     half = (K - 1) // 2
-    q = query @ Wq.transpose(0, 1)                     # [B, A]
+    q = query @ Wq.transpose(0, 1)                     # [B, A]  (kept in fp32 in both precision modes)
     cum_pad = torch.zeros(B, L + 2 * half, dtype=cum.dtype)
     cum_pad[:, half:half + L] = cum
     # f[b, c, l] = sum_k Wc[c, 0, k] * cum[b, l + k - half]   (zero outside [0, L))
@@ -183,7 +196,7 @@ def attention_step(sd, prefix, query, memory, memT, cum, mask):
     e_max = e.max(dim=1, keepdim=True).values
     ex = torch.exp(e - e_max)
     w = ex / ex.sum(dim=1, keepdim=True)
-    ctx = (w[:, :, None] * memory).sum(dim=1)          # bmm(w[B,1,L], memory[B,L,M])
+    ctx = (w[:, :, None] * _q(memory)).sum(dim=1)      # bmm(w[B,1,L], memory[B,L,M])
     return ctx, w, cum + w
 
 

@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--kind', default='dropout')
     ap.add_argument('--iters', type=int, default=3)
     ap.add_argument('--fwd-only', action='store_true')
+    ap.add_argument('--precision', default='fp32')
     a = ap.parse_args()
     import decoder_cases as dc
     from multilingual_text_to_speech_b200 import functional as F, _lib
@@ -27,6 +28,7 @@ def main():
     dev = torch.device('cuda:0')
     cfg, params, memory = dc._cuda_inputs(c, dev)
     target, lens = c.target.to(dev), c.lengths.to(dev)
+    _lib.set_precision(a.precision)
     for it in range(a.iters + 1):
         n0 = _lib.launch_count()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
