@@ -121,6 +121,9 @@ typedef struct {
 /* Bytes of the forward workspace; it also carries everything the backward pass re-reads. */
 size_t b200tts_decoder_workspace_bytes(const b200tts_decoder_shape* shape);
 size_t b200tts_decoder_bwd_workspace_bytes(const b200tts_decoder_shape* shape);
+/* Debug: byte offset, inside the decoder forward workspace, of the per-CTA phase cycle counters the persistent
+ * kernels leave behind ([2][148][8] int64: attention loop, generator loop). */
+size_t b200tts_debug_persist_profile_offset(const b200tts_decoder_shape* shape);
 
 int b200tts_decoder_forward(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
                             const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* out, void* workspace,

@@ -114,6 +114,10 @@ int b200tts_set_precision(int mode) {
     return B200TTS_OK;
 }
 int b200tts_get_precision(void) { return precision_mode(); }
+size_t b200tts_debug_persist_profile_offset(const b200tts_decoder_shape* shape) {
+    if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
+    return decoder_layout(*shape).persist * sizeof(float) + persist_layout(*shape).barrier + 256;
+}
 
 int b200tts_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                      int ldb, float beta, float* C, int ldc, const float* bias, int batch, long long strideA,

@@ -644,7 +644,7 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, M, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih + D, D + M, W(l.dctxs), M, 1.f));
 
     // ---- 3. attention LSTM + attention reverse loop ----
-    const bool persist_att = precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s) && persist_att_bwd_supported(s);
+    const bool persist_att = precision_mode() == B200TTS_PRECISION_BF16 && s.training && persist_supported(s) && persist_att_bwd_supported(s);
     if (persist_att) {
         // bf16 perf mode: cooperative weight-stationary kernel (tensor-core attention backward inside), then a parallel post pass
         const PersistLayout pl = persist_layout(s);

@@ -524,7 +524,9 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
     B200_TRY(launch_fill(c.at(l.cg), 0.f, BD, st));
     B200_TRY(launch_fill(c.at(l.cum), 0.f, (size_t)B * s.L, st));
 
-    const bool persistent = !sequential && precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s);
+    // the persistent forward rounds memory / memT to bf16; only the persistent backward recomputes with the same operands
+    const bool persistent = !sequential && precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s) &&
+                            (!s.training || persist_att_bwd_supported(s));
     if (persistent) {
         // bf16 perf mode: one cooperative, weight-stationary kernel per recurrence (decoder_persist.cu)
         unsigned char* pws = reinterpret_cast<unsigned char*>(c.at(l.persist));

@@ -50,6 +50,7 @@ struct LoopArgs {
     float* cum;                               // [T+1, B, L]
     float* align; long long align_bstride;    // [B, T, L]
     unsigned* barrier; int* abort_flag;
+    long long* prof;                          // optional [gridDim.x][8] per-phase cycle totals (thread 0 of each CTA)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -143,6 +144,12 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
     const int nchunks = (Kp + CHUNK - 1) / CHUNK;
     const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
     unsigned target = 0;
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#define PROF_MARK(slot)                                                      \
+    do {                                                                     \
+        if (p.prof && tid == 0) { const long long now = clock64(); prof_acc[slot] += now - prof_t; prof_t = now; } \
+    } while (0)
 
     for (int i = 0; i < p.T; ++i) {
         // =================== gate GEMM: acc[b, r] = sum_k act[b, k] * W[r, k] ===================
@@ -194,6 +201,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
             if (c + 2 < nchunks) issue(c + 2);
         }
 
+        PROF_MARK(0);
         // =================== tree reduction over the 8 warps (K split) ===================
         // accumulator element (mt, nt, e): b = mt*16 + g + 8*(e>>1), r = nt*8 + 2*tq + (e&1)
         const int g = lane >> 2, tq = lane & 3;
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
         }
         __syncthreads();
 
+        PROF_MARK(1);
         // =================== LSTM cell + regulariser (2 (b, u) pairs per thread) ===================
         for (int idx = tid; idx < BT * UNITS; idx += PT) {
             const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
@@ -284,7 +293,9 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                 }
             }
         }
+        PROF_MARK(2);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        PROF_MARK(3);
 
         if (ATT) {
             // =================== attention of utterance `cta` (CTAs 0 .. B-1) ===================
@@ -328,6 +339,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                     cump[j] = (l >= 0 && l < L) ? __ldcg(cum_prev + l) : 0.f;
                 }
                 __syncthreads();
+                PROF_MARK(4);
                 // energies: warp = 4 consecutive positions, lane = attention dims lane + 32 j
                 for (int l0 = warp * 4; l0 < len; l0 += 32) {
                     float sacc[4][4];
@@ -365,6 +377,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                     }
                 }
                 __syncthreads();
+                PROF_MARK(5);
                 float mx = -INFINITY;
                 for (int l = tid; l < len; l += PT) mx = fmaxf(mx, e[l]);
                 mx = block_max(mx, red);
@@ -411,9 +424,14 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                     p.actb[((size_t)(i + 1) * B + b) * Kp + m] = __float2bfloat16_rn(sctx);
                 }
             }
+            PROF_MARK(6);
             if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+            PROF_MARK(7);
         }
     }
+    if (p.prof && tid == 0)
+        for (int k = 0; k < 8; ++k) p.prof[(size_t)cta * 8 + k] = prof_acc[k];
+#undef PROF_MARK
 }
 
 size_t loop_smem_bytes(int Kp, int A, bool att, int L, int M, int KC) {
@@ -470,7 +488,7 @@ PersistLayout persist_layout(const b200tts_decoder_shape& s) {
     l.memTb = take(B * (size_t)s.L * s.A * 2);
     l.memb = take(B * (size_t)s.L * l.ldm * 2);
     l.wcombT = take((size_t)s.K * s.A * 4);
-    l.barrier = take(256);
+    l.barrier = take(256 + 148 * 8 * 8 * 2);   // barrier + abort flag, then 2 x [148][8] profile counters
     l.total = off;
     return l;
 }
@@ -532,6 +550,7 @@ int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     a.memTb = memTb; a.memb = memb; a.ldm = l.ldm; a.lengths = in.text_lengths; a.cum = ws + fl.cum;
     a.align = align; a.align_bstride = (long long)T * s.L;
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
+    a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256);
     return launch_loop(true, a, loop_smem_bytes(l.Kp_att, s.A, true, s.L, M, s.K), st);
 }
 
@@ -551,6 +570,7 @@ int persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     a.gates = ws + fl.gg; a.cstate = ws + fl.cg;
     a.mask_h = in.mask_gen_h; a.mask_c = in.mask_gen_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
+    a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256) + 148 * 8;
     return launch_loop(false, a, loop_smem_bytes(l.Kp_gen, s.A, false, 0, 0, 0), st);
 }
 

@@ -238,6 +238,7 @@ struct AttBwdArgs {
     const __nv_bfloat16* memTf;                           // [B][MT][32 lanes][64] fragment-major memory projection
     const __nv_bfloat16* memb; int ldm;                   // [B, L, ldm]
     const int* lengths;
+    int dqp_after_g;                                      // 1: dq partials live after the G tile buffer, 0: alias the scratch head
     float* dctx_tot;                                      // [T, B, M] out
     float* dq;                                            // [T, B, A] out
     float* de;                                            // [T, B, L] out (softmax-backward energies, consumed by the post pass)
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
     uint32_t* s_Pl = s_Ph + (L16 + 48);
     float* s_red = reinterpret_cast<float*>(s_Pl + (L16 + 48));   // [64]
     float* s_G = s_red + 64;                              // [L16][GLD]
-    float* s_dqp = scr;                                   // [8][A]: aliases s_dctx .. s_Ph once the tile loop is done
+    float* s_dqp = p.dqp_after_g ? s_G + (size_t)L16 * GLD : scr;   // [8][A]: after G if it fits, else aliases s_dctx .. s_Ph (dead by then)
     float* s_stage = reinterpret_cast<float*>(s_Pl);      // [L16]: d cum staging (Pl is dead by then)
 
     for (int i = p.T - 1; i >= 0; --i) {
@@ -818,6 +819,18 @@ AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s) {
     return x;
 }
 
+// where the [8][A] query-gradient partials go inside the attention scratch: 1 = after the G tiles, 0 = aliasing the
+// (dead) head of the scratch, -1 = the scratch does not fit at all
+static int att_bwd_dqp_mode(const b200tts_decoder_shape& s) {
+    const int UK = s.D / KBA, MT = (s.L + 15) / 16, L16 = MT * 16;
+    const size_t region = (size_t)BT * (4 * UK + 8) * 2 / 4;                     // floats available (the A-operand stage)
+    const size_t head = (size_t)((s.M + 3) & ~3) + 2 * L16 + 2 * s.A;            // s_dctx, s_w, s_de, s_qb, s_vv
+    const size_t base = head + 2 * (L16 + 48) + 64 + (size_t)L16 * GLD;
+    if (base + 8 * s.A <= region) return 1;
+    if (base <= region && (size_t)8 * s.A <= head + (L16 + 48)) return 0;       // must end before Pl (d cum staging)
+    return -1;
+}
+
 bool persist_att_bwd_supported(const b200tts_decoder_shape& s) {
     if (!persist_bwd_supported(s)) return false;
     if (s.A != 128 || s.K > 32 || s.B > 2 * BT || s.B * 8 > 3 * PT || s.D / 8 > KBA * NBA * ((s.B + BT - 1) / BT)) return false;
@@ -825,10 +838,7 @@ bool persist_att_bwd_supported(const b200tts_decoder_shape& s) {
     const int MT = (s.L + 15) / 16, L16 = MT * 16;
     const size_t fixed = ((size_t)4 * UK * (UN + 8) + (size_t)BT * (4 * UK + 8)) * 2 + (size_t)s.A * 40 * 2 + (size_t)32 * (s.A + 8) * 2 +
                          (size_t)(L16 + 32) * 4 + (size_t)s.A * 9 * 4;
-    const size_t head = (size_t)((s.M + 3) & ~3) + 2 * L16 + 2 * s.A;          // s_dctx, s_w, s_de, s_qb, s_vv
-    const size_t scratch = (head + 2 * (L16 + 48) + 64 + (size_t)L16 * GLD) * 4;
-    if ((size_t)8 * s.A > head + (L16 + 48)) return false;                       // dq partials must end before Pl (staging)
-    return fixed <= 227 * 1024 && scratch <= (size_t)BT * (4 * UK + 8) * 2;
+    return fixed <= 227 * 1024 && att_bwd_dqp_mode(s) >= 0;
 }
 
 int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
@@ -855,6 +865,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     __nv_bfloat16* memTf = reinterpret_cast<__nv_bfloat16*>(extra + x.memTf);
     a.WcB = wcb; a.WcB2 = wcb2; a.memTf = memTf;
     a.memb = reinterpret_cast<const __nv_bfloat16*>(pws + pl.memb); a.ldm = pl.ldm;
+    a.dqp_after_g = att_bwd_dqp_mode(s);
     a.lengths = in.text_lengths; a.dctx_tot = dctx_tot; a.dq = dq; a.de = reinterpret_cast<float*>(extra + x.de);
     a.barrier = reinterpret_cast<unsigned*>(extra + x.barrier); a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);
     const float* wcombT = reinterpret_cast<const float*>(pws + pl.wcombT);

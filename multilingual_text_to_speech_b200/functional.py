@@ -183,6 +183,8 @@ class DecoderFunction(torch.autograd.Function):
             check(lib.b200tts_decoder_forward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
                                               ctypes.byref(outs), ptr(ws), nbytes, _stream()), 'b200tts_decoder_forward')
         ctx.cfg, ctx.dims, ctx.ws = cfg, dims, ws
+        if PROFILE.get('keep_ws'):
+            PROFILE['last_ws'], PROFILE['last_shape'] = ws, shape
         ctx.save_for_backward(memory, target, text_lengths, align, *params)
         ctx.set_materialize_grads(False)
         return spec, stop, align

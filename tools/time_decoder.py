@@ -46,6 +46,21 @@ def main():
         print(f'iter {it}: fwd {e0.elapsed_time(e1):.2f} ms  bwd {e1.elapsed_time(e2):.2f} ms  host-enqueue {1e3 * (t1 - t0):.1f} ms '
               f'wall {1e3 * (t2 - t0):.1f} ms  launches {_lib.launch_count() - n0}  '
               f'frames/s {a.B * a.T / (t2 - t0):.0f}', flush=True)
+        if a.precision == 'bf16' and it == a.iters:
+            import ctypes
+            F.PROFILE['keep_ws'] = True
+            with torch.no_grad():
+                F.decoder_forward(cfg, memory, target, lens, params)
+            torch.cuda.synchronize()
+            off = _lib.load().b200tts_debug_persist_profile_offset(ctypes.byref(F.PROFILE['last_shape']))
+            raw = F.PROFILE['last_ws'][off:off + 2 * 148 * 8 * 8].view(torch.int64).view(2, 148, 8).cpu().double()
+            names = ['gemm', 'reduce', 'cell+q', 'barrier1', 'attn:q/load', 'attn:energy', 'attn:softmax+ctx', 'barrier2']
+            for k, loop in enumerate(('att', 'gen')):
+                act = raw[k][raw[k].sum(1) > 0]
+                if len(act):
+                    print(f'{loop} loop: cycles/step by phase, CTA0 | mean | max over CTAs')
+                    for j, nme in enumerate(names):
+                        print(f'   {nme:18s} {raw[k][0, j] / a.T:9.0f} {act[:, j].mean() / a.T:9.0f} {act[:, j].max() / a.T:9.0f}')
         for p in params:
             p.grad = None
         memory.grad = None
