@@ -37,6 +37,8 @@ def parse():
     ap.add_argument('--frames', type=int, default=900)
     ap.add_argument('--regularization', default='zoneout', choices=['zoneout', 'dropout'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help="bf16: tensor-core operands, fp32 master/state (BASELINE configs[1]); fp32: exact parity mode")
     return ap.parse_args()
 
 
@@ -210,6 +212,7 @@ def run_b200(a):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     hp, B, L, T = workload(a)
+    _lib.set_precision(a.precision)
     torch.manual_seed(0)
     model = Tacotron().to(dev).train()
     crit = TacotronLoss(hp.guided_attention_steps, hp.guided_attention_toleration, hp.guided_attention_gain)
@@ -281,10 +284,11 @@ def run_b200(a):
                     'traffic': None, 'kernel': 'decoder forward (b200tts_decoder_forward: attention-LSTM + attention + generator-LSTM '
                     'loop, all launches)', 'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': dur * 1e3, 'peak_source': peak_src}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
-                'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                'data': 'synthetic',
+                'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': {'workload': f'{a.config} train fwd+bwd, B={B}/GPU L={L} T={T} ({a.regularization} cells), tf=1.0',
                            'global_batch': world * B, 'parallelism': f'dp{world}',
+                           'precision': 'bf16 tensor-core operands, fp32 accumulate / master weights / states' if a.precision == 'bf16' else 'fp32',
                            'l2': 'per-step working set (~5 GB of activations) >> 126 MB L2, no flush needed',
                            'note': 'batch 64 is invalid for the 10-language grouped encoder (B % G == 0); shipped batch 60 used'},
                 'clocks': clocks, 'gpu_launches': int(launches),

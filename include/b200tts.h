@@ -124,6 +124,8 @@ size_t b200tts_decoder_bwd_workspace_bytes(const b200tts_decoder_shape* shape);
 /* Debug: byte offset, inside the decoder forward workspace, of the per-CTA phase cycle counters the persistent
  * kernels leave behind ([2][148][8] int64: attention loop, generator loop). */
 size_t b200tts_debug_persist_profile_offset(const b200tts_decoder_shape* shape);
+/* Same for the backward workspace: which = 0 generator loop, 1 attention loop ([148][8] int64 each). */
+size_t b200tts_debug_persist_bwd_profile_offset(const b200tts_decoder_shape* shape, int which);
 
 int b200tts_decoder_forward(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
                             const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* out, void* workspace,

@@ -101,6 +101,7 @@ __global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsi
 
 }  // namespace b200tts
 
+namespace b200tts { size_t decoder_bwd_profile_offset(const b200tts_decoder_shape& s, int which); }
 using namespace b200tts;
 
 extern "C" {
@@ -114,6 +115,10 @@ int b200tts_set_precision(int mode) {
     return B200TTS_OK;
 }
 int b200tts_get_precision(void) { return precision_mode(); }
+size_t b200tts_debug_persist_bwd_profile_offset(const b200tts_decoder_shape* shape, int which) {
+    if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
+    return decoder_bwd_profile_offset(*shape, which);
+}
 size_t b200tts_debug_persist_profile_offset(const b200tts_decoder_shape* shape) {
     if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
     return decoder_layout(*shape).persist * sizeof(float) + persist_layout(*shape).barrier + 256;

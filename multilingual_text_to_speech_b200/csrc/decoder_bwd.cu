@@ -554,6 +554,12 @@ int wgemm(cudaStream_t st, const BwdLayout& l, float* ws, int transA, int transB
 }  // namespace
 
 size_t decoder_bwd_workspace_floats(const b200tts_decoder_shape& s) { return bwd_layout(s).total; }
+// byte offset of the phase counters of the persistent backward kernels inside the backward workspace (0: generator, 1: attention)
+size_t decoder_bwd_profile_offset(const b200tts_decoder_shape& s, int which) {
+    const BwdLayout l = bwd_layout(s);
+    if (which == 0) return l.pextra * sizeof(float) + persist_bwd_gen_extra_bytes(s) - 148 * 8 * 8;
+    return l.pextra2 * sizeof(float) + att_bwd_extra(s).barrier + 256;
+}
 
 int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                           const b200tts_decoder_outputs& fwd_out, const b200tts_decoder_output_grads& dout, const float* fws,

@@ -28,6 +28,9 @@ struct PersistLayout {
     size_t memTb;    // bf16 [B, L, A]
     size_t memb;     // bf16 [B, L, ldm]
     size_t wcombT;   // f32  [K, A]
+    size_t wcb;      // bf16 [A, 40]   Wcomb[a][k]
+    size_t memTf;    // bf16 [B, MT, 32, 64] fragment-major memory projection
+    int MT;
     size_t barrier;  // grid-barrier counter (+ abort flag at +128 B)
     size_t total;
 };

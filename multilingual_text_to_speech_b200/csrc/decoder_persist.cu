@@ -25,8 +25,10 @@ constexpr int PT = 256;             // threads per CTA
 constexpr int UNITS = 16;           // hidden units per CTA
 constexpr int ROWS = 4 * UNITS;     // gate rows per CTA
 constexpr int BT = 32;              // utterances per CTA
-constexpr int CHUNK = 256;          // activation columns per cp.async stage
+constexpr int CHUNK = 128;          // activation columns per cp.async stage (8 k-steps: one per warp)
 constexpr int ALD = CHUNK + 8;      // bf16 row stride of an activation stage
+constexpr int ATT_STAGES = 4;       // 4 x 128 columns in flight (shared memory is almost full: 169 KB of weights)
+constexpr int GEN_STAGES = 8;       // the whole 1024-column operand in flight
 
 struct LoopArgs {
     int B, T, D, K, Kp, RB, NBH;
@@ -42,9 +44,9 @@ struct LoopArgs {
     const float* Wq;                          // [A, D]
     float* qpart;                             // [RB, B, A]
     float* qsave;                             // [T, B, A]
-    const float* WcombT;                      // [KC, A]  (Wloc . Wc)^T
+    const __nv_bfloat16* WcB;                 // [A][40] bf16 Wcomb[a][k] (k contiguous, zero beyond KC)
+    const __nv_bfloat16* memTf; int MT;       // [B][MT][32][64] fragment-major bf16 memory projection
     const float* bias; const float* v;        // [A]
-    const __nv_bfloat16* memTb;               // [B, L, A]
     const __nv_bfloat16* memb; int ldm;       // [B, L, ldm]
     const int* lengths;
     float* cum;                               // [T+1, B, L]
@@ -76,6 +78,16 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Monotonic-counter grid barrier.  Returns false if the watchdog fired (caller must leave the loop).
 __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag) {
     __shared__ int s_ok;
@@ -104,7 +116,7 @@ struct Smem {
     float* sum;            // [BT][ROWS + 1]
 };
 
-template <bool ATT>
+template <bool ATT, int NSTAGE>
 __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,11 +129,11 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
     Smem s;
     size_t off = 0;
     s.W = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += (size_t)ROWS * WLD * 2;
-    s.act = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += (size_t)2 * BT * ALD * 2;
-    s.hs = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (UNITS + 1) * 4;
+    s.act = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += (size_t)NSTAGE * BT * ALD * 2;
+    s.hs = reinterpret_cast<float*>(smem_raw + off); off += (size_t)UNITS * (BT + 4) * 4;      // [UNITS][BT + 4] (transposed)
     s.wq = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)p.A * (UNITS + 1) * 4 : 0;
-    float* WcT = reinterpret_cast<float*>(smem_raw + off);     // [KC][A] resident (ATT only)
-    float* scratch = reinterpret_cast<float*>(s.act);          // 2*BT*ALD*2 B = 33,792 B = 8448 floats
+    __nv_bfloat16* sWcB = reinterpret_cast<__nv_bfloat16*>(smem_raw + off);     // [A][40] resident (ATT only)
+    float* scratch = reinterpret_cast<float*>(s.act);          // >= 4 * BT * ALD * 2 B = 34,816 B = 8704 floats
     s.sum = scratch + 4096;                                    // [BT][ROWS+1] = 2080 floats, past the last reduction round's reads
 
     // ---- one-time: resident weight slice (fp32 -> bf16), query-projection slice ----
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
             const int a = idx / UNITS, u = idx % UNITS;
             s.wq[a * (UNITS + 1) + u] = (u0 + u < D) ? p.Wq[(size_t)a * D + u0 + u] : 0.f;
         }
-        for (int idx = tid; idx < p.KC * p.A; idx += PT) WcT[idx] = p.WcombT[idx];
+        for (int idx = tid; idx < p.A * 40; idx += PT) sWcB[idx] = p.WcB[idx];
     }
     __syncthreads();
 
@@ -161,25 +173,48 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
 
+        // prefetch the epilogue operands of this thread's (b, u) pairs: their DRAM latency hides behind the GEMM
+        float pre[2][6];
+        uint8_t pm[2][2];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            const int idx = tid + e2 * PT;
+            const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
+            pm[e2][0] = 1; pm[e2][1] = 1;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) pre[e2][j] = 0.f;
+            if (idx < BT * UNITS && b < B && u < D) {
+                const size_t g0 = ((size_t)i * B + b) * 4 * D + u, mi = ((size_t)i * B + b) * D + u;
+                pre[e2][0] = p.gates[g0]; pre[e2][1] = p.gates[g0 + D]; pre[e2][2] = p.gates[g0 + 2 * D]; pre[e2][3] = p.gates[g0 + 3 * D];
+                pre[e2][4] = p.cstate[mi];
+                if (p.kind == B200TTS_CELL_ZONEOUT) pre[e2][5] = p.actf[((size_t)i * B + b) * p.ldf + p.hcol + u];
+                if (p.training && p.mask_h) pm[e2][0] = p.mask_h[mi];
+                if (p.training && p.mask_c) pm[e2][1] = p.mask_c[mi];
+            }
+        }
+
         const __nv_bfloat16* arow = p.actb + ((size_t)i * B + b0) * Kp;
         auto issue = [&](int c) {
-            __nv_bfloat16* dst = s.act + (size_t)(c & 1) * BT * ALD;
-            const int kbase = c * CHUNK;
-            const int segs = min(CHUNK, Kp - kbase) / 8;            // 16-byte segments per row in this chunk
-            for (int idx = tid; idx < BT * segs; idx += PT) {
-                const int r = idx / segs, sg = idx % segs;
-                __nv_bfloat16* d = dst + r * ALD + sg * 8;
-                if (b0 + r < B) cp_async16(d, arow + (size_t)r * Kp + kbase + sg * 8);
-                else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+            if (c < nchunks) {
+                __nv_bfloat16* dst = s.act + (size_t)(c % NSTAGE) * BT * ALD;
+                const int kbase = c * CHUNK;
+                const int segs = min(CHUNK, Kp - kbase) / 8;            // 16-byte segments per row in this chunk
+                for (int idx = tid; idx < BT * segs; idx += PT) {
+                    const int r = idx / segs, sg = idx % segs;
+                    __nv_bfloat16* d = dst + r * ALD + sg * 8;
+                    if (b0 + r < B) cp_async16(d, arow + (size_t)r * Kp + kbase + sg * 8);
+                    else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
-            cp_async_commit();
+            cp_async_commit();          // always commit (possibly empty) so that the group count stays uniform
         };
-        issue(0);
-        if (nchunks > 1) issue(1);
+#pragma unroll
+        for (int c = 0; c < NSTAGE - 1; ++c) issue(c);
         for (int c = 0; c < nchunks; ++c) {
-            if (c + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
-            __syncthreads();
-            const __nv_bfloat16* ab = s.act + (size_t)(c & 1) * BT * ALD;
+            cp_async_wait<NSTAGE - 2>();
+            __syncthreads();            // chunk c has landed for everyone; everyone is done computing chunk c-1
+            issue(c + NSTAGE - 1);      // refills the stage chunk c-1 used
+            const __nv_bfloat16* ab = s.act + (size_t)(c % NSTAGE) * BT * ALD;
             const int kbase = c * CHUNK;
             const int ksteps = min(CHUNK, Kp - kbase) / 16;
             for (int ks = warp; ks < ksteps; ks += 8) {
@@ -197,9 +232,9 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) mma_bf16(acc[mt][nt], af[mt], bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
             }
-            __syncthreads();
-            if (c + 2 < nchunks) issue(c + 2);
         }
+        cp_async_wait<0>();
+        __syncthreads();                // the stages are free: the reduction scratch aliases them
 
         PROF_MARK(0);
         // =================== tree reduction over the 8 warps (K split) ===================
@@ -241,28 +276,30 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
 
         PROF_MARK(1);
         // =================== LSTM cell + regulariser (2 (b, u) pairs per thread) ===================
-        for (int idx = tid; idx < BT * UNITS; idx += PT) {
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            const int idx = tid + e2 * PT;
+            if (idx >= BT * UNITS) continue;
             const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
             float hs = 0.f;
             if (b < B && u < D) {
                 const size_t g0 = ((size_t)i * B + b) * 4 * D + u;
-                const float zi = p.gates[g0] + s.sum[bl * (ROWS + 1) + uu];
-                const float zf = p.gates[g0 + D] + s.sum[bl * (ROWS + 1) + UNITS + uu];
-                const float zg = p.gates[g0 + 2 * D] + s.sum[bl * (ROWS + 1) + 2 * UNITS + uu];
-                const float zo = p.gates[g0 + 3 * D] + s.sum[bl * (ROWS + 1) + 3 * UNITS + uu];
+                const float zi = pre[e2][0] + s.sum[bl * (ROWS + 1) + uu];
+                const float zf = pre[e2][1] + s.sum[bl * (ROWS + 1) + UNITS + uu];
+                const float zg = pre[e2][2] + s.sum[bl * (ROWS + 1) + 2 * UNITS + uu];
+                const float zo = pre[e2][3] + s.sum[bl * (ROWS + 1) + 3 * UNITS + uu];
                 const float gi = sigmoidf_acc(zi), gf = sigmoidf_acc(zf), gg = tanhf(zg), go = sigmoidf_acc(zo);
                 const size_t bu = (size_t)b * D + u;
-                const float cp = p.cstate[(size_t)i * B * D + bu];
+                const float cp = pre[e2][4];
                 float cn = gf * cp + gi * gg;
                 float hn = go * tanhf(cn);
                 p.gates[g0] = gi; p.gates[g0 + D] = gf; p.gates[g0 + 2 * D] = gg; p.gates[g0 + 3 * D] = go;
-                const size_t mi = (size_t)i * B * D + bu;
                 if (p.kind == B200TTS_CELL_ZONEOUT) {
-                    const float hp = p.actf[((size_t)i * B + b) * p.ldf + p.hcol + u];
+                    const float hp = pre[e2][5];
                     if (p.training) {
                         float dh = hn - hp, dc = cn - cp;
-                        if (p.mask_h) dh = dh * (float)p.mask_h[mi] * inv_h;
-                        if (p.mask_c) dc = dc * (float)p.mask_c[mi] * inv_c;
+                        if (p.mask_h) dh = dh * (float)pm[e2][0] * inv_h;
+                        if (p.mask_c) dc = dc * (float)pm[e2][1] * inv_c;
                         hn = (1.f - p.rate_h) * dh + hp;
                         cn = (1.f - p.rate_c) * dc + cp;
                     } else {
@@ -270,27 +307,38 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                         cn = p.rate_c * cp + (1.f - p.rate_c) * cn;
                     }
                 } else if (p.training && p.mask_h) {
-                    hn = hn * (float)p.mask_h[mi] * inv_h;
+                    hn = hn * (float)pm[e2][0] * inv_h;
                 }
                 p.cstate[(size_t)(i + 1) * B * D + bu] = cn;
                 p.actf[((size_t)(i + 1) * B + b) * p.ldf + p.hcol + u] = hn;
                 p.actb[((size_t)(i + 1) * B + b) * Kp + p.hcol + u] = __float2bfloat16_rn(hn);
                 hs = hn;
             }
-            if (ATT) s.hs[bl * (UNITS + 1) + uu] = hs;
+            if (ATT) s.hs[uu * (BT + 4) + bl] = hs;
         }
 
         if (ATT) {
             __syncthreads();
-            // partial query projection of this CTA's 16 hidden units: qpart[rb, b, a]
-            for (int idx = tid; idx < BT * p.A; idx += PT) {
-                const int bl = idx / p.A, a = idx % p.A;
-                if (b0 + bl < B) {
-                    float q = 0.f;
+            // partial query projection of this CTA's 16 hidden units: qpart[rb, b, a]; thread = (a, 16 utterances)
+            for (int idx = tid; idx < p.A * (BT / 16); idx += PT) {
+                const int a = idx % p.A, bg = idx / p.A;
+                float qa[16];
 #pragma unroll
-                    for (int uu = 0; uu < UNITS; ++uu) q = fmaf(s.hs[bl * (UNITS + 1) + uu], s.wq[a * (UNITS + 1) + uu], q);
-                    p.qpart[((size_t)rb * B + b0 + bl) * p.A + a] = q;
+                for (int j = 0; j < 16; ++j) qa[j] = 0.f;
+#pragma unroll
+                for (int uu = 0; uu < UNITS; ++uu) {
+                    const float wv = s.wq[a * (UNITS + 1) + uu];
+                    const float4* h4 = reinterpret_cast<const float4*>(&s.hs[uu * (BT + 4) + bg * 16]);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 hv = h4[j4];
+                        qa[4 * j4] = fmaf(wv, hv.x, qa[4 * j4]); qa[4 * j4 + 1] = fmaf(wv, hv.y, qa[4 * j4 + 1]);
+                        qa[4 * j4 + 2] = fmaf(wv, hv.z, qa[4 * j4 + 2]); qa[4 * j4 + 3] = fmaf(wv, hv.w, qa[4 * j4 + 3]);
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (b0 + bg * 16 + j < B) p.qpart[((size_t)rb * B + b0 + bg * 16 + j) * p.A + a] = qa[j];
             }
         }
         PROF_MARK(2);
@@ -300,15 +348,17 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
         if (ATT) {
             // =================== attention of utterance `cta` (CTAs 0 .. B-1) ===================
             if (cta < B) {
-                const int b = cta, L = p.L, A = p.A, M = p.M, KC = p.KC, half = (KC - 1) / 2;
+                const int b = cta, L = p.L, A = p.A, M = p.M, half = (p.KC - 1) / 2;
                 float* qb = scratch;                       // [A]
                 float* vv = qb + A;                        // [A]
-                float* cump = vv + A;                      // [L + KC - 1] (+3)
-                float* e = cump + ((L + KC - 1 + 3) & ~3); // [L] (+3)
-                float* red = e + ((L + 3) & ~3);           // [64]
+                float* e = vv + A;                         // [L16]
+                float* red = e + p.MT * 16;                // [64]
                 float* cred = red + 64;                    // [8][M]  (first used as [PT/A][A] query partials)
+                uint32_t* Ph = reinterpret_cast<uint32_t*>(cred + 8 * M);     // [L16 + 48] Toeplitz pair arrays (hi / lo bf16 split)
+                uint32_t* Pl = Ph + (p.MT * 16 + 48);
                 int len = p.lengths[b];
                 len = len < 0 ? 0 : (len > L ? L : len);
+                const float* cum_prev = p.cum + ((size_t)i * B + b) * L;
                 {   // q[a] = sum over the RB per-CTA partial projections; 8 independent loads in flight per thread
                     const int nsl = PT / A > 0 ? PT / A : 1;            // slices of the RB range (2 for A = 128)
                     const int a = tid % A, sl = tid / A;
@@ -324,6 +374,17 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                         }
                         cred[sl * A + a] = ((qs[0] + qs[1]) + (qs[2] + qs[3])) + ((qs[4] + qs[5]) + (qs[6] + qs[7]));
                     }
+                    // cumulative weights -> (hi, lo) bf16 pairs: Ph[x] = (c[x], c[x+1]) with c[j] = cum[j - half]
+                    for (int x = tid; x < p.MT * 16 + 48; x += PT) {
+                        float c0 = 0.f, c1 = 0.f;
+                        const int la = x - half, lb = x + 1 - half;
+                        if (la >= 0 && la < L) c0 = __ldcg(cum_prev + la);
+                        if (lb >= 0 && lb < L) c1 = __ldcg(cum_prev + lb);
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
+                        __nv_bfloat162 hp2; hp2.x = h0; hp2.y = h1;
+                        Ph[x] = *reinterpret_cast<uint32_t*>(&hp2);
+                        Pl[x] = pack2(c0 - __bfloat162float(h0), c1 - __bfloat162float(h1));
+                    }
                     __syncthreads();
                     for (int a2 = tid; a2 < A; a2 += PT) {
                         float q = 0.f;
@@ -333,47 +394,55 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                         vv[a2] = p.v[a2];
                     }
                 }
-                const float* cum_prev = p.cum + ((size_t)i * B + b) * L;
-                for (int j = tid; j < L + KC - 1; j += PT) {
-                    const int l = j - half;
-                    cump[j] = (l >= 0 && l < L) ? __ldcg(cum_prev + l) : 0.f;
-                }
                 __syncthreads();
                 PROF_MARK(4);
-                // energies: warp = 4 consecutive positions, lane = attention dims lane + 32 j
-                for (int l0 = warp * 4; l0 < len; l0 += 32) {
-                    float sacc[4][4];
+                // energies on the tensor cores: S[l, a] = sum_k cumpad[l + k] * Wcomb[a, k]; warp owns position tiles {warp, warp+8}
+                {
+                    const int g = lane >> 2, tq = lane & 3;
+                    const int mtiles = (len + 15) / 16;
+                    for (int mt = warp; mt < mtiles; mt += 8) {
+                        const int l0 = mt * 16;
+                        float sacc[16][4];
 #pragma unroll
-                    for (int ii = 0; ii < 4; ++ii)
+                        for (int nt = 0; nt < 16; ++nt)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) sacc[ii][j] = 0.f;
-                    float c0 = cump[l0], c1 = cump[l0 + 1], c2 = cump[l0 + 2];
-                    for (int k = 0; k < KC; ++k) {
-                        const float c3 = cump[min(l0 + k + 3, L + KC - 2)];
-                        float w[4];
+                            for (int e4 = 0; e4 < 4; ++e4) sacc[nt][e4] = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) w[j] = (lane + 32 * j < A) ? WcT[k * A + lane + 32 * j] : 0.f;
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const int x = l0 + ks * 16 + g + 2 * tq;
+                            const uint32_t ah[4] = {Ph[x], Ph[x + 8], Ph[x + 8], Ph[x + 16]};
+                            const uint32_t al[4] = {Pl[x], Pl[x + 8], Pl[x + 8], Pl[x + 16]};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            sacc[0][j] = fmaf(c0, w[j], sacc[0][j]); sacc[1][j] = fmaf(c1, w[j], sacc[1][j]);
-                            sacc[2][j] = fmaf(c2, w[j], sacc[2][j]); sacc[3][j] = fmaf(c3, w[j], sacc[3][j]);
-                        }
-                        c0 = c1; c1 = c2; c2 = c3;
-                    }
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const int l = l0 + ii;
-                        if (l < len) {
-                            float ep = 0.f;
-                            const __nv_bfloat16* mt = p.memTb + ((size_t)b * L + l) * A;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int a = lane + 32 * j;
-                                if (a < A) ep = fmaf(vv[a], tanhf(sacc[ii][j] + qb[a] + __bfloat162float(mt[a])), ep);
+                            for (int np = 0; np < 8; ++np) {
+                                uint32_t bfr[4];
+                                ldmatrix_x4(bfr[0], bfr[1], bfr[2], bfr[3],
+                                            sWcB + (size_t)(np * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
+                                mma_bf16(sacc[2 * np], ah, bfr[0], bfr[1]);
+                                mma_bf16(sacc[2 * np], al, bfr[0], bfr[1]);
+                                mma_bf16(sacc[2 * np + 1], ah, bfr[2], bfr[3]);
+                                mma_bf16(sacc[2 * np + 1], al, bfr[2], bfr[3]);
                             }
-                            ep = warp_sum(ep);
-                            if (lane == 0) e[l] = ep;
                         }
+                        const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + mt) * 32 + lane) * 64);
+                        float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const uint4 raw = mf[c4];
+                            const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+                                const int nt = 2 * c4 + hf, a0 = nt * 8 + 2 * tq;
+                                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf]));
+                                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf + 1]));
+                                e0 = fmaf(vv[a0], tanh_fast(sacc[nt][0] + qb[a0] + m01.x), e0);
+                                e0 = fmaf(vv[a0 + 1], tanh_fast(sacc[nt][1] + qb[a0 + 1] + m01.y), e0);
+                                e1 = fmaf(vv[a0], tanh_fast(sacc[nt][2] + qb[a0] + m23.x), e1);
+                                e1 = fmaf(vv[a0 + 1], tanh_fast(sacc[nt][3] + qb[a0 + 1] + m23.y), e1);
+                            }
+                        }
+                        e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+                        e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+                        if (tq == 0) { e[l0 + g] = e0; e[l0 + g + 8] = e1; }
                     }
                 }
                 __syncthreads();
@@ -389,26 +458,38 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                     const float w = l < len ? e[l] / sum : 0.f;
                     e[l] = w;
                     p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
-                    cum_next[l] = cump[l + half] + w;
+                    cum_next[l] = __ldcg(cum_prev + l) + w;
                 }
                 __syncthreads();
-                // context: warp per position, lanes over pairs of memory columns
+                // context: warp per position (4 positions per batch so that 4 x 5 row loads are in flight), lanes over column pairs
                 float cacc[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) cacc[j] = 0.f;
-#pragma unroll 4
-                for (int l = warp; l < len; l += 8) {
-                    const float w = e[l];
-                    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + l) * p.ldm);
+                for (int lb = warp; lb < len; lb += 32) {
+                    __nv_bfloat162 rv[4][8];
+                    float wl[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int m2 = lane + 32 * j;
-                        if (2 * m2 < M) {
-                            const float2 v2 = __bfloat1622float2(row[m2]);
-                            cacc[2 * j] = fmaf(w, v2.x, cacc[2 * j]);
-                            cacc[2 * j + 1] = fmaf(w, v2.y, cacc[2 * j + 1]);
+                    for (int r4 = 0; r4 < 4; ++r4) {
+                        const int l = lb + 8 * r4;
+                        wl[r4] = l < len ? e[l] : 0.f;
+                        const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + (l < len ? l : 0)) * p.ldm);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int m2 = lane + 32 * j;
+                            if (2 * m2 < M) rv[r4][j] = row[m2];
                         }
                     }
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; ++r4)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int m2 = lane + 32 * j;
+                            if (2 * m2 < M) {
+                                const float2 v2 = __bfloat1622float2(rv[r4][j]);
+                                cacc[2 * j] = fmaf(wl[r4], v2.x, cacc[2 * j]);
+                                cacc[2 * j + 1] = fmaf(wl[r4], v2.y, cacc[2 * j + 1]);
+                            }
+                        }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -434,13 +515,15 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
 #undef PROF_MARK
 }
 
-size_t loop_smem_bytes(int Kp, int A, bool att, int L, int M, int KC) {
-    size_t b = (size_t)ROWS * (Kp + 8) * 2 + (size_t)2 * BT * ALD * 2 + (size_t)BT * (UNITS + 1) * 4;
+size_t loop_smem_bytes(int Kp, int A, bool att, int L, int M, int nstage) {
+    size_t b = (size_t)ROWS * (Kp + 8) * 2 + (size_t)nstage * BT * ALD * 2 + (size_t)UNITS * (BT + 4) * 4;
+    if ((size_t)nstage * BT * ALD * 2 < (size_t)4 * BT * ROWS * 4) return 0;   // reduction scratch (the gate sums live inside it)
     if (att) {
-        b += (size_t)A * (UNITS + 1) * 4 + (size_t)KC * A * 4;
+        b += (size_t)A * (UNITS + 1) * 4 + (size_t)A * 40 * 2;
+        const int L16 = (L + 15) / 16 * 16;
         // the attention scratch aliases the activation stages; it must fit there
-        const size_t need = ((size_t)2 * A + ((L + KC - 1 + 3) & ~3) + ((L + 3) & ~3) + 64 + (size_t)8 * M) * 4;
-        if (need > (size_t)2 * BT * ALD * 2 || PT % A != 0) return 0;
+        const size_t need = ((size_t)2 * A + L16 + 64 + (size_t)8 * M + 2 * (L16 + 48)) * 4;
+        if (need > (size_t)nstage * BT * ALD * 2 || PT % A != 0 || A != 128) return 0;
     }
     return b;
 }
@@ -452,6 +535,25 @@ __global__ void f32_to_bf16_rows_kernel(__nv_bfloat16* __restrict__ dst, int ldd
         const size_t r = idx / ldd;
         const int c = idx % ldd;
         dst[idx] = __float2bfloat16_rn(c < cols ? src[r * lds + c] : 0.f);
+    }
+}
+
+// WcB[a][40] = bf16 Wcomb[a][k] (zero for k >= KC);  memTf = fragment-major bf16 memory projection:
+// memTf[b][mt][lane][nt*4 + e] = memT[b][mt*16 + (lane>>2) + 8*(e>>1)][nt*8 + 2*(lane&3) + (e&1)]
+__global__ void att_prep_kernel(__nv_bfloat16* __restrict__ WcB, __nv_bfloat16* __restrict__ memTf, const float* __restrict__ WcombT,
+                                const float* __restrict__ memT, int B, int L, int A, int KC, int MT) {
+    const size_t n1 = (size_t)A * 40, n3 = (size_t)B * MT * 32 * 64;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n1 + n3; idx += (size_t)gridDim.x * blockDim.x) {
+        if (idx < n1) {
+            const int a = idx / 40, k = idx % 40;
+            WcB[idx] = __float2bfloat16_rn(k < KC ? WcombT[(size_t)k * A + a] : 0.f);
+        } else {
+            const size_t j = idx - n1;
+            const int v = j % 64, lane = (j / 64) % 32, mt = (j / (64 * 32)) % MT, b = j / ((size_t)64 * 32 * MT);
+            const int nt = v / 4, e = v % 4, g = lane >> 2, tq = lane & 3;
+            const int l = mt * 16 + g + 8 * (e >> 1), a = nt * 8 + 2 * tq + (e & 1);
+            memTf[j] = __float2bfloat16_rn((l < L && a < A) ? memT[((size_t)b * L + l) * A + a] : 0.f);
+        }
     }
 }
 
@@ -488,6 +590,9 @@ PersistLayout persist_layout(const b200tts_decoder_shape& s) {
     l.memTb = take(B * (size_t)s.L * s.A * 2);
     l.memb = take(B * (size_t)s.L * l.ldm * 2);
     l.wcombT = take((size_t)s.K * s.A * 4);
+    l.wcb = take((size_t)s.A * 40 * 2);
+    l.MT = (s.L + 15) / 16;
+    l.memTf = take((size_t)s.B * l.MT * 32 * 64 * 2);
     l.barrier = take(256 + 148 * 8 * 8 * 2);   // barrier + abort flag, then 2 x [148][8] profile counters
     l.total = off;
     return l;
@@ -498,12 +603,13 @@ bool persist_supported(const b200tts_decoder_shape& s) {
     const int RB = s.D / UNITS, NBH = (s.B + BT - 1) / BT;
     if (RB * NBH > 148 || s.B > RB * NBH) return false;
     const PersistLayout l = persist_layout(s);
-    const size_t a = loop_smem_bytes(l.Kp_att, s.A, true, s.L, s.M, s.K), g = loop_smem_bytes(l.Kp_gen, s.A, false, 0, 0, 0);
-    return a != 0 && a <= 227 * 1024 && g <= 227 * 1024;
+    if (s.K > 32) return false;
+    const size_t a = loop_smem_bytes(l.Kp_att, s.A, true, s.L, s.M, ATT_STAGES), g = loop_smem_bytes(l.Kp_gen, s.A, false, 0, 0, GEN_STAGES);
+    return a != 0 && g != 0 && a <= 227 * 1024 && g <= 227 * 1024;
 }
 
 static int launch_loop(bool att, const LoopArgs& a, size_t smem, cudaStream_t st) {
-    void* fn = att ? (void*)lstm_loop_kernel<true> : (void*)lstm_loop_kernel<false>;
+    void* fn = att ? (void*)lstm_loop_kernel<true, ATT_STAGES> : (void*)lstm_loop_kernel<false, GEN_STAGES>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
@@ -531,11 +637,14 @@ int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
     B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)B * l.Kp_att * 2, st));                 // operand of step 0
     B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
-    f32_to_bf16_rows_kernel<<<grid_for((size_t)B * s.L * s.A), 256, 0, st>>>(memTb, s.A, ws + fl.memT, s.A, (size_t)B * s.L, s.A);
-    B200_LAUNCH_CHECK();
+    (void)memTb;
     f32_to_bf16_rows_kernel<<<grid_for((size_t)B * s.L * l.ldm), 256, 0, st>>>(memb, l.ldm, in.memory, M, (size_t)B * s.L, M);
     B200_LAUNCH_CHECK();
     wcomb_kernel<<<cdiv(s.K * s.A, 256), 256, 0, st>>>(wcombT, w.attn_location, w.attn_loc_features, s.A, s.C, s.K);
+    B200_LAUNCH_CHECK();
+    __nv_bfloat16* wcb = reinterpret_cast<__nv_bfloat16*>(pws + l.wcb);
+    __nv_bfloat16* memTf = reinterpret_cast<__nv_bfloat16*>(pws + l.memTf);
+    att_prep_kernel<<<148 * 4, 256, 0, st>>>(wcb, memTf, wcombT, ws + fl.memT, B, s.L, s.A, s.K, l.MT);
     B200_LAUNCH_CHECK();
     // padding columns [MD, Kp) of every operand row must be zero (weights there are zero too, but NaN * 0 would poison)
     if (l.Kp_att != MD) B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)(T + 1) * B * l.Kp_att * 2, st));
@@ -546,12 +655,12 @@ int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     a.gates = ws + fl.ga; a.cstate = ws + fl.ca;
     a.mask_h = in.mask_att_h; a.mask_c = in.mask_att_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
     a.L = s.L; a.M = M; a.A = s.A; a.KC = s.K;
-    a.Wq = w.attn_query; a.qpart = ws + fl.qpart; a.qsave = ws + fl.q; a.WcombT = wcombT; a.bias = w.attn_bias; a.v = w.attn_energy;
-    a.memTb = memTb; a.memb = memb; a.ldm = l.ldm; a.lengths = in.text_lengths; a.cum = ws + fl.cum;
+    a.Wq = w.attn_query; a.qpart = ws + fl.qpart; a.qsave = ws + fl.q; a.WcB = wcb; a.memTf = memTf; a.MT = l.MT; a.bias = w.attn_bias; a.v = w.attn_energy;
+    a.memb = memb; a.ldm = l.ldm; a.lengths = in.text_lengths; a.cum = ws + fl.cum;
     a.align = align; a.align_bstride = (long long)T * s.L;
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
     a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256);
-    return launch_loop(true, a, loop_smem_bytes(l.Kp_att, s.A, true, s.L, M, s.K), st);
+    return launch_loop(true, a, loop_smem_bytes(l.Kp_att, s.A, true, s.L, M, ATT_STAGES), st);
 }
 
 // Generator-LSTM loop.  Expects: gg = input projection, hg row 0 = 0, cg row 0 = 0.
@@ -571,7 +680,7 @@ int persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     a.mask_h = in.mask_gen_h; a.mask_c = in.mask_gen_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
     a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256) + 148 * 8;
-    return launch_loop(false, a, loop_smem_bytes(l.Kp_gen, s.A, false, 0, 0, 0), st);
+    return launch_loop(false, a, loop_smem_bytes(l.Kp_gen, s.A, false, 0, 0, GEN_STAGES), st);
 }
 
 }  // namespace b200tts

@@ -35,6 +35,7 @@ struct BwdLoopArgs {
     float* part;                           // [KB, B, NOUT] partial products of the previous reverse step
     int hcol;                              // column of d h inside the NOUT outputs (0 for the generator loop)
     unsigned* barrier; int* abort_flag;
+    long long* prof;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -79,6 +80,17 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
     return s_ok != 0;
 }
 
+#define BPROF_DECL long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
+#define BPROF_MARK(slot)                                                                                         \
+    do {                                                                                                         \
+        if (p.prof && threadIdx.x == 0) { const long long now = clock64(); prof_acc[slot] += now - prof_t; prof_t = now; } \
+    } while (0)
+#define BPROF_FLUSH                                                                                              \
+    do {                                                                                                         \
+        if (p.prof && threadIdx.x == 0)                                                                          \
+            for (int k9 = 0; k9 < 8; ++k9) p.prof[(size_t)blockIdx.x * 8 + k9] = prof_acc[k9];                   \
+    } while (0)
+
 // Generator-LSTM reverse loop (no attention): NOUT = D.
 __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_kernel(const BwdLoopArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -110,6 +122,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_kernel(const BwdLoopArgs 
 #pragma unroll
     for (int e = 0; e < MAXE; ++e) { dc_reg[e] = 0.f; dhz_reg[e] = 0.f; }
     unsigned target = 0;
+    BPROF_DECL
 
     for (int i = p.T - 1; i >= 0; --i) {
         const bool last = (i == p.T - 1);
@@ -158,7 +171,9 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_kernel(const BwdLoopArgs 
                 }
             }
         }
+        BPROF_MARK(0);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        BPROF_MARK(1);
         if (i == 0) break;
 
         // ---------------- P2: partial[kb] = dgates[:, K-block kb] . W[K-block kb, N-block nb] ----------------
@@ -243,6 +258,7 @@ struct AttBwdArgs {
     float* dq;                                            // [T, B, A] out
     float* de;                                            // [T, B, L] out (softmax-backward energies, consumed by the post pass)
     unsigned* barrier; int* abort_flag;
+    long long* prof;
 };
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -327,6 +343,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
     float* s_G = s_red + 64;                              // [L16][GLD]
     float* s_dqp = p.dqp_after_g ? s_G + (size_t)L16 * GLD : scr;   // [8][A]: after G if it fits, else aliases s_dctx .. s_Ph (dead by then)
     float* s_stage = reinterpret_cast<float*>(s_Pl);      // [L16]: d cum staging (Pl is dead by then)
+    BPROF_DECL
 
     for (int i = p.T - 1; i >= 0; --i) {
         const bool last = (i == p.T - 1);
@@ -347,25 +364,43 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
             for (int a = tid; a < A; a += PT) { s_qb[a] = p.q[((size_t)i * B + b) * A + a] + p.bias[a]; s_vv[a] = p.v[a]; }
             build_pairs(s_Ph, s_Pl, p.cum + ((size_t)i * B + b) * L, L, half, L16 + 48, tid, PT);
             __syncthreads();
-            // dw[l] = dalign + dcum + <dctx, memory[l]>
-            for (int l = warp; l < L16; l += 8) {
-                float acc = 0.f;
-                if (l < len) {
-                    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + l) * p.ldm);
-                    for (int m2 = lane; 2 * m2 < M; m2 += 32) {
-                        const float2 v2 = __bfloat1622float2(row[m2]);
-                        acc = fmaf(s_dctx[2 * m2], v2.x, acc);
-                        if (2 * m2 + 1 < M) acc = fmaf(s_dctx[2 * m2 + 1], v2.y, acc);
+            // dw[l] = dalign + dcum + <dctx, memory[l]>   (4 positions per warp batch: 4 x 5 row loads in flight)
+            for (int lb = warp; lb < L16; lb += 32) {
+                __nv_bfloat162 rv[4][8];
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    const int l = lb + 8 * r4;
+                    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + (l < len ? l : 0)) * p.ldm);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int m2 = lane + 32 * j;
+                        if (2 * m2 < M && l < len) rv[r4][j] = row[m2];
                     }
                 }
-                acc = warp_sum(acc);
-                if (lane == 0) {
-                    float g = 0.f;
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    const int l = lb + 8 * r4;
+                    float acc = 0.f;
                     if (l < len) {
-                        g = acc + (last ? 0.f : dcum[l]);
-                        if (p.dalign) g += p.dalign[(size_t)b * p.dalign_bstride + (size_t)i * L + l];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int m2 = lane + 32 * j;
+                            if (2 * m2 < M) {
+                                const float2 v2 = __bfloat1622float2(rv[r4][j]);
+                                acc = fmaf(s_dctx[2 * m2], v2.x, acc);
+                                if (2 * m2 + 1 < M) acc = fmaf(s_dctx[2 * m2 + 1], v2.y, acc);
+                            }
+                        }
                     }
-                    s_de[l] = g;
+                    acc = warp_sum(acc);
+                    if (lane == 0 && l < L16) {
+                        float g = 0.f;
+                        if (l < len) {
+                            g = acc + (last ? 0.f : dcum[l]);
+                            if (p.dalign) g += p.dalign[(size_t)b * p.dalign_bstride + (size_t)i * L + l];
+                        }
+                        s_de[l] = g;
+                    }
                 }
             }
             __syncthreads();
@@ -378,6 +413,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                 if (l < L) p.de[((size_t)i * B + b) * L + l] = d;
             }
             __syncthreads();
+            BPROF_MARK(0);
             // energies backward on the tensor cores; warp owns position tiles {warp, warp + 8}
             float dqacc[16][2];
 #pragma unroll
@@ -481,7 +517,9 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
             __syncthreads();
             for (int j = tid; j < L; j += PT) dcum[j] = s_stage[j];
         }
+        BPROF_MARK(1);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        BPROF_MARK(2);
 
         // =========================== PB: attention-LSTM cell backward ===========================
         if (owner) {
@@ -494,6 +532,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                     float dh = p.dh_static[(size_t)i * B * D + bu];
                     const float* dqr = p.dq + ((size_t)i * B + b) * A;
                     float dhq = 0.f;
+#pragma unroll 8
                     for (int a = 0; a < A; a += 4) {
                         const float4 d4 = __ldcg(reinterpret_cast<const float4*>(dqr + a));
                         dhq = fmaf(d4.x, wq8[a * (UOWN + 1) + uu], dhq); dhq = fmaf(d4.y, wq8[(a + 1) * (UOWN + 1) + uu], dhq);
@@ -536,7 +575,9 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                 }
             }
         }
+        BPROF_MARK(3);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        BPROF_MARK(4);
         if (i == 0) break;
 
         // =========================== P2: [d ctx | d h](i-1) partial = dgates_i[:, kb] . W[kb, nb] ===========================
@@ -585,8 +626,11 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                         }
             }
         }
+        BPROF_MARK(5);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        BPROF_MARK(6);
     }
+    BPROF_FLUSH;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -814,7 +858,7 @@ AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s) {
     x.de = take((size_t)s.T * s.B * s.L * 4);
     x.dwpart = take((size_t)s.B * x.MT * s.A * 32 * 4);
     x.dvpart = take((size_t)s.B * x.MT * s.A * 4);
-    x.barrier = take(256);
+    x.barrier = take(256 + 148 * 8 * 8);
     x.total = off;
     return x;
 }
@@ -868,6 +912,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     a.dqp_after_g = att_bwd_dqp_mode(s);
     a.lengths = in.text_lengths; a.dctx_tot = dctx_tot; a.dq = dq; a.de = reinterpret_cast<float*>(extra + x.de);
     a.barrier = reinterpret_cast<unsigned*>(extra + x.barrier); a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);
+    a.prof = reinterpret_cast<long long*>(extra + x.barrier + 256);
     const float* wcombT = reinterpret_cast<const float*>(pws + pl.wcombT);
     B200_CUDA(cudaMemsetAsync(a.barrier, 0, 256, st));
     att_bwd_prep_kernel<<<148 * 4, 256, 0, st>>>(wcb, wcb2, memTf, wcombT, fws + fl.memT, B, L, A, s.K, x.MT);
@@ -905,7 +950,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
 
 size_t persist_bwd_gen_extra_bytes(const b200tts_decoder_shape& s) {
     // dgb [B, 4D] bf16 + part [KB, B, D] fp32 + barrier
-    return ((size_t)s.B * 4 * s.D * 2 + 255) / 256 * 256 + ((size_t)KB * s.B * s.D * 4 + 255) / 256 * 256 + 256;
+    return ((size_t)s.B * 4 * s.D * 2 + 255) / 256 * 256 + ((size_t)KB * s.B * s.D * 4 + 255) / 256 * 256 + 256 + 148 * 8 * 8;
 }
 
 // dgates for all T steps of the generator LSTM.  `extra` = persist_bwd_gen_extra_bytes scratch.
@@ -924,6 +969,7 @@ int persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     a.part = reinterpret_cast<float*>(extra + off); off += ((size_t)KB * B * D * 4 + 255) / 256 * 256;
     a.barrier = reinterpret_cast<unsigned*>(extra + off);
     a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);
+    a.prof = reinterpret_cast<long long*>(extra + off + 256);
     a.hcol = 0;
     B200_CUDA(cudaMemsetAsync(a.barrier, 0, 256, st));
     const size_t smem = ((size_t)4 * a.UK * (a.UN + 8) + (size_t)BT * (4 * a.UK + 8)) * 2;

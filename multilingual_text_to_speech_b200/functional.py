@@ -197,6 +197,8 @@ class DecoderFunction(torch.autograd.Function):
         lib = _lib.load()
         nbytes = lib.b200tts_decoder_bwd_workspace_bytes(ctypes.byref(shape))
         bws = torch.empty(nbytes, dtype=torch.uint8, device=memory.device)
+        if PROFILE.get('keep_ws'):
+            PROFILE['last_bws'] = bws
         grads = [torch.zeros_like(p) for p in params]
         gstruct = DecoderParams(*[ptr(g) for g in grads])
         d_memory = torch.empty_like(memory) if ctx.needs_input_grad[1] else None

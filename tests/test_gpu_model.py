@@ -19,3 +19,58 @@ def _built():
 @pytest.mark.parametrize('name', GOLDEN_CASES)
 def test_model_matches_reference_golden(name):
     model_cases.run_golden(name, check_grads=True, verbose=True)
+
+
+def test_full_size_model_fp32_and_bf16_modes():
+    """generated_training at the real dimensions (D=1024, A=128, G=10): fp32 mode meets the parity gate against the fp64
+    oracle; bf16 perf mode (persistent kernels + tensor-core GEMMs) meets the north_star gate mel L1 < 1e-3."""
+    import types
+    from multilingual_text_to_speech_b200 import configs, _lib
+    from multilingual_text_to_speech_b200.modules.tacotron2 import Tacotron
+    from multilingual_text_to_speech_b200.rng import MaskSource
+    from oracle import tacotron_oracle as O
+    from helpers import assert_close
+    hp = configs.apply('generated_training', decoder_regularization='zoneout')
+    B, L, T = 20, 48, 24
+    torch.manual_seed(0)
+    model = Tacotron().train()
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(1, hp.symbols_count() + 3, (B, L), generator=g)
+    lens = torch.sort(torch.randint(L // 2, L + 1, (B,), generator=g), descending=True).values; lens[0] = L
+    for b in range(B):
+        text[b, lens[b]:] = 0
+    mel = torch.randn(B, hp.num_mels, T, generator=g)
+    tlens = torch.full((B,), T)
+    lang = torch.arange(B) % hp.language_number
+    D, P = hp.decoder_dimension, hp.prenet_dimension
+    keep = lambda shape, p: (torch.rand(*shape, generator=g) >= p).float()   # noqa: E731
+    tape = {'teacher': torch.ones(T, dtype=torch.bool), 'prenet0': keep((B, T + 1, P), 0.5), 'prenet1': keep((B, T + 1, P), 0.5),
+            'att_h': keep((T, B, D), 0.1), 'att_c': keep((T, B, D), 0.1), 'gen_h': keep((T, B, D), 0.1), 'gen_c': keep((T, B, D), 0.1)}
+    sd = {k: v.detach().double() for k, v in model.state_dict().items()}
+    for k in list(sd):
+        if k.startswith('_decoder._prenet.') or k.startswith('_decoder._attention.'):
+            sd[k] = sd[k[len('_decoder.'):]]
+    ns = types.SimpleNamespace(**hp.state_dict())
+    with torch.no_grad():
+        post_o, pre_o, stop_o, align_o, _, enc_o = O.tacotron_forward(sd, ns, text, lens, mel.double(), tlens, None, lang, tape, training=True)
+    dev = torch.device('cuda:0')
+    model = model.to(dev)
+    results = {}
+    for mode in ('fp32', 'bf16'):
+        _lib.set_precision(mode)
+        MaskSource.use_tape(tape)
+        try:
+            with torch.no_grad():
+                post, pre, stop, align, _, enc = model(text.to(dev), lens.to(dev), mel.to(dev), tlens.to(dev), None, lang.to(dev), 1.0)
+        finally:
+            MaskSource.use_tape(None)
+            _lib.set_precision('fp32')
+        results[mode] = {'pre_l1': float((pre.cpu().double() - pre_o).abs().mean()), 'post_l1': float((post.cpu().double() - post_o).abs().mean()),
+                         'align_l1': float((align.cpu().double() - align_o).abs().mean()),
+                         'argmax': float((align.cpu().argmax(2) == align_o.argmax(2)).float().mean())}
+        if mode == 'fp32':
+            assert_close(enc, enc_o, 1e-3, 1e-4, 'enc'); assert_close(pre, pre_o, 1e-3, 1e-4, 'pre'); assert_close(align, align_o, 1e-3, 1e-4, 'align')
+            assert_close(stop, stop_o, 1e-3, 1e-4, 'stop')
+            assert torch.equal(align.cpu().argmax(2), align_o.argmax(2))
+    print('full-size model vs fp64 oracle:', results, 'mean |pre| =', float(pre_o.abs().mean()))
+    assert results['bf16']['pre_l1'] < 1e-3 and results['bf16']['post_l1'] < 1e-3, results

@@ -49,9 +49,23 @@ def main():
         if a.precision == 'bf16' and it == a.iters:
             import ctypes
             F.PROFILE['keep_ws'] = True
-            with torch.no_grad():
-                F.decoder_forward(cfg, memory, target, lens, params)
+            spec, stop, align = F.decoder_forward(cfg, memory, target, lens, params)
+            if not a.fwd_only:
+                (spec.sum() + stop.sum() + (align * align).sum()).backward()
             torch.cuda.synchronize()
+            if not a.fwd_only:
+                shp = F.PROFILE['last_shape']
+                bnames = [['cell', 'barrier1', 'mma', 'barrier2', '-', '-', '-', '-'],
+                          ['attn:dw/softmax', 'attn:mma+dcum', 'barrier1', 'cell', 'barrier2', 'mma', 'barrier3', '-']]
+                for which, loop in enumerate(('gen-bwd', 'att-bwd')):
+                    boff = _lib.load().b200tts_debug_persist_bwd_profile_offset(ctypes.byref(shp), which)
+                    rb = F.PROFILE['last_bws'][boff:boff + 148 * 8 * 8].view(torch.int64).view(148, 8).cpu().double()
+                    act = rb[rb.sum(1) > 0]
+                    if len(act):
+                        print(f'{loop} loop: cycles/step by phase, CTA0 | mean | max over CTAs')
+                        for j, nme in enumerate(bnames[which]):
+                            if nme != '-':
+                                print(f'   {nme:18s} {rb[0, j] / a.T:9.0f} {act[:, j].mean() / a.T:9.0f} {act[:, j].max() / a.T:9.0f}')
             off = _lib.load().b200tts_debug_persist_profile_offset(ctypes.byref(F.PROFILE['last_shape']))
             raw = F.PROFILE['last_ws'][off:off + 2 * 148 * 8 * 8].view(torch.int64).view(2, 148, 8).cpu().double()
             names = ['gemm', 'reduce', 'cell+q', 'barrier1', 'attn:q/load', 'attn:energy', 'attn:softmax+ctx', 'barrier2']
