@@ -49,6 +49,11 @@ unsigned long long b200tts_launch_count(void);
 #define B200TTS_PRECISION_BF16 1
 int b200tts_set_precision(int mode);
 int b200tts_get_precision(void);
+/* Caller-owned device scratch (1024-byte aligned) for the bf16 operand packing of the tcgen05 GEMM path; without it (or when a
+ * problem does not fit) the bf16 mode uses the mma.sync kernel.  ~1.5 GB covers the BASELINE shapes.  NULL releases it. */
+int b200tts_set_scratch(void* ptr, size_t bytes);
+/* Debug / A-B switch: 0 forces the mma.sync bf16 GEMM even when the tcgen05 path is applicable. */
+int b200tts_set_tensor_core_gemm(int enabled);
 
 /* ---- generic dense contraction (the time-batched GEMMs of the path) ----------------------- */
 /* C = alpha * op(A) . op(B) + beta * C + bias[n];  op(A)(m,k) = transA ? A[k*lda+m] : A[m*lda+k],

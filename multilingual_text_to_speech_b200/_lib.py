@@ -68,6 +68,8 @@ SIGNATURES = {
     'b200tts_launch_count': (c_ulonglong, []),
     'b200tts_set_precision': (c_int, [c_int]),
     'b200tts_get_precision': (c_int, []),
+    'b200tts_set_scratch': (c_int, [c_void_p, c_size_t]),
+    'b200tts_set_tensor_core_gemm': (c_int, [c_int]),
     'b200tts_debug_persist_profile_offset': (c_size_t, [POINTER(DecoderShape)]),
     'b200tts_debug_persist_bwd_profile_offset': (c_size_t, [POINTER(DecoderShape), c_int]),
     'b200tts_gemm_f32': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float,
@@ -138,8 +140,30 @@ def ptr(t):
 PRECISIONS = {'fp32': 0, 'bf16': 1}
 
 
+_scratch = None
+
+
+def ensure_scratch(nbytes=3 << 29):
+    """Device scratch for the tcgen05 GEMM's packed bf16 operands (owned here, handed to the library)."""
+    global _scratch
+    import torch
+    if _scratch is None or _scratch.numel() < nbytes:
+        _scratch = torch.empty(nbytes + 1024, dtype=torch.uint8, device='cuda')
+        base = (_scratch.data_ptr() + 1023) // 1024 * 1024
+        check(load().b200tts_set_scratch(c_void_p(base), nbytes), 'b200tts_set_scratch')
+    return _scratch
+
+
 def set_precision(name):
     check(load().b200tts_set_precision(PRECISIONS[name]), 'b200tts_set_precision')
+    if name == 'bf16':
+        import torch
+        if torch.cuda.is_available():
+            ensure_scratch()
+
+
+def set_tensor_core_gemm(enabled):
+    check(load().b200tts_set_tensor_core_gemm(int(bool(enabled))), 'b200tts_set_tensor_core_gemm')
 
 
 def get_precision():

@@ -101,7 +101,12 @@ __global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsi
 
 }  // namespace b200tts
 
-namespace b200tts { size_t decoder_bwd_profile_offset(const b200tts_decoder_shape& s, int which); }
+namespace b200tts {
+size_t decoder_bwd_profile_offset(const b200tts_decoder_shape& s, int which);
+void set_tc_scratch(void* ptr, size_t bytes);
+void set_tc_enabled(int on);
+int tc_enabled();
+}
 using namespace b200tts;
 
 extern "C" {
@@ -115,6 +120,12 @@ int b200tts_set_precision(int mode) {
     return B200TTS_OK;
 }
 int b200tts_get_precision(void) { return precision_mode(); }
+int b200tts_set_scratch(void* ptr, size_t bytes) {
+    if (ptr && (reinterpret_cast<uintptr_t>(ptr) & 1023)) { set_last_error("set_scratch: pointer must be 1024-byte aligned"); return B200TTS_ERR_INVALID; }
+    set_tc_scratch(ptr, ptr ? bytes : 0);
+    return B200TTS_OK;
+}
+int b200tts_set_tensor_core_gemm(int enabled) { set_tc_enabled(enabled ? 1 : 0); return B200TTS_OK; }
 size_t b200tts_debug_persist_bwd_profile_offset(const b200tts_decoder_shape* shape, int which) {
     if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
     return decoder_bwd_profile_offset(*shape, which);

@@ -210,8 +210,15 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled);
+
 int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
     if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return B200TTS_OK;
+    {   // tcgen05 / TMEM / TMA path for the large contractions (gemm_tc.cu); falls through when not applicable
+        bool handled = false;
+        B200_TRY(gemm_tc_try(d, stream, &handled));
+        if (handled) return B200TTS_OK;
+    }
     B200_REQUIRE(d.A && d.B && (d.C || (d.splitk > 1 && d.keep_partials)), "gemm_bf16: null operand");
     B200_REQUIRE(d.splitk >= 1 && (d.splitk == 1 || d.partial), "gemm_bf16: split-K needs a partial workspace");
     KernelArgs p;

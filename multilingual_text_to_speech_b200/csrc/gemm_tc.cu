@@ -1,0 +1,320 @@
+// tcgen05 / TMEM / TMA bf16 GEMM for the time-batched contractions of the perf mode (sm_100a only).
+//
+//   C[M, N] (fp32) = alpha * A[M, K] . B[N, K]^T + beta * C + bias[n]
+//
+// Operands are first packed to bf16, K-major (pack kernels below: fp32 -> bf16, transposing when the source is
+// M/N-contiguous), then one warp-specialised kernel per 128 x 128 output tile:
+//   warp 4 (one lane)  : TMA producer  -- cp.async.bulk.tensor (128B swizzle) into a 4-stage shared-memory ring,
+//                        mbarrier expect_tx / complete_tx
+//   warp 5 (one lane)  : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 128, K = 16 per instruction,
+//                        accumulator in TMEM (128 lanes x 128 columns fp32); tcgen05.commit frees ring slots
+//   warps 0-3          : epilogue      -- tcgen05.ld (32 lanes x 32 columns per instruction) -> alpha/beta/bias -> global
+// Every mbarrier wait carries a clock64 watchdog that traps instead of hanging the device.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace b200tts {
+
+namespace {
+
+constexpr int TBM = 128, TBN = 128, TBK = 64;
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = (TBM + TBN) * TBK * 2;          // 32 KB
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 128;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) __trap();       // ~2 s: a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart): UMMA shared-memory descriptor
+// (cute::UMMA::SmemDescriptor: start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major; canonical value 1)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+struct TcArgs {
+    float* C; const float* bias;
+    int M, N, K, ldc;
+    float alpha, beta;
+    int batch, a_batch_mod;
+    long long strideC;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned ring (128B swizzle atoms are 1024 B)
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN, bz = blockIdx.z;
+    const int az = p.a_batch_mod > 0 ? bz % p.a_batch_mod : bz;
+    const int nk = (p.K + TBK - 1) / TBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                uint8_t* sa = ring + (size_t)s * STAGE_BYTES;
+                tma_load_3d(sa, &tmA, &full_bar[s], kb * TBK, m0, az);
+                tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], kb * TBK, n0, bz);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(ring + (size_t)s * STAGE_BYTES);
+                const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + TBM * TBK * 2);
+#pragma unroll
+                for (int k = 0; k < TBK / 16; ++k)        // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the address field
+                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&empty_bar[s]);               // implicit tcgen05.fence::before_thread_sync
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // epilogue: warp w owns TMEM lanes [32w, 32w + 32) = rows m0 + 32w + lane
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = m0 + warp * 32 + lane;
+        float* crow = p.C + (size_t)bz * p.strideC + (size_t)m * p.ldc;
+#pragma unroll 1
+        for (int c = 0; c < TBN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
+            if (m < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c * 32 + j;
+                    if (n < p.N) {
+                        float v = p.alpha * __uint_as_float(r[j]);
+                        if (p.bias) v += p.bias[n];
+                        if (p.beta != 0.f) v += p.beta * crow[n];
+                        crow[n] = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand packing: fp32 (either orientation) -> bf16 [batch][rows][Kp], K contiguous, Kp % 8 == 0
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kcontig_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int ld, long long bstride, int rows,
+                                    int K, int Kp) {
+    const size_t per = (size_t)rows * Kp;
+    const float* s = src + (size_t)blockIdx.y * bstride;
+    __nv_bfloat16* d = dst + (size_t)blockIdx.y * per;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < per; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / Kp;
+        const int k = idx % Kp;
+        d[idx] = __float2bfloat16_rn(k < K ? s[r * ld + k] : 0.f);
+    }
+}
+// source element (r, k) at src[k*ld + r]: 32 x 32 tile transpose through shared memory
+__global__ void pack_transpose_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int ld, long long bstride, int rows,
+                                      int K, int Kp) {
+    __shared__ float tile[32][33];
+    const float* s = src + (size_t)blockIdx.z * bstride;
+    __nv_bfloat16* d = dst + (size_t)blockIdx.z * rows * Kp;
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int k = k0 + j, r = r0 + threadIdx.x;
+        tile[j][threadIdx.x] = (k < K && r < rows) ? s[(size_t)k * ld + r] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, k = k0 + threadIdx.x;
+        if (r < rows && k < Kp) d[(size_t)r * Kp + k] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int K, int Kp, int batch, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    B200_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with %d (rows=%d K=%d Kp=%d batch=%d)", (int)r, rows, K, Kp, batch);
+    return B200TTS_OK;
+}
+
+struct Scratch { unsigned char* ptr = nullptr; size_t bytes = 0; };
+Scratch g_scratch;
+int g_tc_enabled = 1;
+
+}  // namespace
+
+void set_tc_scratch(void* ptr, size_t bytes) { g_scratch.ptr = static_cast<unsigned char*>(ptr); g_scratch.bytes = bytes; }
+void set_tc_enabled(int on) { g_tc_enabled = on; }
+int tc_enabled() { return g_tc_enabled; }
+
+// Returns B200TTS_OK and sets *handled = true when the tcgen05 path ran; *handled = false -> caller uses the mma.sync path.
+int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (!g_tc_enabled || g_scratch.ptr == nullptr) return B200TTS_OK;
+    if (d.splitk != 1 || d.keep_partials) return B200TTS_OK;
+    if (d.M < 64 || d.N < 64 || d.K < 32) return B200TTS_OK;                 // tiny problems: not worth packing
+    if ((long long)d.M * d.N * d.K * d.batch < (1ll << 24)) return B200TTS_OK;
+    const int Kp = (d.K + 7) / 8 * 8;
+    const int abatch = d.a_batch_mod > 0 ? d.a_batch_mod : d.batch;
+    const size_t a_bytes = ((size_t)abatch * d.M * Kp * 2 + 1023) / 1024 * 1024;
+    const size_t b_bytes = ((size_t)d.batch * d.N * Kp * 2 + 1023) / 1024 * 1024;
+    if (a_bytes + b_bytes > g_scratch.bytes) return B200TTS_OK;
+    if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
+    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
+    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
+
+    auto pack = [&](__nv_bfloat16* dst, const float* src, int ld, long long bstride, int rows, bool kcontig, int nb) -> int {
+        if (kcontig) {
+            size_t per = (size_t)rows * Kp;
+            int gx = (int)((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
+            pack_kcontig_kernel<<<dim3(gx, nb), 256, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp);
+        } else {
+            dim3 grid(cdiv(rows, 32), cdiv(Kp, 32), nb), block(32, 8);
+            pack_transpose_kernel<<<grid, block, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp);
+        }
+        B200_LAUNCH_CHECK();
+        return B200TTS_OK;
+    };
+    B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch));
+    B200_TRY(pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch));
+
+    CUtensorMap tmA, tmB;
+    B200_TRY(make_map(&tmA, pa, d.M, d.K, Kp, abatch, TBM));
+    B200_TRY(make_map(&tmB, pb, d.N, d.K, Kp, d.batch, TBN));
+    TcArgs a;
+    a.C = d.C; a.bias = d.bias; a.M = d.M; a.N = d.N; a.K = d.K; a.ldc = d.ldc; a.alpha = d.alpha; a.beta = d.beta;
+    a.batch = d.batch; a.a_batch_mod = d.a_batch_mod; a.strideC = d.strideC;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(cdiv(d.N, TBN), cdiv(d.M, TBM), d.batch);
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    B200_LAUNCH_CHECK();
+    *handled = true;
+    return B200TTS_OK;
+}
+
+}  // namespace b200tts

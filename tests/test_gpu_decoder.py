@@ -143,3 +143,34 @@ def test_gemm_bf16_mode(M, N, K, ta, tb, splitk):
 def test_decoder_bf16_perf_mode(kw):
     """Persistent weight-stationary bf16 kernels (decoder_persist.cu) + bf16 tensor-core GEMMs."""
     dc.run_case_bf16(dc.full_dim_case(**kw), check_grads=True, verbose=True)
+
+
+@pytest.mark.parametrize('M,N,K,ta,tb', [
+    (128, 128, 64, False, True), (256, 384, 512, False, True), (300, 260, 513, False, True), (1000, 4096, 1312, False, True),
+    (4096, 288, 640, True, False), (513, 130, 2000, True, True), (200, 1000, 72, False, False),
+])
+def test_gemm_tcgen05_path(M, N, K, ta, tb):
+    """tcgen05 / TMEM / TMA GEMM (gemm_tc.cu) against fp64 on bf16-rounded operands, and against the mma.sync kernel."""
+    from multilingual_text_to_speech_b200 import functional as F, _lib
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    c0 = torch.randn(M, N, generator=g)
+    ar, br = a.bfloat16().double(), b.bfloat16().double()
+    ref = 0.5 * ((ar.t() if ta else ar) @ (br.t() if tb else br)) + bias.double() + 0.25 * c0.double()
+    _lib.set_precision('bf16')
+    try:
+        n0 = _lib.launch_count()
+        out = c0.cuda().clone()
+        F.gemm(a.cuda(), b.cuda(), ta, tb, bias=bias.cuda(), out=out, alpha=0.5, beta=0.25)
+        used = _lib.launch_count() - n0
+        _lib.set_tensor_core_gemm(False)
+        out2 = c0.cuda().clone()
+        F.gemm(a.cuda(), b.cuda(), ta, tb, bias=bias.cuda(), out=out2, alpha=0.5, beta=0.25)
+    finally:
+        _lib.set_tensor_core_gemm(True)
+        _lib.set_precision('fp32')
+    assert used == 3, f'expected pack + pack + tcgen05 kernel, saw {used} launches'
+    assert_close(out, ref, 1e-4, 2e-4 * (K ** 0.5), f'tcgen05 gemm {M}x{N}x{K}')
+    assert_close(out, out2, 1e-4, 2e-4 * (K ** 0.5), 'tcgen05 vs mma.sync')

@@ -73,4 +73,6 @@ def test_full_size_model_fp32_and_bf16_modes():
             assert_close(stop, stop_o, 1e-3, 1e-4, 'stop')
             assert torch.equal(align.cpu().argmax(2), align_o.argmax(2))
     print('full-size model vs fp64 oracle:', results, 'mean |pre| =', float(pre_o.abs().mean()))
-    assert results['bf16']['pre_l1'] < 1e-3 and results['bf16']['post_l1'] < 1e-3, results
+    # mel gate on the decoder output; `post` adds 5 train-mode BatchNorm layers that amplify ANY input difference ~50x at
+    # random init (a 3.5e-4 pre difference became 1.7e-2 in post with an exact fp32 postnet), so it is only bounded loosely
+    assert results['bf16']['pre_l1'] < 1e-3 and results['bf16']['post_l1'] < 5e-2, results
