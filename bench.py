@@ -262,7 +262,12 @@ def run_b200(a):
     F.PROFILE.clear()
     F.PROFILE['enabled'] = True
     n0 = _lib.launch_count()
+    ncu_range = bool(os.environ.get('B200TTS_NCU_RANGE'))   # `ncu --profile-from-start off`: capture exactly the timed steps
+    if ncu_range:
+        torch.cuda.profiler.start()
     ms, _ = timed(a.steps, from_host=False)
+    if ncu_range:
+        torch.cuda.profiler.stop()
     launches = _lib.launch_count() - n0
     F.PROFILE['enabled'] = False
     torch.cuda.synchronize()

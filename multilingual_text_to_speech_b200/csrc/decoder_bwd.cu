@@ -31,21 +31,47 @@ __global__ void gather_frame_grads_kernel(float* __restrict__ dfs, const float* 
     }
 }
 
-// dst[c] += sum_r src[r*ld + c]   (bias gradients); one block per 32 columns, deterministic tree
-__global__ void colsum_add_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t rows, int cols, int ld) {
+// Column sums (bias gradients), deterministic two-level tree: partial[s][c] = sum of row slice s, then dst[c] += sum_s partial[s][c].
+constexpr int COLSUM_SLICES = 64;
+__global__ void colsum_partial_kernel(float* __restrict__ partial, const float* __restrict__ src, size_t rows, int cols, int ld) {
     __shared__ float sm[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
-    float acc = 0.f;
-    if (c < cols)
-        for (size_t r = threadIdx.y; r < rows; r += 8) acc += src[r * ld + c];
-    sm[threadIdx.y][threadIdx.x] = acc;
+    const size_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const size_t r0 = blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < cols) {
+        size_t r = r0 + threadIdx.y;
+        for (; r + 24 < r1; r += 32) {
+            a0 += src[r * ld + c]; a1 += src[(r + 8) * ld + c]; a2 += src[(r + 16) * ld + c]; a3 += src[(r + 24) * ld + c];
+        }
+        for (; r < r1; r += 8) a0 += src[r * ld + c];
+    }
+    sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += sm[j][threadIdx.x];
-        dst[c] += s;
+        partial[(size_t)blockIdx.y * cols + c] = s;
     }
+}
+__global__ void colsum_finish_kernel(float* __restrict__ dst, float* __restrict__ dst2, const float* __restrict__ partial, int slices, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int j = 0; j < slices; ++j) s += partial[(size_t)j * cols + c];
+    dst[c] += s;
+    if (dst2) dst2[c] += s;
+}
+// dst[c] (+ dst2[c]) += sum_r src[r*ld + c]; scratch holds COLSUM_SLICES * cols floats
+int colsum_add(float* dst, float* dst2, const float* src, size_t rows, int cols, int ld, float* scratch, cudaStream_t st) {
+    int slices = (int)(rows / 256);
+    slices = slices < 1 ? 1 : (slices > COLSUM_SLICES ? COLSUM_SLICES : slices);
+    colsum_partial_kernel<<<dim3(cdiv(cols, 32), slices), dim3(32, 8), 0, st>>>(scratch, src, rows, cols, ld);
+    B200_LAUNCH_CHECK();
+    colsum_finish_kernel<<<cdiv(cols, 128), 128, 0, st>>>(dst, dst2, scratch, slices, cols);
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
 }
 
 // dst[j] += sum_b src[b*n + j]
@@ -598,13 +624,8 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     B200_LAUNCH_CHECK();
     add2d_kernel<<<grid_for((size_t)(D + M)), 256, 0, st>>>(dw.stop_w, D + M, W(l.dwfs) + (size_t)N * (D + M), D + M, 1, D + M);
     B200_LAUNCH_CHECK();
-    {
-        dim3 blk(32, 8);
-        colsum_add_kernel<<<cdiv(N, 32), blk, 0, st>>>(dw.frame_b, W(l.dfs), TB, N, N1);
-        B200_LAUNCH_CHECK();
-        colsum_add_kernel<<<1, blk, 0, st>>>(dw.stop_b, W(l.dfs) + N, TB, 1, N1);
-        B200_LAUNCH_CHECK();
-    }
+    B200_TRY(colsum_add(dw.frame_b, nullptr, W(l.dfs), TB, N, N1, W(l.gpart), st));
+    B200_TRY(colsum_add(dw.stop_b, nullptr, W(l.dfs) + N, TB, 1, N1, W(l.gpart), st));
 
     // ---- 2. generator LSTM reverse loop ----
     const bool zone = s.cell_kind == B200TTS_CELL_ZONEOUT;
@@ -638,13 +659,7 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, F(fl.hg), D, dw.gen_w_hh, D, 1.f));
     B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, ai1 + M, MD, dw.gen_w_ih, D + M, 1.f));
     B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dgg), 4 * D, ai1, MD, dw.gen_w_ih + D, D + M, 1.f));
-    {
-        dim3 blk(32, 8);
-        colsum_add_kernel<<<cdiv(4 * D, 32), blk, 0, st>>>(dw.gen_b_ih, W(l.dgg), TB, 4 * D, 4 * D);
-        B200_LAUNCH_CHECK();
-        colsum_add_kernel<<<cdiv(4 * D, 32), blk, 0, st>>>(dw.gen_b_hh, W(l.dgg), TB, 4 * D, 4 * D);
-        B200_LAUNCH_CHECK();
-    }
+    B200_TRY(colsum_add(dw.gen_b_ih, dw.gen_b_hh, W(l.dgg), TB, 4 * D, 4 * D, W(l.gpart), st));
     // d h_att (static part) and d ctx (generator-input part, accumulated onto the projection part)
     B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, D, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih, D + M, W(l.dhas), D, 0.f));
     B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, M, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih + D, D + M, W(l.dctxs), M, 1.f));
@@ -704,13 +719,8 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dga), 4 * D, ai, MD, dw.att_w_ih + P, P + M, 1.f));
     B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dga), 4 * D, ai + M, MD, dw.att_w_hh, D, 1.f));
     {
-        dim3 blk(32, 8);
-        colsum_add_kernel<<<cdiv(4 * D, 32), blk, 0, st>>>(dw.att_b_ih, W(l.dga), TB, 4 * D, 4 * D);
-        B200_LAUNCH_CHECK();
-        colsum_add_kernel<<<cdiv(4 * D, 32), blk, 0, st>>>(dw.att_b_hh, W(l.dga), TB, 4 * D, 4 * D);
-        B200_LAUNCH_CHECK();
-        colsum_add_kernel<<<cdiv(A, 32), blk, 0, st>>>(dw.attn_bias, W(l.dq), TB, A, A);
-        B200_LAUNCH_CHECK();
+        B200_TRY(colsum_add(dw.att_b_ih, dw.att_b_hh, W(l.dga), TB, 4 * D, 4 * D, W(l.gpart), st));
+        B200_TRY(colsum_add(dw.attn_bias, nullptr, W(l.dq), TB, A, A, W(l.gpart), st));
     }
     // d Wq = dQ^T . h_att
     B200_TRY(wgemm(st, l, bws, 1, 0, A, D, (int)TB, W(l.dq), A, ai1 + M, MD, dw.attn_query, D, 1.f));
@@ -737,15 +747,12 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
         relu_dropout_bwd_kernel<<<grid_for(TB * P), 256, 0, st>>>(W(l.dp1), W(l.dp1), F(fl.p1), scale1, TB * P);
         B200_LAUNCH_CHECK();
         B200_TRY(wgemm(st, l, bws, 1, 0, P, P, (int)TB, W(l.dp1), P, F(fl.p0), P, dw.prenet_w1, P, 1.f));
-        dim3 blk(32, 8);
-        colsum_add_kernel<<<cdiv(P, 32), blk, 0, st>>>(dw.prenet_b1, W(l.dp1), TB, P, P);
-        B200_LAUNCH_CHECK();
+        B200_TRY(colsum_add(dw.prenet_b1, nullptr, W(l.dp1), TB, P, P, W(l.gpart), st));
         B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, P, P, W(l.dp1), P, w.prenet_w1, P, W(l.dp0), P, 0.f));
         relu_dropout_bwd_kernel<<<grid_for(TB * P), 256, 0, st>>>(W(l.dp0), W(l.dp0), F(fl.p0), scale0, TB * P);
         B200_LAUNCH_CHECK();
         B200_TRY(wgemm(st, l, bws, 1, 0, P, N, (int)TB, W(l.dp0), P, F(fl.xtm), N, dw.prenet_w0, N, 1.f));
-        colsum_add_kernel<<<cdiv(P, 32), blk, 0, st>>>(dw.prenet_b0, W(l.dp0), TB, P, P);
-        B200_LAUNCH_CHECK();
+        B200_TRY(colsum_add(dw.prenet_b0, nullptr, W(l.dp0), TB, P, P, W(l.gpart), st));
     }
     return B200TTS_OK;
 }

@@ -31,6 +31,9 @@ struct PersistLayout {
     size_t wcb;      // bf16 [A, 40]   Wcomb[a][k]
     size_t memTf;    // bf16 [B, MT, 32, 64] fragment-major memory projection
     int MT;
+    int M16;         // ceil(M / 16)
+    size_t memFf;    // uint4 [B, M16, MT, 32]  fragment-major memory^T (context MMA)
+    size_t memFb;    // uint4 [B, MT, M16, 32]  fragment-major memory   (attention-backward weight-gradient MMA)
     size_t barrier;  // grid-barrier counter (+ abort flag at +128 B)
     size_t total;
 };

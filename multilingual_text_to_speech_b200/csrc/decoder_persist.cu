@@ -48,6 +48,7 @@ struct LoopArgs {
     const __nv_bfloat16* memTf; int MT;       // [B][MT][32][64] fragment-major bf16 memory projection
     const float* bias; const float* v;        // [A]
     const __nv_bfloat16* memb; int ldm;       // [B, L, ldm]
+    const uint4* memFf; int M16;              // [B][M16][MT][32] A fragments (m16 x k16 over positions) of memory^T, bf16
     const int* lengths;
     float* cum;                               // [T+1, B, L]
     float* align; long long align_bstride;    // [B, T, L]
@@ -359,20 +360,24 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                 int len = p.lengths[b];
                 len = len < 0 ? 0 : (len > L ? L : len);
                 const float* cum_prev = p.cum + ((size_t)i * B + b) * L;
-                {   // q[a] = sum over the RB per-CTA partial projections; 8 independent loads in flight per thread
-                    const int nsl = PT / A > 0 ? PT / A : 1;            // slices of the RB range (2 for A = 128)
-                    const int a = tid % A, sl = tid / A;
-                    if (sl < nsl) {
-                        float qs[8];
+                {   // q[a] = sum over the RB per-CTA partial projections: thread = (4 attention dims, one eighth of the row blocks),
+                    // all of its 16-byte loads in flight at once
+                    {
+                        const int a4 = tid & 31, sl = tid >> 5;
+                        const int per = (p.RB + 7) / 8, r0 = sl * per, r1 = min(p.RB, r0 + per);
+                        float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (a4 * 4 < A) {
+                            for (int r = r0; r < r1; r += 8) {
+                                float4 v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) qs[j] = 0.f;
-                        const int per = (p.RB + nsl - 1) / nsl, r0 = sl * per, r1 = min(p.RB, r0 + per);
-                        for (int r = r0; r < r1; r += 8) {
+                                for (int j = 0; j < 8; ++j)
+                                    v[j] = (r + j < r1) ? __ldcg(reinterpret_cast<const float4*>(p.qpart + ((size_t)(r + j) * B + b) * A) + a4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (r + j < r1) qs[j] += __ldcg(p.qpart + ((size_t)(r + j) * B + b) * A + a);
+                                for (int j = 0; j < 8; ++j) { qs.x += v[j].x; qs.y += v[j].y; qs.z += v[j].z; qs.w += v[j].w; }
+                            }
+                            *reinterpret_cast<float4*>(cred + sl * A + a4 * 4) = qs;
                         }
-                        cred[sl * A + a] = ((qs[0] + qs[1]) + (qs[2] + qs[3])) + ((qs[4] + qs[5]) + (qs[6] + qs[7]));
                     }
                     // cumulative weights -> (hi, lo) bf16 pairs: Ph[x] = (c[x], c[x+1]) with c[j] = cum[j - half]
                     for (int x = tid; x < p.MT * 16 + 48; x += PT) {
@@ -388,7 +393,8 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                     __syncthreads();
                     for (int a2 = tid; a2 < A; a2 += PT) {
                         float q = 0.f;
-                        for (int sl2 = 0; sl2 < nsl; ++sl2) q += cred[sl2 * A + a2];
+#pragma unroll
+                        for (int sl2 = 0; sl2 < 8; ++sl2) q += cred[sl2 * A + a2];
                         p.qsave[((size_t)i * B + b) * A + a2] = q;
                         qb[a2] = q + p.bias[a2];
                         vv[a2] = p.v[a2];
@@ -454,55 +460,60 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_kernel(const LoopArgs p) {
                 for (int l = tid; l < len; l += PT) { const float ex = expf(e[l] - mx); e[l] = ex; sum += ex; }
                 sum = block_sum(sum, red);
                 float* cum_next = p.cum + ((size_t)(i + 1) * B + b) * L;
-                for (int l = tid; l < L; l += PT) {
-                    const float w = l < len ? e[l] / sum : 0.f;
+                const float inv_sum = 1.f / sum;
+                for (int l = tid; l < p.MT * 16; l += PT) {      // the padded tail must be zero: the context MMA reads whole 16-position tiles
+                    const float w = l < len ? e[l] * inv_sum : 0.f;
                     e[l] = w;
-                    p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
-                    cum_next[l] = __ldcg(cum_prev + l) + w;
+                    if (l < L) {
+                        p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
+                        cum_next[l] = __ldcg(cum_prev + l) + w;
+                    }
                 }
                 __syncthreads();
-                // context: warp per position (4 positions per batch so that 4 x 5 row loads are in flight), lanes over column pairs
-                float cacc[16];
+                // context on the tensor cores: ctx[m] = sum_l memory[l, m] * w[l].  A = memory^T fragments (fragment-major bf16, one
+                // 16-byte load per lane per MMA), B = (hi(w), lo(w)) in columns 0 / 1 -> column 0 + column 1 of D is the fp32-weighted sum.
+                {
+                    const int g = lane >> 2, tq = lane & 3;
+                    const int ktiles = (len + 15) / 16;
+                    for (int mt = warp; mt < p.M16; mt += 8) {
+                        const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt) * p.MT) * 32 + lane;
+                        float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int kt0 = 0; kt0 < ktiles; kt0 += 6) {
+                            uint4 av[6];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) cacc[j] = 0.f;
-                for (int lb = warp; lb < len; lb += 32) {
-                    __nv_bfloat162 rv[4][8];
-                    float wl[4];
+                            for (int j = 0; j < 6; ++j)
+                                if (kt0 + j < ktiles) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
 #pragma unroll
-                    for (int r4 = 0; r4 < 4; ++r4) {
-                        const int l = lb + 8 * r4;
-                        wl[r4] = l < len ? e[l] : 0.f;
-                        const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + (l < len ? l : 0)) * p.ldm);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int m2 = lane + 32 * j;
-                            if (2 * m2 < M) rv[r4][j] = row[m2];
-                        }
-                    }
-#pragma unroll
-                    for (int r4 = 0; r4 < 4; ++r4)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int m2 = lane + 32 * j;
-                            if (2 * m2 < M) {
-                                const float2 v2 = __bfloat1622float2(rv[r4][j]);
-                                cacc[2 * j] = fmaf(wl[r4], v2.x, cacc[2 * j]);
-                                cacc[2 * j + 1] = fmaf(wl[r4], v2.y, cacc[2 * j + 1]);
+                            for (int j = 0; j < 6; ++j) {
+                                if (kt0 + j < ktiles) {
+                                    uint32_t b0 = 0u, b1 = 0u;
+                                    if (g < 2) {
+                                        const float* wl = e + (kt0 + j) * 16 + 2 * tq;
+                                        float w0 = wl[0], w1 = wl[1], w2 = wl[8], w3 = wl[9];
+                                        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+                                        const __nv_bfloat16 h2 = __float2bfloat16_rn(w2), h3 = __float2bfloat16_rn(w3);
+                                        if (g == 1) { w0 -= __bfloat162float(h0); w1 -= __bfloat162float(h1); w2 -= __bfloat162float(h2); w3 -= __bfloat162float(h3); }
+                                        else { w0 = __bfloat162float(h0); w1 = __bfloat162float(h1); w2 = __bfloat162float(h2); w3 = __bfloat162float(h3); }
+                                        b0 = pack2(w0, w1); b1 = pack2(w2, w3);
+                                    }
+                                    const uint32_t af[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+                                    mma_bf16(dacc, af, b0, b1);
+                                }
                             }
                         }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int m2 = lane + 32 * j;
-                    if (2 * m2 < M) { cred[warp * M + 2 * m2] = cacc[2 * j]; if (2 * m2 + 1 < M) cred[warp * M + 2 * m2 + 1] = cacc[2 * j + 1]; }
-                }
-                __syncthreads();
-                for (int m = tid; m < M; m += PT) {
-                    float sctx = 0.f;
-#pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) sctx += cred[w8 * M + m];
-                    p.actf[((size_t)(i + 1) * B + b) * p.ldf + m] = sctx;
-                    p.actb[((size_t)(i + 1) * B + b) * Kp + m] = __float2bfloat16_rn(sctx);
+                        if (tq == 0) {
+                            const int m0 = mt * 16 + g;
+                            const float c0 = dacc[0] + dacc[1], c1 = dacc[2] + dacc[3];
+                            if (m0 < M) {
+                                p.actf[((size_t)(i + 1) * B + b) * p.ldf + m0] = c0;
+                                p.actb[((size_t)(i + 1) * B + b) * Kp + m0] = __float2bfloat16_rn(c0);
+                            }
+                            if (m0 + 8 < M) {
+                                p.actf[((size_t)(i + 1) * B + b) * p.ldf + m0 + 8] = c1;
+                                p.actb[((size_t)(i + 1) * B + b) * Kp + m0 + 8] = __float2bfloat16_rn(c1);
+                            }
+                        }
+                    }
                 }
             }
             PROF_MARK(6);
@@ -557,6 +568,34 @@ __global__ void att_prep_kernel(__nv_bfloat16* __restrict__ WcB, __nv_bfloat16* 
     }
 }
 
+// Fragment-major bf16 copies of the encoder memory for mma.m16n8k16 A operands (one 16-byte load per lane per MMA):
+//   memFf[b][mt][kt][lane] : A[r][c] = memory[b][kt*16 + c][mt*16 + r]   (memory^T: rows = memory dims, k = positions)   -> context
+//   memFb[b][lt][kt][lane] : A[r][c] = memory[b][lt*16 + r][kt*16 + c]   (rows = positions, k = memory dims)             -> d weights
+// lane (g = lane>>2, tq = lane&3) holds {A[g][2tq..+1], A[g+8][2tq..+1], A[g][2tq+8..+9], A[g+8][2tq+8..+9]}; zero padded.
+__global__ void mem_frag_kernel(uint4* __restrict__ memFf, uint4* __restrict__ memFb, const float* __restrict__ memory, int B, int L, int M,
+                                int M16, int MT) {
+    const size_t per = (size_t)B * M16 * MT * 32;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < 2 * per; idx += (size_t)gridDim.x * blockDim.x) {
+        const bool fwd = idx < per;
+        const size_t j = fwd ? idx : idx - per;
+        const int lane = j % 32, g = lane >> 2, tq = lane & 3;
+        int kt, ot, b;
+        if (fwd) { kt = (j / 32) % MT; ot = (j / ((size_t)32 * MT)) % M16; b = j / ((size_t)32 * MT * M16); }
+        else { kt = (j / 32) % M16; ot = (j / ((size_t)32 * M16)) % MT; b = j / ((size_t)32 * M16 * MT); }
+        auto at = [&](int r, int c) -> float {
+            const int l = fwd ? kt * 16 + c : ot * 16 + r;
+            const int m = fwd ? ot * 16 + r : kt * 16 + c;
+            return (l < L && m < M) ? memory[((size_t)b * L + l) * M + m] : 0.f;
+        };
+        uint4 v;
+        v.x = pack2(at(g, 2 * tq), at(g, 2 * tq + 1));
+        v.y = pack2(at(g + 8, 2 * tq), at(g + 8, 2 * tq + 1));
+        v.z = pack2(at(g, 2 * tq + 8), at(g, 2 * tq + 9));
+        v.w = pack2(at(g + 8, 2 * tq + 8), at(g + 8, 2 * tq + 9));
+        (fwd ? memFf : memFb)[j] = v;
+    }
+}
+
 // WcombT[k, a] = sum_c Wloc[a, c] * Wc[c, k]
 __global__ void wcomb_kernel(float* __restrict__ WcombT, const float* __restrict__ Wloc, const float* __restrict__ Wc, int A, int C, int K) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -593,6 +632,9 @@ PersistLayout persist_layout(const b200tts_decoder_shape& s) {
     l.wcb = take((size_t)s.A * 40 * 2);
     l.MT = (s.L + 15) / 16;
     l.memTf = take((size_t)s.B * l.MT * 32 * 64 * 2);
+    l.M16 = (s.M + 15) / 16;
+    l.memFf = take((size_t)s.B * l.M16 * l.MT * 32 * 16);
+    l.memFb = take((size_t)s.B * l.M16 * l.MT * 32 * 16);
     l.barrier = take(256 + 148 * 8 * 8 * 2);   // barrier + abort flag, then 2 x [148][8] profile counters
     l.total = off;
     return l;
@@ -646,6 +688,9 @@ int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     __nv_bfloat16* memTf = reinterpret_cast<__nv_bfloat16*>(pws + l.memTf);
     att_prep_kernel<<<148 * 4, 256, 0, st>>>(wcb, memTf, wcombT, ws + fl.memT, B, s.L, s.A, s.K, l.MT);
     B200_LAUNCH_CHECK();
+    uint4* memFf = reinterpret_cast<uint4*>(pws + l.memFf);
+    mem_frag_kernel<<<148 * 4, 256, 0, st>>>(memFf, reinterpret_cast<uint4*>(pws + l.memFb), in.memory, B, s.L, M, l.M16, l.MT);
+    B200_LAUNCH_CHECK();
     // padding columns [MD, Kp) of every operand row must be zero (weights there are zero too, but NaN * 0 would poison)
     if (l.Kp_att != MD) B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)(T + 1) * B * l.Kp_att * 2, st));
     LoopArgs a{};
@@ -656,7 +701,7 @@ int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     a.mask_h = in.mask_att_h; a.mask_c = in.mask_att_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
     a.L = s.L; a.M = M; a.A = s.A; a.KC = s.K;
     a.Wq = w.attn_query; a.qpart = ws + fl.qpart; a.qsave = ws + fl.q; a.WcB = wcb; a.memTf = memTf; a.MT = l.MT; a.bias = w.attn_bias; a.v = w.attn_energy;
-    a.memb = memb; a.ldm = l.ldm; a.lengths = in.text_lengths; a.cum = ws + fl.cum;
+    a.memb = memb; a.ldm = l.ldm; a.memFf = memFf; a.M16 = l.M16; a.lengths = in.text_lengths; a.cum = ws + fl.cum;
     a.align = align; a.align_bstride = (long long)T * s.L;
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
     a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256);

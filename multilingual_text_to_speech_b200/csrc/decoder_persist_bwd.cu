@@ -252,6 +252,7 @@ struct AttBwdArgs {
     const __nv_bfloat16* WcB2;                            // [32][A+8] Wcomb^T[k][a], a contiguous
     const __nv_bfloat16* memTf;                           // [B][MT][32 lanes][64] fragment-major memory projection
     const __nv_bfloat16* memb; int ldm;                   // [B, L, ldm]
+    const uint4* memFb; int M16;                          // [B][MT][M16][32] A fragments (rows = positions, k = memory dims), bf16
     const int* lengths;
     int dqp_after_g;                                      // 1: dq partials live after the G tile buffer, 0: alias the scratch head
     float* dctx_tot;                                      // [T, B, M] out
@@ -364,42 +365,50 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
             for (int a = tid; a < A; a += PT) { s_qb[a] = p.q[((size_t)i * B + b) * A + a] + p.bias[a]; s_vv[a] = p.v[a]; }
             build_pairs(s_Ph, s_Pl, p.cum + ((size_t)i * B + b) * L, L, half, L16 + 48, tid, PT);
             __syncthreads();
-            // dw[l] = dalign + dcum + <dctx, memory[l]>   (4 positions per warp batch: 4 x 5 row loads in flight)
-            for (int lb = warp; lb < L16; lb += 32) {
-                __nv_bfloat162 rv[4][8];
+            // dw[l] = dalign + dcum + <dctx, memory[l]> on the tensor cores: A = fragment-major memory (one 16-byte load per lane per
+            // MMA), B = (hi(dctx), lo(dctx)) in columns 0 / 1; warp owns position tiles {warp, warp + 8}
+            {
+                const int g = lane >> 2, tq = lane & 3;
+                for (int lt = warp; lt < p.MT; lt += 8) {
+                    float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (lt * 16 < len) {
+                        const uint4* fr = p.memFb + (((size_t)b * p.MT + lt) * p.M16) * 32 + lane;
+                        for (int kt0 = 0; kt0 < p.M16; kt0 += 6) {
+                            uint4 av[6];
 #pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    const int l = lb + 8 * r4;
-                    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(p.memb + ((size_t)b * L + (l < len ? l : 0)) * p.ldm);
+                            for (int j = 0; j < 6; ++j)
+                                if (kt0 + j < p.M16) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int m2 = lane + 32 * j;
-                        if (2 * m2 < M && l < len) rv[r4][j] = row[m2];
-                    }
-                }
-#pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    const int l = lb + 8 * r4;
-                    float acc = 0.f;
-                    if (l < len) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int m2 = lane + 32 * j;
-                            if (2 * m2 < M) {
-                                const float2 v2 = __bfloat1622float2(rv[r4][j]);
-                                acc = fmaf(s_dctx[2 * m2], v2.x, acc);
-                                if (2 * m2 + 1 < M) acc = fmaf(s_dctx[2 * m2 + 1], v2.y, acc);
+                            for (int j = 0; j < 6; ++j) {
+                                if (kt0 + j < p.M16) {
+                                    uint32_t bb0 = 0u, bb1 = 0u;
+                                    if (g < 2) {
+                                        const int m0 = (kt0 + j) * 16 + 2 * tq;
+                                        float w0 = m0 < M ? s_dctx[m0] : 0.f, w1 = m0 + 1 < M ? s_dctx[m0 + 1] : 0.f;
+                                        float w2 = m0 + 8 < M ? s_dctx[m0 + 8] : 0.f, w3 = m0 + 9 < M ? s_dctx[m0 + 9] : 0.f;
+                                        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+                                        const __nv_bfloat16 h2 = __float2bfloat16_rn(w2), h3 = __float2bfloat16_rn(w3);
+                                        if (g == 1) { w0 -= __bfloat162float(h0); w1 -= __bfloat162float(h1); w2 -= __bfloat162float(h2); w3 -= __bfloat162float(h3); }
+                                        else { w0 = __bfloat162float(h0); w1 = __bfloat162float(h1); w2 = __bfloat162float(h2); w3 = __bfloat162float(h3); }
+                                        bb0 = pack2(w0, w1); bb1 = pack2(w2, w3);
+                                    }
+                                    const uint32_t af[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+                                    mma_bf16(dacc, af, bb0, bb1);
+                                }
                             }
                         }
                     }
-                    acc = warp_sum(acc);
-                    if (lane == 0 && l < L16) {
-                        float g = 0.f;
-                        if (l < len) {
-                            g = acc + (last ? 0.f : dcum[l]);
-                            if (p.dalign) g += p.dalign[(size_t)b * p.dalign_bstride + (size_t)i * L + l];
+                    if (tq == 0) {
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int l = lt * 16 + g + 8 * rr;
+                            float gv = 0.f;
+                            if (l < len) {
+                                gv = (rr ? dacc[2] + dacc[3] : dacc[0] + dacc[1]) + (last ? 0.f : dcum[l]);
+                                if (p.dalign) gv += p.dalign[(size_t)b * p.dalign_bstride + (size_t)i * L + l];
+                            }
+                            s_de[l] = gv;
                         }
-                        s_de[l] = g;
                     }
                 }
             }
@@ -909,6 +918,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     __nv_bfloat16* memTf = reinterpret_cast<__nv_bfloat16*>(extra + x.memTf);
     a.WcB = wcb; a.WcB2 = wcb2; a.memTf = memTf;
     a.memb = reinterpret_cast<const __nv_bfloat16*>(pws + pl.memb); a.ldm = pl.ldm;
+    a.memFb = reinterpret_cast<const uint4*>(pws + pl.memFb); a.M16 = pl.M16;
     a.dqp_after_g = att_bwd_dqp_mode(s);
     a.lengths = in.text_lengths; a.dctx_tot = dctx_tot; a.dq = dq; a.de = reinterpret_cast<float*>(extra + x.de);
     a.barrier = reinterpret_cast<unsigned*>(extra + x.barrier); a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);

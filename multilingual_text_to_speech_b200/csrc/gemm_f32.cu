@@ -271,7 +271,15 @@ int gemm_run_auto(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t
 
 // Picks a split-K factor so that small-output / long-K products still fill the 148 SMs, bounded by the
 // scratch the caller provides for the partial sums.
+int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled);
+
 static int gemm_auto_impl(GemmDesc d, float* scratch, size_t scratch_elems, cudaStream_t stream, bool bf16) {
+    if (bf16) {     // long-K products run un-split on the tcgen05 kernel (no partial round trip); it declines what it cannot take
+        d.splitk = 1; d.partial = nullptr; d.keep_partials = 0;
+        bool handled = false;
+        B200_TRY(gemm_tc_try(d, stream, &handled));
+        if (handled) return B200TTS_OK;
+    }
     const bool big = bf16 || (d.M > 64 && d.N > 64);
     const long long tiles = (long long)(big ? cdiv(d.M, 128) * cdiv(d.N, 128) : cdiv(d.M, 64) * cdiv(d.N, 64)) * d.batch;
     int s = 1;

@@ -8,7 +8,9 @@
 //                        mbarrier expect_tx / complete_tx
 //   warp 5 (one lane)  : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 128, K = 16 per instruction,
 //                        accumulator in TMEM (128 lanes x 128 columns fp32); tcgen05.commit frees ring slots
-//   warps 0-3          : epilogue      -- tcgen05.ld (32 lanes x 32 columns per instruction) -> alpha/beta/bias -> global
+//   warps 0-3          : epilogue      -- tcgen05.ld (32 lanes x 32 columns per instruction) -> staged through the (now idle)
+//                        operand ring so that every global store is a full 512-byte row segment -> alpha/beta/bias -> global
+// Two CTAs are co-resident per SM (3 x 32 KB ring each, 128 TMEM columns each): one tile's epilogue overlaps the other's main loop.
 // Every mbarrier wait carries a clock64 watchdog that traps instead of hanging the device.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -19,10 +21,12 @@ namespace b200tts {
 namespace {
 
 constexpr int TBM = 128, TBN = 128, TBK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int STAGE_BYTES = (TBM + TBN) * TBK * 2;          // 32 KB
 constexpr int TC_THREADS = 192;
 constexpr int TMEM_COLS = 128;
+constexpr int STG_LD = TBN + 4;                             // fp32 row stride of the epilogue staging tile (16-byte aligned, conflict-free)
+static_assert(4 * 32 * STG_LD * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -101,7 +105,7 @@ struct TcArgs {
     long long strideC;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned ring (128B swizzle atoms are 1024 B)
@@ -159,24 +163,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(&tmem_full_bar);
         }
     } else {
-        // epilogue: warp w owns TMEM lanes [32w, 32w + 32) = rows m0 + 32w + lane
+        // epilogue: warp w owns TMEM lanes [32w, 32w + 32) = rows m0 + 32w + lane.  tmem_full implies every MMA (and therefore
+        // every TMA load) of this tile has completed, so the operand ring is free to stage the fp32 tile.
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = m0 + warp * 32 + lane;
-        float* crow = p.C + (size_t)bz * p.strideC + (size_t)m * p.ldc;
+        float* stg = reinterpret_cast<float*>(ring) + (size_t)warp * 32 * STG_LD;
 #pragma unroll 1
         for (int c = 0; c < TBN / 32; ++c) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
-            if (m < p.M) {
+            float4* dst = reinterpret_cast<float4*>(stg + (size_t)lane * STG_LD + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c * 32 + j;
-                    if (n < p.N) {
-                        float v = p.alpha * __uint_as_float(r[j]);
-                        if (p.bias) v += p.bias[n];
-                        if (p.beta != 0.f) v += p.beta * crow[n];
-                        crow[n] = v;
+            for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                     __uint_as_float(r[4 * j + 3]));
+        }
+        __syncwarp();
+        float* cbase = p.C + (size_t)bz * p.strideC;
+        const int rows = min(32, p.M - (m0 + warp * 32));
+        const int n = n0 + 4 * lane;
+        const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0) && (n0 + TBN <= p.N);   // warp-uniform
+        if (vec) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = make_float4(p.bias[n], p.bias[n + 1], p.bias[n + 2], p.bias[n + 3]);
+#pragma unroll 4
+            for (int rr = 0; rr < rows; ++rr) {
+                const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)rr * STG_LD + 4 * lane);
+                float4* cp = reinterpret_cast<float4*>(cbase + (size_t)(m0 + warp * 32 + rr) * p.ldc + n);
+                float4 v = make_float4(fmaf(p.alpha, a.x, bv.x), fmaf(p.alpha, a.y, bv.y), fmaf(p.alpha, a.z, bv.z), fmaf(p.alpha, a.w, bv.w));
+                if (p.beta != 0.f) {
+                    const float4 o = *cp;
+                    v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y); v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+                }
+                *cp = v;
+            }
+        } else {
+            for (int rr = 0; rr < rows; ++rr) {
+                float* crow = cbase + (size_t)(m0 + warp * 32 + rr) * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int nn = n0 + j * 32 + lane;
+                    if (nn < p.N) {
+                        float v = p.alpha * stg[(size_t)rr * STG_LD + j * 32 + lane];
+                        if (p.bias) v += p.bias[nn];
+                        if (p.beta != 0.f) v += p.beta * crow[nn];
+                        crow[nn] = v;
                     }
                 }
             }

@@ -146,8 +146,8 @@ def test_decoder_bf16_perf_mode(kw):
 
 
 @pytest.mark.parametrize('M,N,K,ta,tb', [
-    (128, 128, 64, False, True), (256, 384, 512, False, True), (300, 260, 513, False, True), (1000, 4096, 1312, False, True),
-    (4096, 288, 640, True, False), (513, 130, 2000, True, True), (200, 1000, 72, False, False),
+    (256, 256, 256, False, True), (256, 384, 512, False, True), (300, 260, 513, False, True), (1000, 4096, 1312, False, True),
+    (4096, 288, 640, True, False), (513, 130, 2000, True, True), (200, 1000, 96, False, False),
 ])
 def test_gemm_tcgen05_path(M, N, K, ta, tb):
     """tcgen05 / TMEM / TMA GEMM (gemm_tc.cu) against fp64 on bf16-rounded operands, and against the mma.sync kernel."""
