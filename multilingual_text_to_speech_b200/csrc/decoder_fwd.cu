@@ -530,9 +530,11 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
     if (persistent) {
         // bf16 perf mode: one cooperative, weight-stationary kernel per recurrence (decoder_persist.cu)
         unsigned char* pws = reinterpret_cast<unsigned char*>(c.at(l.persist));
-        B200_TRY(persist_att_loop(s, w, in, l, ws, pws, out.alignments, st));
+        const bool tc = tc_persist_supported(s);         // TMA + tcgen05 + TMEM loops (decoder_persist_tc.cu) when D % 64 == 0
+        B200_TRY(persist_att_prep(s, w, in, l, ws, pws, st));
+        B200_TRY(tc ? tc_persist_att_loop(s, w, in, l, ws, pws, out.alignments, st) : persist_att_loop(s, w, in, l, ws, pws, out.alignments, st));
         B200_TRY(gen_input_proj(c, 0, T));
-        B200_TRY(persist_gen_loop(s, w, in, l, ws, pws, st));
+        B200_TRY(tc ? tc_persist_gen_loop(s, w, in, l, ws, pws, st) : persist_gen_loop(s, w, in, l, ws, pws, st));
         B200_TRY(frame_proj(c, 0, T));
     } else if (!sequential) {
         for (int i = 0; i < T; ++i) B200_TRY(att_step(c, i, out.alignments));

@@ -101,6 +101,17 @@ static inline DecoderLayout decoder_layout(const b200tts_decoder_shape& s) {
 }
 
 int validate_decoder_shape(const b200tts_decoder_shape& s);
+// tcgen05 / TMA persistent forward loops (decoder_persist_tc.cu): operand rows are [h | ctx | 0] in 64-column k-blocks
+struct TcPersistGeom { int Kp_att, Kp_gen, nkb_att, nkb_gen, nkb_h, ns_att, ns_gen; };
+TcPersistGeom tc_persist_geom(const b200tts_decoder_shape& s);
+bool tc_persist_supported(const b200tts_decoder_shape& s);
+int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                        const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st);
+int tc_persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                        const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st);
+// attention operands of the persistent loops (bf16 memory, Wcomb, fragment-major projections) -> persistent workspace
+int persist_att_prep(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                     const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st);
 int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                      const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st);
 struct AttBwdExtra { int MT; size_t dgb, part, wcb, wcb2, memTf, de, dwpart, dvpart, barrier, total; };

@@ -667,19 +667,13 @@ static int launch_loop(bool att, const LoopArgs& a, size_t smem, cudaStream_t st
     return B200TTS_OK;
 }
 
-// Attention-LSTM + attention loop (all T steps).  Expects: ga = input projection, ai row 0 = 0, ca row 0 = 0, cum row 0 = 0.
-int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
-                     const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st) {
+// bf16 memory, Wcomb and the fragment-major projections shared by the forward and backward persistent kernels
+int persist_att_prep(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                     const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st) {
     const PersistLayout l = persist_layout(s);
-    const int B = s.B, T = s.T, D = s.D, M = s.M, MD = M + D;
-    __nv_bfloat16* aib = reinterpret_cast<__nv_bfloat16*>(pws + l.aib);
-    __nv_bfloat16* memTb = reinterpret_cast<__nv_bfloat16*>(pws + l.memTb);
+    const int B = s.B, M = s.M;
     __nv_bfloat16* memb = reinterpret_cast<__nv_bfloat16*>(pws + l.memb);
     float* wcombT = reinterpret_cast<float*>(pws + l.wcombT);
-    unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
-    B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)B * l.Kp_att * 2, st));                 // operand of step 0
-    B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
-    (void)memTb;
     f32_to_bf16_rows_kernel<<<grid_for((size_t)B * s.L * l.ldm), 256, 0, st>>>(memb, l.ldm, in.memory, M, (size_t)B * s.L, M);
     B200_LAUNCH_CHECK();
     wcomb_kernel<<<cdiv(s.K * s.A, 256), 256, 0, st>>>(wcombT, w.attn_location, w.attn_loc_features, s.A, s.C, s.K);
@@ -688,9 +682,26 @@ int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
     __nv_bfloat16* memTf = reinterpret_cast<__nv_bfloat16*>(pws + l.memTf);
     att_prep_kernel<<<148 * 4, 256, 0, st>>>(wcb, memTf, wcombT, ws + fl.memT, B, s.L, s.A, s.K, l.MT);
     B200_LAUNCH_CHECK();
-    uint4* memFf = reinterpret_cast<uint4*>(pws + l.memFf);
-    mem_frag_kernel<<<148 * 4, 256, 0, st>>>(memFf, reinterpret_cast<uint4*>(pws + l.memFb), in.memory, B, s.L, M, l.M16, l.MT);
+    mem_frag_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<uint4*>(pws + l.memFf), reinterpret_cast<uint4*>(pws + l.memFb), in.memory, B,
+                                             s.L, M, l.M16, l.MT);
     B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+
+// Attention-LSTM + attention loop (all T steps), mma.sync variant (any D % 16 == 0).  Expects: ga = input projection, ai row 0 = 0,
+// ca row 0 = 0, cum row 0 = 0 and persist_att_prep() done.
+int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                     const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st) {
+    const PersistLayout l = persist_layout(s);
+    const int B = s.B, T = s.T, D = s.D, M = s.M, MD = M + D;
+    __nv_bfloat16* aib = reinterpret_cast<__nv_bfloat16*>(pws + l.aib);
+    __nv_bfloat16* memb = reinterpret_cast<__nv_bfloat16*>(pws + l.memb);
+    unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
+    B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)B * l.Kp_att * 2, st));                 // operand of step 0
+    B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
+    __nv_bfloat16* wcb = reinterpret_cast<__nv_bfloat16*>(pws + l.wcb);
+    __nv_bfloat16* memTf = reinterpret_cast<__nv_bfloat16*>(pws + l.memTf);
+    uint4* memFf = reinterpret_cast<uint4*>(pws + l.memFf);
     // padding columns [MD, Kp) of every operand row must be zero (weights there are zero too, but NaN * 0 would poison)
     if (l.Kp_att != MD) B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)(T + 1) * B * l.Kp_att * 2, st));
     LoopArgs a{};

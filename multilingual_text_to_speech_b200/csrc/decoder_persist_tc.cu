@@ -1,0 +1,725 @@
+// Persistent recurrent kernels of the bf16 perf mode (forward), Blackwell-native: TMA + tcgen05 + TMEM.
+//
+// ONE cooperative launch runs all T steps of an LSTM recurrence (attention-LSTM + location-sensitive attention, or the
+// generator LSTM).  CTA (rb, bh) owns 16 hidden units x {i,f,g,o} = 64 gate rows and a batch half of 32 utterances:
+//   * weight-stationary: the bf16 slice W[64 rows, K] lives in shared memory for the whole sequence, laid out as
+//     K-major SWIZZLE_128B tiles of 64 x 64 (8 KB) -- the A operand of tcgen05.mma (M = 64);
+//   * per step the bf16 activation operand [32 utterances x K] is fetched by TMA (cp.async.bulk.tensor, 64-column boxes,
+//     SWIZZLE_128B) into a small ring -- the B operand (N = 32); one elected thread issues tcgen05.mma.kind::f16
+//     (K = 16 per instruction), the fp32 accumulator [64 x 32] lives in TMEM; tcgen05.commit recycles ring slots;
+//   * warp roles: warps 0-7 compute (epilogue: tcgen05.ld -> LSTM cell / regulariser -> state stores, attention),
+//     warp 8 lane 0 = TMA producer, warp 9 lane 0 = MMA issuer;
+//   * the K range is ordered [h | ctx]: the h part (available after the cell barrier) is loaded and multiplied WHILE
+//     the attention of the same step runs; only the short ctx part (5 boxes) follows the attention barrier;
+//   * grid barriers are monotonic counters in global memory; every wait carries a clock64 watchdog.
+// fp32 state (c, h, gates, cumulative weights, context, alignments) is written exactly where the fp32 per-step path
+// writes it, so the backward pass is unaffected.
+// Reference semantics: modules/tacotron2.py:180-198, modules/layers.py:18-47, modules/attention.py:39-86.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "decoder_internal.cuh"
+
+namespace b200tts {
+
+int tc_make_map_bf16(void* map, const void* base, int rows, int K, int Kp, int batch, int box_rows);   // gemm_tc.cu
+
+namespace {
+
+constexpr int NCW = 8;                  // compute warps
+constexpr int CT = 32 * NCW;            // compute threads
+constexpr int PT = CT + 64;             // + TMA producer warp + MMA issuer warp
+constexpr int UNITS = 16;               // hidden units per CTA
+constexpr int ROWS = 4 * UNITS;         // gate rows per CTA (MMA M)
+constexpr int BT = 32;                  // utterances per CTA (MMA N)
+constexpr int KB = 64;                  // K columns per tile / TMA box (128-byte rows)
+constexpr int WTILE = ROWS * KB * 2;    // 8 KB
+constexpr int ATILE = BT * KB * 2;      // 4 KB
+constexpr int MAXNS = 16;               // ring stages (run-time value <= MAXNS)
+constexpr int TMEM_COLS = 32;
+
+struct TcLoopArgs {
+    int B, T, D, K, Kp, RB, NBH;
+    int nkb, nkb_h, NS;                       // k-blocks in total / in the h part; ring stages
+    const float* W; int ldw; int wcol_h, wcol_c;   // fp32 weights [4D, ldw]: operand column k < D -> wcol_h + k, else wcol_c + k - D
+    __nv_bfloat16* actb;                      // [T+1, B, Kp] bf16 operand rows: [h | ctx | 0]
+    float* actf; int ldf; int hcol;           // fp32 mirror ([T+1, B, ldf]); h at column hcol, ctx at column 0
+    float* gates;                             // [T, B, 4D] in: input projection (+biases); out: activated gates
+    float* cstate;                            // [T+1, B, D]
+    const uint8_t* mask_h; const uint8_t* mask_c;
+    int kind, training; float rate_h, rate_c;
+    // attention (ATT instantiation only)
+    int L, M, A, KC;
+    const float* Wq; float* qpart; float* qsave;
+    const __nv_bfloat16* WcB;                 // [A][40]
+    const __nv_bfloat16* memTf; int MT;       // [B][MT][32][64]
+    const float* bias; const float* v;
+    const uint4* memFf; int M16;              // [B][M16][MT][32]
+    const int* lengths;
+    float* cum; float* align; long long align_bstride;
+    unsigned* barrier; int* abort_flag;
+    long long* prof;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) __trap();       // ~2 s: a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barrier among the compute warps only
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
+
+// K-major SWIZZLE_128B operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart): UMMA shared-memory descriptor
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Block-wide max / sum among the CT compute threads (named barrier 1); `scratch` holds >= 33 floats.
+__device__ __forceinline__ float cblock_max(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_max(v);
+    csync();
+    if (lane == 0) scratch[warp] = v;
+    csync();
+    float t = scratch[lane & (NCW - 1)];
+#pragma unroll
+    for (int o = NCW / 2; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return t;
+}
+__device__ __forceinline__ float cblock_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    csync();
+    if (lane == 0) scratch[warp] = v;
+    csync();
+    float t = scratch[lane & (NCW - 1)];
+#pragma unroll
+    for (int o = NCW / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+
+// Monotonic-counter grid barrier over ALL threads of every CTA.  Returns false if the watchdog fired.
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag, int* s_ok) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        int ok = 1;
+        const long long t0 = clock64();
+        while (ld_acquire(counter) < target) {
+            if (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag)) { ok = 0; *abort_flag = 1; break; }
+        }
+        __threadfence();
+        *s_ok = ok;
+    }
+    __syncthreads();
+    return *s_ok != 0;
+}
+
+template <bool ATT>
+__global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const TcLoopArgs p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw0[];
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw0) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[MAXNS], empty_bar[MAXNS], accum_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_ok;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const int rb = cta % p.RB, bh = cta / p.RB;
+    const int u0 = rb * UNITS, b0 = bh * BT;
+    const int Kp = p.Kp, D = p.D, B = p.B, NS = p.NS;
+    const unsigned nblocks = gridDim.x;
+    const bool compute = warp < NCW;
+    const bool is_producer = (warp == NCW) && lane == 0;
+    const bool is_mma = (warp == NCW + 1) && lane == 0;
+
+    // ---- shared memory carve-up (1024-byte aligned base: SWIZZLE_128B atoms) ----
+    size_t off = 0;
+    unsigned char* sW = smem_raw + off; off += (size_t)p.nkb * WTILE;                 // [nkb][64 rows][128 B] swizzled
+    unsigned char* ring = smem_raw + off; off += (size_t)NS * ATILE;                  // [NS][32 rows][128 B] swizzled (TMA)
+    float* s_sum = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (ROWS + 1) * 4;
+    float* s_hs = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)UNITS * (BT + 4) * 4 : 0;
+    float* s_wq = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)p.A * (UNITS + 1) * 4 : 0;
+    __nv_bfloat16* sWcB = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += ATT ? (size_t)p.A * 40 * 2 : 0;
+    float* scratch = reinterpret_cast<float*>(smem_raw + off);                        // attention scratch (ATT only)
+
+    // ---- one-time: resident weight slice fp32 -> bf16 in the canonical K-major SWIZZLE_128B layout ----
+    for (int idx = tid; idx < ROWS * p.nkb * KB; idx += PT) {
+        const int r = idx / (p.nkb * KB), k = idx % (p.nkb * KB);
+        const int g = r / UNITS, u = r % UNITS;
+        float w = 0.f;
+        if (k < p.K && u0 + u < D) w = p.W[(size_t)(g * D + u0 + u) * p.ldw + (k < D ? p.wcol_h + k : p.wcol_c + (k - D))];
+        const int kb = k / KB, kc = k % KB, chunk = kc >> 3, e = kc & 7;
+        *reinterpret_cast<__nv_bfloat16*>(sW + (size_t)kb * WTILE + r * 128 + ((chunk ^ (r & 7)) << 4) + e * 2) = __float2bfloat16_rn(w);
+    }
+    if (ATT) {
+        for (int idx = tid; idx < p.A * UNITS; idx += PT) {
+            const int a = idx / UNITS, u = idx % UNITS;
+            s_wq[a * (UNITS + 1) + u] = (u0 + u < D) ? p.Wq[(size_t)a * D + u0 + u] : 0.f;
+        }
+        for (int idx = tid; idx < p.A * 40; idx += PT) sWcB[idx] = p.WcB[idx];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == NCW + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    proxy_fence_shared();              // the weight tiles were written through the generic proxy; tcgen05.mma reads via the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+
+    uint32_t prod_it = 0, cons_it = 0;            // running box counters of the producer / MMA thread
+    // TMA producer: operand row block of `step`, k-blocks [kb0, kb1)
+    auto produce = [&](int step, int kb0, int kb1) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int s = prod_it % NS;
+            mbar_wait(&empty_bar[s], ((prod_it / NS) & 1) ^ 1);
+            mbar_expect_tx(&full_bar[s], ATILE);
+            tma_load_3d(ring + (size_t)s * ATILE, &tmAct, &full_bar[s], kb * KB, step * B + b0, 0);
+            ++prod_it;
+        }
+    };
+    // MMA issuer: acc (+)= W[:, kb] . act[:, kb]^T for k-blocks [kb0, kb1)
+    auto consume = [&](int kb0, int kb1, bool zero_first, bool signal_accum) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int s = cons_it % NS;
+            mbar_wait(&full_bar[s], (cons_it / NS) & 1);
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_desc(smem_u32(sW + (size_t)kb * WTILE));
+            const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)s * ATILE));
+#pragma unroll
+            for (int k = 0; k < KB / 16; ++k)
+                umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (zero_first && kb == kb0 && k == 0) ? 0u : 1u);
+            umma_commit(&empty_bar[s]);
+            ++cons_it;
+        }
+        if (signal_accum) umma_commit(&accum_bar);
+    };
+
+    const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
+    unsigned target = 0;
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#define PROF_MARK(slot)                                                      \
+    do {                                                                     \
+        if (p.prof && tid == 0) { const long long now = clock64(); prof_acc[slot] += now - prof_t; prof_t = now; } \
+    } while (0)
+
+    // prologue: the h part of step 0 (operand row 0 is all zeros)
+    if (is_producer) produce(0, 0, p.nkb_h);
+    if (is_mma) consume(0, p.nkb_h, true, !ATT || p.nkb_h == p.nkb);
+    __syncwarp();
+
+    bool alive = true;
+    for (int i = 0; i < p.T && alive; ++i) {
+        // =================== ctx part of the gate product (the context of step i-1 is visible now) ===================
+        if (ATT && p.nkb_h < p.nkb) {
+            if (is_producer) { proxy_fence_global(); produce(i, p.nkb_h, p.nkb); }
+            if (is_mma) consume(p.nkb_h, p.nkb, false, true);
+            __syncwarp();
+        }
+        if (compute) {
+            // prefetch the epilogue operands of this thread's two (b, u) pairs: their latency hides behind the product
+            float pre[2][6];
+            uint8_t pm[2][2];
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+                const int idx = tid + e2 * CT;
+                const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
+                pm[e2][0] = 1; pm[e2][1] = 1;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) pre[e2][j] = 0.f;
+                if (b < B && u < D) {
+                    const size_t g0 = ((size_t)i * B + b) * 4 * D + u, mi = ((size_t)i * B + b) * D + u;
+                    pre[e2][0] = p.gates[g0]; pre[e2][1] = p.gates[g0 + D]; pre[e2][2] = p.gates[g0 + 2 * D]; pre[e2][3] = p.gates[g0 + 3 * D];
+                    pre[e2][4] = p.cstate[mi];
+                    if (p.kind == B200TTS_CELL_ZONEOUT) pre[e2][5] = p.actf[((size_t)i * B + b) * p.ldf + p.hcol + u];
+                    if (p.training && p.mask_h) pm[e2][0] = p.mask_h[mi];
+                    if (p.training && p.mask_c) pm[e2][1] = p.mask_c[mi];
+                }
+            }
+            // accumulator [64 gate rows x 32 utterances]: TMEM lane 32 * gate + unit, column = utterance
+            mbar_wait(&accum_bar, i & 1);
+            tc_fence_after();
+            PROF_MARK(0);
+            {
+                const int q = warp & 3, c0 = (warp >> 2) * 16;
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (lane < UNITS) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) s_sum[(c0 + j) * (ROWS + 1) + q * UNITS + lane] = __uint_as_float(r[j]);
+                }
+            }
+            tc_fence_before();
+            csync();
+            PROF_MARK(1);
+            // =================== LSTM cell + regulariser (2 (b, u) pairs per thread) ===================
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+                const int idx = tid + e2 * CT;
+                const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
+                float hs = 0.f;
+                if (b < B && u < D) {
+                    const size_t g0 = ((size_t)i * B + b) * 4 * D + u;
+                    const float zi = pre[e2][0] + s_sum[bl * (ROWS + 1) + uu];
+                    const float zf = pre[e2][1] + s_sum[bl * (ROWS + 1) + UNITS + uu];
+                    const float zg = pre[e2][2] + s_sum[bl * (ROWS + 1) + 2 * UNITS + uu];
+                    const float zo = pre[e2][3] + s_sum[bl * (ROWS + 1) + 3 * UNITS + uu];
+                    const float gi = sigmoidf_acc(zi), gf = sigmoidf_acc(zf), gg = tanhf(zg), go = sigmoidf_acc(zo);
+                    const size_t bu = (size_t)b * D + u;
+                    const float cp = pre[e2][4];
+                    float cn = gf * cp + gi * gg;
+                    float hn = go * tanhf(cn);
+                    p.gates[g0] = gi; p.gates[g0 + D] = gf; p.gates[g0 + 2 * D] = gg; p.gates[g0 + 3 * D] = go;
+                    if (p.kind == B200TTS_CELL_ZONEOUT) {
+                        const float hp = pre[e2][5];
+                        if (p.training) {
+                            float dh = hn - hp, dc = cn - cp;
+                            if (p.mask_h) dh = dh * (float)pm[e2][0] * inv_h;
+                            if (p.mask_c) dc = dc * (float)pm[e2][1] * inv_c;
+                            hn = (1.f - p.rate_h) * dh + hp;
+                            cn = (1.f - p.rate_c) * dc + cp;
+                        } else {
+                            hn = p.rate_h * hp + (1.f - p.rate_h) * hn;
+                            cn = p.rate_c * cp + (1.f - p.rate_c) * cn;
+                        }
+                    } else if (p.training && p.mask_h) {
+                        hn = hn * (float)pm[e2][0] * inv_h;
+                    }
+                    p.cstate[(size_t)(i + 1) * B * D + bu] = cn;
+                    p.actf[((size_t)(i + 1) * B + b) * p.ldf + p.hcol + u] = hn;
+                    p.actb[((size_t)(i + 1) * B + b) * Kp + u] = __float2bfloat16_rn(hn);
+                    hs = hn;
+                }
+                if (ATT) s_hs[uu * (BT + 4) + bl] = hs;
+            }
+            if (ATT) {
+                csync();
+                // partial query projection of this CTA's 16 hidden units: qpart[rb, b, a]; thread = (a, 16 utterances)
+                for (int idx = tid; idx < p.A * (BT / 16); idx += CT) {
+                    const int a = idx % p.A, bg = idx / p.A;
+                    float qa[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) qa[j] = 0.f;
+#pragma unroll
+                    for (int uu = 0; uu < UNITS; ++uu) {
+                        const float wv = s_wq[a * (UNITS + 1) + uu];
+                        const float4* h4 = reinterpret_cast<const float4*>(&s_hs[uu * (BT + 4) + bg * 16]);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 hv = h4[j4];
+                            qa[4 * j4] = fmaf(wv, hv.x, qa[4 * j4]); qa[4 * j4 + 1] = fmaf(wv, hv.y, qa[4 * j4 + 1]);
+                            qa[4 * j4 + 2] = fmaf(wv, hv.z, qa[4 * j4 + 2]); qa[4 * j4 + 3] = fmaf(wv, hv.w, qa[4 * j4 + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (b0 + bg * 16 + j < B) p.qpart[((size_t)rb * B + b0 + bg * 16 + j) * p.A + a] = qa[j];
+                }
+            }
+            proxy_fence_global();          // the bf16 h values are read by other CTAs' TMA (async proxy) after the barrier
+        }
+        PROF_MARK(2);
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
+        PROF_MARK(3);
+
+        // =================== h part of step i+1: TMA + tcgen05 run while the attention of step i is computed ===================
+        if (i + 1 < p.T) {
+            if (is_producer) { proxy_fence_global(); produce(i + 1, 0, p.nkb_h); }
+            if (is_mma) { tc_fence_after(); consume(0, p.nkb_h, true, !ATT || p.nkb_h == p.nkb); }
+            __syncwarp();
+        }
+
+        if (ATT) {
+            // =================== attention of utterance `cta` (CTAs 0 .. B-1, compute warps) ===================
+            if (compute && cta < B) {
+                const int b = cta, L = p.L, A = p.A, M = p.M, half = (p.KC - 1) / 2;
+                float* qb = scratch;                       // [A]
+                float* vv = qb + A;                        // [A]
+                float* e = vv + A;                         // [L16]
+                float* red = e + p.MT * 16;                // [64]
+                float* cred = red + 64;                    // [8][A] query partials
+                uint32_t* Ph = reinterpret_cast<uint32_t*>(cred + 8 * A);     // [L16 + 48] Toeplitz pair arrays (hi / lo bf16 split)
+                uint32_t* Pl = Ph + (p.MT * 16 + 48);
+                int len = p.lengths[b];
+                len = len < 0 ? 0 : (len > L ? L : len);
+                const float* cum_prev = p.cum + ((size_t)i * B + b) * L;
+                {   // q[a] = sum over the RB per-CTA partial projections: thread = (4 attention dims, one eighth of the row blocks)
+                    const int a4 = tid & 31, sl = tid >> 5;
+                    const int per = (p.RB + 7) / 8, r0 = sl * per, r1 = min(p.RB, r0 + per);
+                    float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a4 * 4 < A) {
+                        for (int r = r0; r < r1; r += 8) {
+                            float4 v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                v[j] = (r + j < r1) ? __ldcg(reinterpret_cast<const float4*>(p.qpart + ((size_t)(r + j) * B + b) * A) + a4)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { qs.x += v[j].x; qs.y += v[j].y; qs.z += v[j].z; qs.w += v[j].w; }
+                        }
+                        *reinterpret_cast<float4*>(cred + sl * A + a4 * 4) = qs;
+                    }
+                    // cumulative weights -> (hi, lo) bf16 pairs: Ph[x] = (c[x], c[x+1]) with c[j] = cum[j - half]
+                    for (int x = tid; x < p.MT * 16 + 48; x += CT) {
+                        float c0 = 0.f, c1 = 0.f;
+                        const int la = x - half, lb = x + 1 - half;
+                        if (la >= 0 && la < L) c0 = __ldcg(cum_prev + la);
+                        if (lb >= 0 && lb < L) c1 = __ldcg(cum_prev + lb);
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
+                        __nv_bfloat162 hp2; hp2.x = h0; hp2.y = h1;
+                        Ph[x] = *reinterpret_cast<uint32_t*>(&hp2);
+                        Pl[x] = pack2(c0 - __bfloat162float(h0), c1 - __bfloat162float(h1));
+                    }
+                    csync();
+                    for (int a2 = tid; a2 < A; a2 += CT) {
+                        float q = 0.f;
+#pragma unroll
+                        for (int sl2 = 0; sl2 < 8; ++sl2) q += cred[sl2 * A + a2];
+                        p.qsave[((size_t)i * B + b) * A + a2] = q;
+                        qb[a2] = q + p.bias[a2];
+                        vv[a2] = p.v[a2];
+                    }
+                }
+                csync();
+                PROF_MARK(4);
+                // energies on the tensor cores: S[l, a] = sum_k cumpad[l + k] * Wcomb[a, k]; warp owns position tiles {warp, warp+8}
+                {
+                    const int g = lane >> 2, tq = lane & 3;
+                    const int mtiles = (len + 15) / 16;
+                    for (int mt = warp; mt < mtiles; mt += NCW) {
+                        const int l0 = mt * 16;
+                        float sacc[16][4];
+#pragma unroll
+                        for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+                            for (int e4 = 0; e4 < 4; ++e4) sacc[nt][e4] = 0.f;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const int x = l0 + ks * 16 + g + 2 * tq;
+                            const uint32_t ah[4] = {Ph[x], Ph[x + 8], Ph[x + 8], Ph[x + 16]};
+                            const uint32_t al[4] = {Pl[x], Pl[x + 8], Pl[x + 8], Pl[x + 16]};
+#pragma unroll
+                            for (int np = 0; np < 8; ++np) {
+                                uint32_t bfr[4];
+                                ldmatrix_x4(bfr[0], bfr[1], bfr[2], bfr[3],
+                                            sWcB + (size_t)(np * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
+                                mma_bf16(sacc[2 * np], ah, bfr[0], bfr[1]);
+                                mma_bf16(sacc[2 * np], al, bfr[0], bfr[1]);
+                                mma_bf16(sacc[2 * np + 1], ah, bfr[2], bfr[3]);
+                                mma_bf16(sacc[2 * np + 1], al, bfr[2], bfr[3]);
+                            }
+                        }
+                        const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + mt) * 32 + lane) * 64);
+                        float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const uint4 raw = mf[c4];
+                            const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+                                const int nt = 2 * c4 + hf, a0 = nt * 8 + 2 * tq;
+                                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf]));
+                                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf + 1]));
+                                e0 = fmaf(vv[a0], tanh_fast(sacc[nt][0] + qb[a0] + m01.x), e0);
+                                e0 = fmaf(vv[a0 + 1], tanh_fast(sacc[nt][1] + qb[a0 + 1] + m01.y), e0);
+                                e1 = fmaf(vv[a0], tanh_fast(sacc[nt][2] + qb[a0] + m23.x), e1);
+                                e1 = fmaf(vv[a0 + 1], tanh_fast(sacc[nt][3] + qb[a0 + 1] + m23.y), e1);
+                            }
+                        }
+                        e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+                        e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+                        if (tq == 0) { e[l0 + g] = e0; e[l0 + g + 8] = e1; }
+                    }
+                }
+                csync();
+                PROF_MARK(5);
+                float mx = -INFINITY;
+                for (int l = tid; l < len; l += CT) mx = fmaxf(mx, e[l]);
+                mx = cblock_max(mx, red);
+                float sum = 0.f;
+                for (int l = tid; l < len; l += CT) { const float ex = expf(e[l] - mx); e[l] = ex; sum += ex; }
+                sum = cblock_sum(sum, red + 32);
+                float* cum_next = p.cum + ((size_t)(i + 1) * B + b) * L;
+                const float inv_sum = 1.f / sum;
+                for (int l = tid; l < p.MT * 16; l += CT) {      // the padded tail must be zero: the context MMA reads whole 16-position tiles
+                    const float w = l < len ? e[l] * inv_sum : 0.f;
+                    e[l] = w;
+                    if (l < L) {
+                        p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
+                        cum_next[l] = __ldcg(cum_prev + l) + w;
+                    }
+                }
+                csync();
+                // context on the tensor cores: ctx[m] = sum_l memory[l, m] * w[l].  A = memory^T fragments (fragment-major bf16, one
+                // 16-byte load per lane per MMA), B = (hi(w), lo(w)) in columns 0 / 1 -> column 0 + column 1 of D is the fp32-weighted sum.
+                {
+                    const int g = lane >> 2, tq = lane & 3;
+                    const int ktiles = (len + 15) / 16;
+                    for (int mt = warp; mt < p.M16; mt += NCW) {
+                        const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt) * p.MT) * 32 + lane;
+                        float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int kt0 = 0; kt0 < ktiles; kt0 += 6) {
+                            uint4 av[6];
+#pragma unroll
+                            for (int j = 0; j < 6; ++j)
+                                if (kt0 + j < ktiles) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) {
+                                if (kt0 + j < ktiles) {
+                                    uint32_t bb0 = 0u, bb1 = 0u;
+                                    if (g < 2) {
+                                        const float* wl = e + (kt0 + j) * 16 + 2 * tq;
+                                        float w0 = wl[0], w1 = wl[1], w2 = wl[8], w3 = wl[9];
+                                        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+                                        const __nv_bfloat16 h2 = __float2bfloat16_rn(w2), h3 = __float2bfloat16_rn(w3);
+                                        if (g == 1) { w0 -= __bfloat162float(h0); w1 -= __bfloat162float(h1); w2 -= __bfloat162float(h2); w3 -= __bfloat162float(h3); }
+                                        else { w0 = __bfloat162float(h0); w1 = __bfloat162float(h1); w2 = __bfloat162float(h2); w3 = __bfloat162float(h3); }
+                                        bb0 = pack2(w0, w1); bb1 = pack2(w2, w3);
+                                    }
+                                    const uint32_t af[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+                                    mma_bf16(dacc, af, bb0, bb1);
+                                }
+                            }
+                        }
+                        if (tq == 0) {
+                            const int m0 = mt * 16 + g;
+                            const float c0 = dacc[0] + dacc[1], c1 = dacc[2] + dacc[3];
+                            if (m0 < M) {
+                                p.actf[((size_t)(i + 1) * B + b) * p.ldf + m0] = c0;
+                                p.actb[((size_t)(i + 1) * B + b) * Kp + D + m0] = __float2bfloat16_rn(c0);
+                            }
+                            if (m0 + 8 < M) {
+                                p.actf[((size_t)(i + 1) * B + b) * p.ldf + m0 + 8] = c1;
+                                p.actb[((size_t)(i + 1) * B + b) * Kp + D + m0 + 8] = __float2bfloat16_rn(c1);
+                            }
+                        }
+                    }
+                }
+                proxy_fence_global();
+            }
+            PROF_MARK(6);
+            if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
+            PROF_MARK(7);
+        }
+    }
+    if (p.prof && tid == 0)
+        for (int k = 0; k < 8; ++k) p.prof[(size_t)cta * 8 + k] = prof_acc[k];
+#undef PROF_MARK
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NCW + 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// shared memory of one loop CTA; 0 when the shape does not fit
+size_t tc_loop_smem_bytes(int nkb, int ns, int A, bool att, int L) {
+    size_t b = 1024 + (size_t)nkb * WTILE + (size_t)ns * ATILE + (size_t)BT * (ROWS + 1) * 4;
+    if (att) {
+        const int L16 = (L + 15) / 16 * 16;
+        b += (size_t)UNITS * (BT + 4) * 4 + (size_t)A * (UNITS + 1) * 4 + (size_t)A * 40 * 2;
+        b += ((size_t)2 * A + L16 + 64 + 8 * A + 2 * (L16 + 48)) * 4;
+    }
+    return b;
+}
+constexpr size_t SMEM_LIMIT = 227 * 1024 - 1088;    // leave room for the static barriers (1 KB of static shared memory)
+
+int pick_stages(int nkb, int A, bool att, int L, int want) {
+    int ns = want > MAXNS ? MAXNS : want;
+    while (ns >= 2 && tc_loop_smem_bytes(nkb, ns, A, att, L) > SMEM_LIMIT) --ns;
+    return ns >= 2 ? ns : 0;
+}
+
+}  // namespace
+
+// column geometry of the bf16 operand rows of the tcgen05 loops: [h (D) | ctx (M) | zero pad], 64-column k-blocks
+TcPersistGeom tc_persist_geom(const b200tts_decoder_shape& s) {
+    TcPersistGeom g{};
+    g.Kp_att = (s.D + s.M + 7) / 8 * 8;
+    g.Kp_gen = (s.D + 7) / 8 * 8;
+    g.nkb_att = (s.D + s.M + KB - 1) / KB;
+    g.nkb_gen = (s.D + KB - 1) / KB;
+    g.nkb_h = s.D / KB;
+    g.ns_att = pick_stages(g.nkb_att, s.A, true, s.L, 8);
+    g.ns_gen = pick_stages(g.nkb_gen, s.A, false, 0, g.nkb_gen);
+    return g;
+}
+
+bool tc_persist_supported(const b200tts_decoder_shape& s) {
+    if (s.D % KB != 0 || s.D % UNITS != 0) return false;
+    const int RB = s.D / UNITS, NBH = (s.B + BT - 1) / BT;
+    if (RB * NBH > 148 || s.B > RB * NBH) return false;
+    if (s.K > 32 || s.A != 128) return false;
+    const TcPersistGeom g = tc_persist_geom(s);
+    return g.ns_att >= 2 && g.ns_gen >= 2;
+}
+
+static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tm, size_t smem, cudaStream_t st) {
+    void* fn = att ? (void*)lstm_loop_tc_kernel<true> : (void*)lstm_loop_tc_kernel<false>;
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
+    int dev = 0, sms = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = a.RB * a.NBH;
+    B200_REQUIRE(per_sm * sms >= grid, "tcgen05 persistent loop: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, sms);
+    TcLoopArgs args = a;
+    CUtensorMap map = tm;
+    void* params[] = {&map, &args};
+    B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+
+// Attention-LSTM + attention loop (all T steps).  Expects: ga = input projection, ai row 0 = 0, ca row 0 = 0, cum row 0 = 0,
+// and the attention operands (wcb, memTf, memFf) already prepared in the persistent workspace.
+int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                        const DecoderLayout& fl, float* ws, unsigned char* pws, float* align, cudaStream_t st) {
+    const PersistLayout l = persist_layout(s);
+    const TcPersistGeom g = tc_persist_geom(s);
+    const int B = s.B, T = s.T, D = s.D, M = s.M, MD = M + D;
+    __nv_bfloat16* aib = reinterpret_cast<__nv_bfloat16*>(pws + l.aib);
+    unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
+    // operand of step 0 and the zero padding columns [MD, Kp)
+    B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)(g.Kp_att != MD ? (size_t)(T + 1) : 1) * B * g.Kp_att * 2, st));
+    B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
+    CUtensorMap tm;
+    B200_TRY(tc_make_map_bf16(&tm, aib, (T + 1) * B, g.Kp_att, g.Kp_att, 1, BT));
+    TcLoopArgs a{};
+    a.B = B; a.T = T; a.D = D; a.K = MD; a.Kp = g.Kp_att; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
+    a.nkb = g.nkb_att; a.nkb_h = g.nkb_h; a.NS = g.ns_att;
+    a.W = ws + fl.wcat_att; a.ldw = MD; a.wcol_h = M; a.wcol_c = 0;
+    a.actb = aib; a.actf = ws + fl.ai; a.ldf = MD; a.hcol = M;
+    a.gates = ws + fl.ga; a.cstate = ws + fl.ca;
+    a.mask_h = in.mask_att_h; a.mask_c = in.mask_att_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
+    a.L = s.L; a.M = M; a.A = s.A; a.KC = s.K;
+    a.Wq = w.attn_query; a.qpart = ws + fl.qpart; a.qsave = ws + fl.q;
+    a.WcB = reinterpret_cast<const __nv_bfloat16*>(pws + l.wcb);
+    a.memTf = reinterpret_cast<const __nv_bfloat16*>(pws + l.memTf); a.MT = l.MT;
+    a.bias = w.attn_bias; a.v = w.attn_energy;
+    a.memFf = reinterpret_cast<const uint4*>(pws + l.memFf); a.M16 = l.M16;
+    a.lengths = in.text_lengths; a.cum = ws + fl.cum;
+    a.align = align; a.align_bstride = (long long)T * s.L;
+    a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
+    a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256);
+    return launch_tc_loop(true, a, tm, tc_loop_smem_bytes(g.nkb_att, g.ns_att, s.A, true, s.L), st);
+}
+
+// Generator-LSTM loop.  Expects: gg = input projection, hg row 0 = 0, cg row 0 = 0.
+int tc_persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                        const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st) {
+    const PersistLayout l = persist_layout(s);
+    const TcPersistGeom g = tc_persist_geom(s);
+    const int B = s.B, T = s.T, D = s.D;
+    __nv_bfloat16* hgb = reinterpret_cast<__nv_bfloat16*>(pws + l.hgb);
+    unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
+    B200_CUDA(cudaMemsetAsync(hgb, 0, (size_t)(g.Kp_gen != D ? (size_t)(T + 1) : 1) * B * g.Kp_gen * 2, st));
+    B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
+    CUtensorMap tm;
+    B200_TRY(tc_make_map_bf16(&tm, hgb, (T + 1) * B, g.Kp_gen, g.Kp_gen, 1, BT));
+    TcLoopArgs a{};
+    a.B = B; a.T = T; a.D = D; a.K = D; a.Kp = g.Kp_gen; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
+    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.NS = g.ns_gen;
+    a.W = w.gen_w_hh; a.ldw = D; a.wcol_h = 0; a.wcol_c = 0;
+    a.actb = hgb; a.actf = ws + fl.hg; a.ldf = D; a.hcol = 0;
+    a.gates = ws + fl.gg; a.cstate = ws + fl.cg;
+    a.mask_h = in.mask_gen_h; a.mask_c = in.mask_gen_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
+    a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
+    a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256) + 148 * 8;
+    return launch_tc_loop(false, a, tm, tc_loop_smem_bytes(g.nkb_gen, g.ns_gen, s.A, false, 0), st);
+}
+
+}  // namespace b200tts

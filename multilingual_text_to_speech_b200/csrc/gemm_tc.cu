@@ -294,6 +294,11 @@ int g_tc_enabled = 1;
 
 }  // namespace
 
+// 3-D bf16 tensor map {K, rows, batch} with a {64, box_rows, 1} box and SWIZZLE_128B (shared with the persistent loop kernels)
+int tc_make_map_bf16(void* map, const void* base, int rows, int K, int Kp, int batch, int box_rows) {
+    return make_map(static_cast<CUtensorMap*>(map), static_cast<const __nv_bfloat16*>(base), rows, K, Kp, batch, box_rows);
+}
+
 void set_tc_scratch(void* ptr, size_t bytes) { g_scratch.ptr = static_cast<unsigned char*>(ptr); g_scratch.bytes = bytes; }
 void set_tc_enabled(int on) { g_tc_enabled = on; }
 int tc_enabled() { return g_tc_enabled; }
