@@ -624,8 +624,9 @@ PersistLayout persist_layout(const b200tts_decoder_shape& s) {
     l.Kp_att = (s.M + s.D + 15) / 16 * 16;
     l.Kp_gen = (s.D + 15) / 16 * 16;
     l.ldm = (s.M + 7) / 8 * 8;
-    l.aib = take((T + 1) * B * l.Kp_att * 2);
-    l.hgb = take((T + 1) * B * l.Kp_gen * 2);
+    // sized for the 64-column k-block padding of the tcgen05 loops (decoder_persist_tc.cu) as well
+    l.aib = take((T + 1) * B * (size_t)((s.M + s.D + 63) / 64 * 64) * 2);
+    l.hgb = take((T + 1) * B * (size_t)((s.D + 63) / 64 * 64) * 2);
     l.memTb = take(B * (size_t)s.L * s.A * 2);
     l.memb = take(B * (size_t)s.L * l.ldm * 2);
     l.wcombT = take((size_t)s.K * s.A * 4);
@@ -635,7 +636,7 @@ PersistLayout persist_layout(const b200tts_decoder_shape& s) {
     l.M16 = (s.M + 15) / 16;
     l.memFf = take((size_t)s.B * l.M16 * l.MT * 32 * 16);
     l.memFb = take((size_t)s.B * l.M16 * l.MT * 32 * 16);
-    l.barrier = take(256 + 148 * 8 * 8 * 2);   // barrier + abort flag, then 2 x [148][8] profile counters
+    l.barrier = take(256 + 148 * 8 * 8 * 4);   // barrier + abort flag, then 4 x [148][8] profile counters (att, gen, att roles, gen roles)
     l.total = off;
     return l;
 }

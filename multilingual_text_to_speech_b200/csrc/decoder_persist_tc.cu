@@ -21,7 +21,8 @@
 
 namespace b200tts {
 
-int tc_make_map_bf16(void* map, const void* base, int rows, int K, int Kp, int batch, int box_rows);   // gemm_tc.cu
+// gemm_tc.cu: 3-D bf16 tensor map, dims {d0, d1, d2} (d0 contiguous), byte strides of d1 / d2, box {b0, b1, b2}, SWIZZLE_128B
+int tc_make_map3_bf16(void* map, const void* base, int d0, int d1, int d2, size_t stride1, size_t stride2, int b0, int b1, int b2);
 
 namespace {
 
@@ -34,12 +35,12 @@ constexpr int BT = 32;                  // utterances per CTA (MMA N)
 constexpr int KB = 64;                  // K columns per tile / TMA box (128-byte rows)
 constexpr int WTILE = ROWS * KB * 2;    // 8 KB
 constexpr int ATILE = BT * KB * 2;      // 4 KB
-constexpr int MAXNS = 16;               // ring stages (run-time value <= MAXNS)
 constexpr int TMEM_COLS = 32;
 
 struct TcLoopArgs {
     int B, T, D, K, Kp, RB, NBH;
-    int nkb, nkb_h, NS;                       // k-blocks in total / in the h part; ring stages
+    int nkb, nkb_h;                           // k-blocks in total / in the h part
+    int ch_h, n_h, ch_c, slot_kb;             // TMA chunking: n_h instructions of ch_h k-blocks (h part), one of ch_c (ctx part); slot capacity
     const float* W; int ldw; int wcol_h, wcol_c;   // fp32 weights [4D, ldw]: operand column k < D -> wcol_h + k, else wcol_c + k - D
     __nv_bfloat16* actb;                      // [T+1, B, Kp] bf16 operand rows: [h | ctx | 0]
     float* actf; int ldf; int hcol;           // fp32 mirror ([T+1, B, ldf]); h at column hcol, ctx at column 0
@@ -57,7 +58,8 @@ struct TcLoopArgs {
     const int* lengths;
     float* cum; float* align; long long align_bstride;
     unsigned* barrier; int* abort_flag;
-    long long* prof;
+    long long* prof;                          // [grid][8] phase cycles seen by compute thread 0
+    long long* prof2;                         // [grid][8] MMA issuer (0-3) / TMA producer (4-7) waits
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -184,6 +186,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
     if (threadIdx.x == 0) {
         target += nblocks;
         __threadfence();
+        proxy_fence_global();          // the bf16 operand rows written above are read by other CTAs through TMA (async proxy)
         atomicAdd(counter, 1u);
         int ok = 1;
         const long long t0 = clock64();
@@ -198,10 +201,11 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
 }
 
 template <bool ATT>
-__global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const TcLoopArgs p) {
+__global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmC,
+                                                             const TcLoopArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw0) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar[MAXNS], empty_bar[MAXNS], accum_bar;
+    __shared__ uint64_t full_bar, empty_bar, accum_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_ok;
 
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     const int cta = blockIdx.x;
     const int rb = cta % p.RB, bh = cta / p.RB;
     const int u0 = rb * UNITS, b0 = bh * BT;
-    const int Kp = p.Kp, D = p.D, B = p.B, NS = p.NS;
+    const int Kp = p.Kp, D = p.D, B = p.B;
     const unsigned nblocks = gridDim.x;
     const bool compute = warp < NCW;
     const bool is_producer = (warp == NCW) && lane == 0;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     // ---- shared memory carve-up (1024-byte aligned base: SWIZZLE_128B atoms) ----
     size_t off = 0;
     unsigned char* sW = smem_raw + off; off += (size_t)p.nkb * WTILE;                 // [nkb][64 rows][128 B] swizzled
-    unsigned char* ring = smem_raw + off; off += (size_t)NS * ATILE;                  // [NS][32 rows][128 B] swizzled (TMA)
+    unsigned char* ring = smem_raw + off; off += (size_t)p.slot_kb * ATILE;           // one slot of [slot_kb][32 rows][128 B] swizzled (TMA)
     float* s_sum = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (ROWS + 1) * 4;
     float* s_hs = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)UNITS * (BT + 4) * 4 : 0;
     float* s_wq = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)p.A * (UNITS + 1) * 4 : 0;
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         for (int idx = tid; idx < p.A * 40; idx += PT) sWcB[idx] = p.WcB[idx];
     }
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&full_bar, 1); mbar_init(&empty_bar, 1);
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -258,32 +262,47 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 
-    uint32_t prod_it = 0, cons_it = 0;            // running box counters of the producer / MMA thread
-    // TMA producer: operand row block of `step`, k-blocks [kb0, kb1)
-    auto produce = [&](int step, int kb0, int kb1) {
-        for (int kb = kb0; kb < kb1; ++kb) {
-            const int s = prod_it % NS;
-            mbar_wait(&empty_bar[s], ((prod_it / NS) & 1) ^ 1);
-            mbar_expect_tx(&full_bar[s], ATILE);
-            tma_load_3d(ring + (size_t)s * ATILE, &tmAct, &full_bar[s], kb * KB, step * B + b0, 0);
+    // A TMA instruction costs ~500 cycles of issue time whatever its size (measured), so the operand is fetched with FEW LARGE
+    // boxes: the tensor maps are 3-D {64 columns, rows, k-block} (k-block stride 128 B), one instruction brings ch k-blocks
+    // of [32 rows x 128 B] = ch swizzled 4 KB tiles into the single ring slot.
+    uint32_t prod_it = 0, cons_it = 0;            // running chunk counters of the producer / MMA thread
+    long long rp[4] = {0, 0, 0, 0};               // role-thread cycle counters (see prof2)
+    // TMA producer: operand row block of `step`; part 0 = ctx k-blocks (one instruction), part 1 = h k-blocks (n_h instructions)
+    auto produce = [&](int step, int part) {
+        const long long t0 = clock64();
+        proxy_fence_global();          // generic-proxy writes of other CTAs (ordered by the grid barrier) -> async-proxy reads
+        const long long t1 = clock64();
+        const int n = part ? p.n_h : 1, ch = part ? p.ch_h : p.ch_c;
+        for (int j = 0; j < n; ++j) {
+            mbar_wait(&empty_bar, (prod_it & 1) ^ 1);
+            mbar_expect_tx(&full_bar, (uint32_t)ch * ATILE);
+            tma_load_3d(ring, part ? &tmH : &tmC, &full_bar, 0, step * B + b0, part ? j * ch : p.nkb_h);
             ++prod_it;
         }
+        rp[2 * part] += t1 - t0; rp[2 * part + 1] += clock64() - t1;
     };
-    // MMA issuer: acc (+)= W[:, kb] . act[:, kb]^T for k-blocks [kb0, kb1)
-    auto consume = [&](int kb0, int kb1, bool zero_first, bool signal_accum) {
-        for (int kb = kb0; kb < kb1; ++kb) {
-            const int s = cons_it % NS;
-            mbar_wait(&full_bar[s], (cons_it / NS) & 1);
+    // MMA issuer: acc (+)= W[:, kb] . act[:, kb]^T over the k-blocks of the part
+    auto consume = [&](int part, bool signal_accum) {
+        const long long t0 = clock64();
+        long long t1 = t0;
+        const int n = part ? p.n_h : 1, ch = part ? p.ch_h : p.ch_c;
+        for (int j = 0; j < n; ++j) {
+            mbar_wait(&full_bar, cons_it & 1);
+            if (j == 0) t1 = clock64();
             tc_fence_after();
-            const uint64_t adesc = make_sw128_desc(smem_u32(sW + (size_t)kb * WTILE));
-            const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)s * ATILE));
+            const int kb0 = part ? j * ch : p.nkb_h;
+            for (int c = 0; c < ch; ++c) {
+                const uint64_t adesc = make_sw128_desc(smem_u32(sW + (size_t)(kb0 + c) * WTILE));
+                const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)c * ATILE));
 #pragma unroll
-            for (int k = 0; k < KB / 16; ++k)
-                umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (zero_first && kb == kb0 && k == 0) ? 0u : 1u);
-            umma_commit(&empty_bar[s]);
+                for (int k = 0; k < KB / 16; ++k)
+                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (part == 1 && j == 0 && c == 0 && k == 0) ? 0u : 1u);
+            }
+            umma_commit(&empty_bar);
             ++cons_it;
         }
         if (signal_accum) umma_commit(&accum_bar);
+        rp[2 * part] += t1 - t0; rp[2 * part + 1] += clock64() - t1;
     };
 
     const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
@@ -296,38 +315,47 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     } while (0)
 
     // prologue: the h part of step 0 (operand row 0 is all zeros)
-    if (is_producer) produce(0, 0, p.nkb_h);
-    if (is_mma) consume(0, p.nkb_h, true, !ATT || p.nkb_h == p.nkb);
+    if (is_producer) produce(0, 1);
+    if (is_mma) consume(1, !ATT || p.nkb_h == p.nkb);
     __syncwarp();
+
+    // Epilogue operands of this thread's two (b, u) pairs.  The input-projection gates and the keep masks of step i+1 are fetched
+    // (from DRAM) right after the cell barrier of step i, i.e. a whole attention phase ahead; c and the regularised h are carried
+    // in registers from step to step.
+    float pre[2][6];
+    uint8_t pm[2][2];
+    auto prefetch = [&](int step, bool state) {
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            const int idx = tid + e2 * CT;
+            const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
+            pm[e2][0] = 1; pm[e2][1] = 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pre[e2][j] = 0.f;
+            if (state) { pre[e2][4] = 0.f; pre[e2][5] = 0.f; }
+            if (b < B && u < D) {
+                const size_t g0 = ((size_t)step * B + b) * 4 * D + u, mi = ((size_t)step * B + b) * D + u;
+                pre[e2][0] = p.gates[g0]; pre[e2][1] = p.gates[g0 + D]; pre[e2][2] = p.gates[g0 + 2 * D]; pre[e2][3] = p.gates[g0 + 3 * D];
+                if (state) {
+                    pre[e2][4] = p.cstate[mi];
+                    pre[e2][5] = p.actf[((size_t)step * B + b) * p.ldf + p.hcol + u];
+                }
+                if (p.training && p.mask_h) pm[e2][0] = p.mask_h[mi];
+                if (p.training && p.mask_c) pm[e2][1] = p.mask_c[mi];
+            }
+        }
+    };
+    if (compute) prefetch(0, true);
 
     bool alive = true;
     for (int i = 0; i < p.T && alive; ++i) {
         // =================== ctx part of the gate product (the context of step i-1 is visible now) ===================
         if (ATT && p.nkb_h < p.nkb) {
-            if (is_producer) { proxy_fence_global(); produce(i, p.nkb_h, p.nkb); }
-            if (is_mma) consume(p.nkb_h, p.nkb, false, true);
+            if (is_producer) produce(i, 0);
+            if (is_mma) consume(0, true);
             __syncwarp();
         }
         if (compute) {
-            // prefetch the epilogue operands of this thread's two (b, u) pairs: their latency hides behind the product
-            float pre[2][6];
-            uint8_t pm[2][2];
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-                const int idx = tid + e2 * CT;
-                const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
-                pm[e2][0] = 1; pm[e2][1] = 1;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) pre[e2][j] = 0.f;
-                if (b < B && u < D) {
-                    const size_t g0 = ((size_t)i * B + b) * 4 * D + u, mi = ((size_t)i * B + b) * D + u;
-                    pre[e2][0] = p.gates[g0]; pre[e2][1] = p.gates[g0 + D]; pre[e2][2] = p.gates[g0 + 2 * D]; pre[e2][3] = p.gates[g0 + 3 * D];
-                    pre[e2][4] = p.cstate[mi];
-                    if (p.kind == B200TTS_CELL_ZONEOUT) pre[e2][5] = p.actf[((size_t)i * B + b) * p.ldf + p.hcol + u];
-                    if (p.training && p.mask_h) pm[e2][0] = p.mask_h[mi];
-                    if (p.training && p.mask_c) pm[e2][1] = p.mask_c[mi];
-                }
-            }
             // accumulator [64 gate rows x 32 utterances]: TMEM lane 32 * gate + unit, column = utterance
             mbar_wait(&accum_bar, i & 1);
             tc_fence_after();
@@ -381,6 +409,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     p.actf[((size_t)(i + 1) * B + b) * p.ldf + p.hcol + u] = hn;
                     p.actb[((size_t)(i + 1) * B + b) * Kp + u] = __float2bfloat16_rn(hn);
                     hs = hn;
+                    pre[e2][4] = cn; pre[e2][5] = hn;           // state of the next step
                 }
                 if (ATT) s_hs[uu * (BT + 4) + bl] = hs;
             }
@@ -408,7 +437,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         if (b0 + bg * 16 + j < B) p.qpart[((size_t)rb * B + b0 + bg * 16 + j) * p.A + a] = qa[j];
                 }
             }
-            proxy_fence_global();          // the bf16 h values are read by other CTAs' TMA (async proxy) after the barrier
         }
         PROF_MARK(2);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
@@ -416,9 +444,10 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
 
         // =================== h part of step i+1: TMA + tcgen05 run while the attention of step i is computed ===================
         if (i + 1 < p.T) {
-            if (is_producer) { proxy_fence_global(); produce(i + 1, 0, p.nkb_h); }
-            if (is_mma) { tc_fence_after(); consume(0, p.nkb_h, true, !ATT || p.nkb_h == p.nkb); }
+            if (is_producer) produce(i + 1, 1);
+            if (is_mma) { tc_fence_after(); consume(1, !ATT || p.nkb_h == p.nkb); }
             __syncwarp();
+            if (compute) prefetch(i + 1, false);
         }
 
         if (ATT) {
@@ -550,13 +579,13 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     for (int mt = warp; mt < p.M16; mt += NCW) {
                         const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt) * p.MT) * 32 + lane;
                         float dacc[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int kt0 = 0; kt0 < ktiles; kt0 += 6) {
-                            uint4 av[6];
+                        for (int kt0 = 0; kt0 < ktiles; kt0 += 12) {
+                            uint4 av[12];
 #pragma unroll
-                            for (int j = 0; j < 6; ++j)
+                            for (int j = 0; j < 12; ++j)
                                 if (kt0 + j < ktiles) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) {
+                            for (int j = 0; j < 12; ++j) {
                                 if (kt0 + j < ktiles) {
                                     uint32_t bb0 = 0u, bb1 = 0u;
                                     if (g < 2) {
@@ -587,7 +616,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         }
                     }
                 }
-                proxy_fence_global();
             }
             PROF_MARK(6);
             if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
@@ -597,6 +625,8 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     if (p.prof && tid == 0)
         for (int k = 0; k < 8; ++k) p.prof[(size_t)cta * 8 + k] = prof_acc[k];
 #undef PROF_MARK
+    if (p.prof2 && (is_mma || is_producer))
+        for (int k = 0; k < 4; ++k) p.prof2[(size_t)cta * 8 + (is_producer ? 4 : 0) + k] = rp[k];
     tc_fence_before();
     __syncthreads();
     if (warp == NCW + 1) {
@@ -604,9 +634,9 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     }
 }
 
-// shared memory of one loop CTA; 0 when the shape does not fit
-size_t tc_loop_smem_bytes(int nkb, int ns, int A, bool att, int L) {
-    size_t b = 1024 + (size_t)nkb * WTILE + (size_t)ns * ATILE + (size_t)BT * (ROWS + 1) * 4;
+// shared memory of one loop CTA with a ring slot of slot_kb k-blocks
+size_t tc_loop_smem_bytes(int nkb, int slot_kb, int A, bool att, int L) {
+    size_t b = 1024 + (size_t)nkb * WTILE + (size_t)slot_kb * ATILE + (size_t)BT * (ROWS + 1) * 4;
     if (att) {
         const int L16 = (L + 15) / 16 * 16;
         b += (size_t)UNITS * (BT + 4) * 4 + (size_t)A * (UNITS + 1) * 4 + (size_t)A * 40 * 2;
@@ -616,10 +646,16 @@ size_t tc_loop_smem_bytes(int nkb, int ns, int A, bool att, int L) {
 }
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 1088;    // leave room for the static barriers (1 KB of static shared memory)
 
-int pick_stages(int nkb, int A, bool att, int L, int want) {
-    int ns = want > MAXNS ? MAXNS : want;
-    while (ns >= 2 && tc_loop_smem_bytes(nkb, ns, A, att, L) > SMEM_LIMIT) --ns;
-    return ns >= 2 ? ns : 0;
+// largest ring slot (in k-blocks, <= want) that fits
+int pick_slot(int nkb, int A, bool att, int L, int want) {
+    int kb = want;
+    while (kb >= 1 && tc_loop_smem_bytes(nkb, kb, A, att, L) > SMEM_LIMIT) --kb;
+    return kb;
+}
+int largest_divisor_le(int n, int cap) {
+    for (int d = cap < n ? cap : n; d >= 1; --d)
+        if (n % d == 0) return d;
+    return 1;
 }
 
 }  // namespace
@@ -627,13 +663,16 @@ int pick_stages(int nkb, int A, bool att, int L, int want) {
 // column geometry of the bf16 operand rows of the tcgen05 loops: [h (D) | ctx (M) | zero pad], 64-column k-blocks
 TcPersistGeom tc_persist_geom(const b200tts_decoder_shape& s) {
     TcPersistGeom g{};
-    g.Kp_att = (s.D + s.M + 7) / 8 * 8;
-    g.Kp_gen = (s.D + 7) / 8 * 8;
     g.nkb_att = (s.D + s.M + KB - 1) / KB;
     g.nkb_gen = (s.D + KB - 1) / KB;
     g.nkb_h = s.D / KB;
-    g.ns_att = pick_stages(g.nkb_att, s.A, true, s.L, 8);
-    g.ns_gen = pick_stages(g.nkb_gen, s.A, false, 0, g.nkb_gen);
+    g.Kp_att = g.nkb_att * KB;
+    g.Kp_gen = g.nkb_gen * KB;
+    g.ch_c_att = g.nkb_att - g.nkb_h;
+    g.slot_att = pick_slot(g.nkb_att, s.A, true, s.L, g.nkb_h);
+    g.ch_h_att = g.slot_att >= 1 ? largest_divisor_le(g.nkb_h, g.slot_att) : 0;
+    g.slot_gen = pick_slot(g.nkb_gen, s.A, false, 0, g.nkb_gen);
+    g.ch_h_gen = g.slot_gen >= 1 ? largest_divisor_le(g.nkb_gen, g.slot_gen) : 0;
     return g;
 }
 
@@ -643,10 +682,10 @@ bool tc_persist_supported(const b200tts_decoder_shape& s) {
     if (RB * NBH > 148 || s.B > RB * NBH) return false;
     if (s.K > 32 || s.A != 128) return false;
     const TcPersistGeom g = tc_persist_geom(s);
-    return g.ns_att >= 2 && g.ns_gen >= 2;
+    return g.ch_c_att >= 1 && g.ch_c_att <= 256 && g.slot_att >= g.ch_c_att && g.ch_h_att >= 1 && g.ch_h_gen >= 1;
 }
 
-static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tm, size_t smem, cudaStream_t st) {
+static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tmH, const CUtensorMap& tmC, size_t smem, cudaStream_t st) {
     void* fn = att ? (void*)lstm_loop_tc_kernel<true> : (void*)lstm_loop_tc_kernel<false>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -657,8 +696,8 @@ static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tm, 
     const int grid = a.RB * a.NBH;
     B200_REQUIRE(per_sm * sms >= grid, "tcgen05 persistent loop: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, sms);
     TcLoopArgs args = a;
-    CUtensorMap map = tm;
-    void* params[] = {&map, &args};
+    CUtensorMap mapH = tmH, mapC = tmC;
+    void* params[] = {&mapH, &mapC, &args};
     B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
@@ -674,13 +713,15 @@ int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     __nv_bfloat16* aib = reinterpret_cast<__nv_bfloat16*>(pws + l.aib);
     unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
     // operand of step 0 and the zero padding columns [MD, Kp)
-    B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)(g.Kp_att != MD ? (size_t)(T + 1) : 1) * B * g.Kp_att * 2, st));
+    B200_CUDA(cudaMemsetAsync(aib, 0, (size_t)(g.Kp_att != MD ? (size_t)(T + 1) : 1) * B * g.Kp_att * 2, st));   // step 0 + padding
     B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
-    CUtensorMap tm;
-    B200_TRY(tc_make_map_bf16(&tm, aib, (T + 1) * B, g.Kp_att, g.Kp_att, 1, BT));
+    CUtensorMap tmH, tmC;       // {64 columns, rows, k-block}: k-block stride 128 B, row stride Kp * 2 B
+    B200_TRY(tc_make_map3_bf16(&tmH, aib, KB, (T + 1) * B, g.nkb_att, (size_t)g.Kp_att * 2, 128, KB, BT, g.ch_h_att));
+    B200_TRY(tc_make_map3_bf16(&tmC, aib, KB, (T + 1) * B, g.nkb_att, (size_t)g.Kp_att * 2, 128, KB, BT, g.ch_c_att));
     TcLoopArgs a{};
     a.B = B; a.T = T; a.D = D; a.K = MD; a.Kp = g.Kp_att; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
-    a.nkb = g.nkb_att; a.nkb_h = g.nkb_h; a.NS = g.ns_att;
+    a.nkb = g.nkb_att; a.nkb_h = g.nkb_h; a.ch_h = g.ch_h_att; a.n_h = g.nkb_h / g.ch_h_att; a.ch_c = g.ch_c_att;
+    a.slot_kb = g.ch_h_att > g.ch_c_att ? g.ch_h_att : g.ch_c_att;
     a.W = ws + fl.wcat_att; a.ldw = MD; a.wcol_h = M; a.wcol_c = 0;
     a.actb = aib; a.actf = ws + fl.ai; a.ldf = MD; a.hcol = M;
     a.gates = ws + fl.ga; a.cstate = ws + fl.ca;
@@ -695,7 +736,8 @@ int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     a.align = align; a.align_bstride = (long long)T * s.L;
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
     a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256);
-    return launch_tc_loop(true, a, tm, tc_loop_smem_bytes(g.nkb_att, g.ns_att, s.A, true, s.L), st);
+    a.prof2 = a.prof + 2 * 148 * 8;
+    return launch_tc_loop(true, a, tmH, tmC, tc_loop_smem_bytes(g.nkb_att, a.slot_kb, s.A, true, s.L), st);
 }
 
 // Generator-LSTM loop.  Expects: gg = input projection, hg row 0 = 0, cg row 0 = 0.
@@ -708,18 +750,19 @@ int tc_persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     unsigned* barrier = reinterpret_cast<unsigned*>(pws + l.barrier);
     B200_CUDA(cudaMemsetAsync(hgb, 0, (size_t)(g.Kp_gen != D ? (size_t)(T + 1) : 1) * B * g.Kp_gen * 2, st));
     B200_CUDA(cudaMemsetAsync(barrier, 0, 256, st));
-    CUtensorMap tm;
-    B200_TRY(tc_make_map_bf16(&tm, hgb, (T + 1) * B, g.Kp_gen, g.Kp_gen, 1, BT));
+    CUtensorMap tmH;
+    B200_TRY(tc_make_map3_bf16(&tmH, hgb, KB, (T + 1) * B, g.nkb_gen, (size_t)g.Kp_gen * 2, 128, KB, BT, g.ch_h_gen));
     TcLoopArgs a{};
     a.B = B; a.T = T; a.D = D; a.K = D; a.Kp = g.Kp_gen; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
-    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.NS = g.ns_gen;
+    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.ch_h = g.ch_h_gen; a.n_h = g.nkb_gen / g.ch_h_gen; a.ch_c = 0; a.slot_kb = g.ch_h_gen;
     a.W = w.gen_w_hh; a.ldw = D; a.wcol_h = 0; a.wcol_c = 0;
     a.actb = hgb; a.actf = ws + fl.hg; a.ldf = D; a.hcol = 0;
     a.gates = ws + fl.gg; a.cstate = ws + fl.cg;
     a.mask_h = in.mask_gen_h; a.mask_c = in.mask_gen_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
     a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256) + 148 * 8;
-    return launch_tc_loop(false, a, tm, tc_loop_smem_bytes(g.nkb_gen, g.ns_gen, s.A, false, 0), st);
+    a.prof2 = a.prof + 2 * 148 * 8;
+    return launch_tc_loop(false, a, tmH, tmH, tc_loop_smem_bytes(g.nkb_gen, a.slot_kb, s.A, false, 0), st);
 }
 
 }  // namespace b200tts

@@ -299,6 +299,21 @@ int tc_make_map_bf16(void* map, const void* base, int rows, int K, int Kp, int b
     return make_map(static_cast<CUtensorMap*>(map), static_cast<const __nv_bfloat16*>(base), rows, K, Kp, batch, box_rows);
 }
 
+int tc_make_map3_bf16(void* map, const void* base, int d0, int d1, int d2, size_t stride1, size_t stride2, int b0, int b1, int b2) {
+    EncodeTiledFn fn = encode_fn();
+    B200_REQUIRE(fn != nullptr, "tc_make_map3: cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride1, (cuuint64_t)stride2};
+    const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "tc_make_map3: cuTensorMapEncodeTiled failed with %d (dims %d %d %d, strides %zu %zu, box %d %d %d)", (int)r,
+                 d0, d1, d2, stride1, stride2, b0, b1, b2);
+    return B200TTS_OK;
+}
+
 void set_tc_scratch(void* ptr, size_t bytes) { g_scratch.ptr = static_cast<unsigned char*>(ptr); g_scratch.bytes = bytes; }
 void set_tc_enabled(int on) { g_tc_enabled = on; }
 int tc_enabled() { return g_tc_enabled; }

@@ -67,7 +67,8 @@ def main():
                             if nme != '-':
                                 print(f'   {nme:18s} {rb[0, j] / a.T:9.0f} {act[:, j].mean() / a.T:9.0f} {act[:, j].max() / a.T:9.0f}')
             off = _lib.load().b200tts_debug_persist_profile_offset(ctypes.byref(F.PROFILE['last_shape']))
-            raw = F.PROFILE['last_ws'][off:off + 2 * 148 * 8 * 8].view(torch.int64).view(2, 148, 8).cpu().double()
+            raw4 = F.PROFILE['last_ws'][off:off + 4 * 148 * 8 * 8].view(torch.int64).view(4, 148, 8).cpu().double()
+            raw = raw4[:2]
             names = ['gemm', 'reduce', 'cell+q', 'barrier1', 'attn:q/load', 'attn:energy', 'attn:softmax+ctx', 'barrier2']
             for k, loop in enumerate(('att', 'gen')):
                 act = raw[k][raw[k].sum(1) > 0]
@@ -75,6 +76,16 @@ def main():
                     print(f'{loop} loop: cycles/step by phase, CTA0 | mean | max over CTAs')
                     for j, nme in enumerate(names):
                         print(f'   {nme:18s} {raw[k][0, j] / a.T:9.0f} {act[:, j].mean() / a.T:9.0f} {act[:, j].max() / a.T:9.0f}')
+        if a.precision == 'bf16' and it == a.iters:
+            rn = ['mma ctx: wait 1st box', 'mma ctx: rest', 'mma h: wait 1st box', 'mma h: rest', 'tma ctx: proxy fence', 'tma ctx: issue',
+                  'tma h: proxy fence', 'tma h: issue']
+            for k, loop in enumerate(('att', 'gen')):
+                rr = raw4[2 + k]
+                act = rr[rr.sum(1) > 0]
+                if len(act):
+                    print(f'{loop} loop role threads: cycles/step, CTA0 | mean | max')
+                    for j, nme in enumerate(rn):
+                        print(f'   {nme:22s} {rr[0, j] / a.T:9.0f} {act[:, j].mean() / a.T:9.0f} {act[:, j].max() / a.T:9.0f}')
         for p in params:
             p.grad = None
         memory.grad = None
