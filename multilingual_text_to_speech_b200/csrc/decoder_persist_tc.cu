@@ -118,6 +118,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // named barrier among the compute warps only
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
@@ -209,15 +215,16 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_ok;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform by construction (lets the role loops use uniform registers)
     const int cta = blockIdx.x;
     const int rb = cta % p.RB, bh = cta / p.RB;
     const int u0 = rb * UNITS, b0 = bh * BT;
     const int Kp = p.Kp, D = p.D, B = p.B;
     const unsigned nblocks = gridDim.x;
     const bool compute = warp < NCW;
-    const bool is_producer = (warp == NCW) && lane == 0;
-    const bool is_mma = (warp == NCW + 1) && lane == 0;
+    const bool is_producer = (warp == NCW);        // whole warps run the role loops; one elected lane issues the TMA / MMA instructions
+    const bool is_mma = (warp == NCW + 1);
 
     // ---- shared memory carve-up (1024-byte aligned base: SWIZZLE_128B atoms) ----
     size_t off = 0;
@@ -225,7 +232,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     unsigned char* ring = smem_raw + off; off += (size_t)p.slot_kb * ATILE;           // one slot of [slot_kb][32 rows][128 B] swizzled (TMA)
     float* s_sum = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (ROWS + 1) * 4;
     float* s_hs = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)UNITS * (BT + 4) * 4 : 0;
-    float* s_wq = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)p.A * (UNITS + 1) * 4 : 0;
     __nv_bfloat16* sWcB = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += ATT ? (size_t)p.A * 40 * 2 : 0;
     float* scratch = reinterpret_cast<float*>(smem_raw + off);                        // attention scratch (ATT only)
 
@@ -239,10 +245,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         *reinterpret_cast<__nv_bfloat16*>(sW + (size_t)kb * WTILE + r * 128 + ((chunk ^ (r & 7)) << 4) + e * 2) = __float2bfloat16_rn(w);
     }
     if (ATT) {
-        for (int idx = tid; idx < p.A * UNITS; idx += PT) {
-            const int a = idx / UNITS, u = idx % UNITS;
-            s_wq[a * (UNITS + 1) + u] = (u0 + u < D) ? p.Wq[(size_t)a * D + u0 + u] : 0.f;
-        }
         for (int idx = tid; idx < p.A * 40; idx += PT) sWcB[idx] = p.WcB[idx];
     }
     if (tid == 0) {
@@ -275,8 +277,11 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         const int n = part ? p.n_h : 1, ch = part ? p.ch_h : p.ch_c;
         for (int j = 0; j < n; ++j) {
             mbar_wait(&empty_bar, (prod_it & 1) ^ 1);
-            mbar_expect_tx(&full_bar, (uint32_t)ch * ATILE);
-            tma_load_3d(ring, part ? &tmH : &tmC, &full_bar, 0, step * B + b0, part ? j * ch : p.nkb_h);
+            if (elect_one()) {
+                mbar_expect_tx(&full_bar, (uint32_t)ch * ATILE);
+                tma_load_3d(ring, part ? &tmH : &tmC, &full_bar, 0, step * B + b0, part ? j * ch : p.nkb_h);
+            }
+            __syncwarp();
             ++prod_it;
         }
         rp[2 * part] += t1 - t0; rp[2 * part + 1] += clock64() - t1;
@@ -291,20 +296,40 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             if (j == 0) t1 = clock64();
             tc_fence_after();
             const int kb0 = part ? j * ch : p.nkb_h;
-            for (int c = 0; c < ch; ++c) {
-                const uint64_t adesc = make_sw128_desc(smem_u32(sW + (size_t)(kb0 + c) * WTILE));
-                const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)c * ATILE));
+            if (elect_one()) {
+                for (int c = 0; c < ch; ++c) {
+                    const uint64_t adesc = make_sw128_desc(smem_u32(sW + (size_t)(kb0 + c) * WTILE));
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)c * ATILE));
 #pragma unroll
-                for (int k = 0; k < KB / 16; ++k)
-                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (part == 1 && j == 0 && c == 0 && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < KB / 16; ++k)
+                        umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (part == 1 && j == 0 && c == 0 && k == 0) ? 0u : 1u);
+                }
+                umma_commit(&empty_bar);
+                if (signal_accum && j == n - 1) umma_commit(&accum_bar);
             }
-            umma_commit(&empty_bar);
+            __syncwarp();
             ++cons_it;
         }
-        if (signal_accum) umma_commit(&accum_bar);
         rp[2 * part] += t1 - t0; rp[2 * part + 1] += clock64() - t1;
     };
 
+    // B fragments (k = this CTA's 16 hidden units, n = attention dims of the n-tiles {2 warp, 2 warp + 1}) of the query projection,
+    // split into bf16 hi + lo, resident in registers for the whole sequence
+    uint32_t wqh[2][2] = {{0u, 0u}, {0u, 0u}}, wql[2][2] = {{0u, 0u}, {0u, 0u}};
+    if (ATT && compute) {
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+                const int a = (2 * warp + j) * 8 + g, u = u0 + 2 * tq + 8 * r2;
+                const float x0 = (a < p.A && u < D) ? p.Wq[(size_t)a * D + u] : 0.f, x1 = (a < p.A && u + 1 < D) ? p.Wq[(size_t)a * D + u + 1] : 0.f;
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                __nv_bfloat162 hp2; hp2.x = h0; hp2.y = h1;
+                wqh[j][r2] = *reinterpret_cast<uint32_t*>(&hp2);
+                wql[j][r2] = pack2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+            }
+    }
     const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
     unsigned target = 0;
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -345,7 +370,23 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             }
         }
     };
-    if (compute) prefetch(0, true);
+    // DRAM -> L2 two steps ahead, so that the register prefetch above is an L2 hit (the load-return path is in order: a DRAM-latency
+    // load in front of the attention's L2 loads would stall them)
+    auto prefetch_l2 = [&](int step) {
+        if (step >= p.T) return;
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            const int idx = tid + e2 * CT;
+            const int bl = idx / UNITS, uu = idx % UNITS, b = b0 + bl, u = u0 + uu;
+            if (b < B && u < D && (uu & 7) == 0) {
+                const size_t g0 = ((size_t)step * B + b) * 4 * D + u, mi = ((size_t)step * B + b) * D + u;
+                l2_prefetch(p.gates + g0); l2_prefetch(p.gates + g0 + D); l2_prefetch(p.gates + g0 + 2 * D); l2_prefetch(p.gates + g0 + 3 * D);
+                if (uu == 0 && p.training && p.mask_h) l2_prefetch(p.mask_h + mi);
+                if (uu == 0 && p.training && p.mask_c) l2_prefetch(p.mask_c + mi);
+            }
+        }
+    };
+    if (compute) { prefetch_l2(0); prefetch(0, true); prefetch_l2(1); }
 
     bool alive = true;
     for (int i = 0; i < p.T && alive; ++i) {
@@ -415,26 +456,35 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             }
             if (ATT) {
                 csync();
-                // partial query projection of this CTA's 16 hidden units: qpart[rb, b, a]; thread = (a, 16 utterances)
-                for (int idx = tid; idx < p.A * (BT / 16); idx += CT) {
-                    const int a = idx % p.A, bg = idx / p.A;
-                    float qa[16];
+                // partial query projection of this CTA's 16 hidden units on the tensor cores: qpart[rb, b, a] = sum_u h[b, u] Wq[a, u].
+                // h and Wq are split into bf16 hi + lo and three products are summed (hi.hi + lo.hi + hi.lo), i.e. fp32-equivalent.
+                {
+                    const int g = lane >> 2, tq = lane & 3;
+                    uint32_t ah[2][4], al[2][4];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) qa[j] = 0.f;
+                    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int uu = 0; uu < UNITS; ++uu) {
-                        const float wv = s_wq[a * (UNITS + 1) + uu];
-                        const float4* h4 = reinterpret_cast<const float4*>(&s_hs[uu * (BT + 4) + bg * 16]);
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 hv = h4[j4];
-                            qa[4 * j4] = fmaf(wv, hv.x, qa[4 * j4]); qa[4 * j4 + 1] = fmaf(wv, hv.y, qa[4 * j4 + 1]);
-                            qa[4 * j4 + 2] = fmaf(wv, hv.z, qa[4 * j4 + 2]); qa[4 * j4 + 3] = fmaf(wv, hv.w, qa[4 * j4 + 3]);
+                        for (int r4 = 0; r4 < 4; ++r4) {
+                            const int bl = mt * 16 + g + 8 * (r4 & 1), k = 2 * tq + 8 * (r4 >> 1);
+                            const float x0 = s_hs[k * (BT + 4) + bl], x1 = s_hs[(k + 1) * (BT + 4) + bl];
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                            __nv_bfloat162 hp2; hp2.x = h0; hp2.y = h1;
+                            ah[mt][r4] = *reinterpret_cast<uint32_t*>(&hp2);
+                            al[mt][r4] = pack2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
                         }
-                    }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (b0 + bg * 16 + j < B) p.qpart[((size_t)rb * B + b0 + bg * 16 + j) * p.A + a] = qa[j];
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            mma_bf16(acc, ah[mt], wqh[j][0], wqh[j][1]);
+                            mma_bf16(acc, al[mt], wqh[j][0], wqh[j][1]);
+                            mma_bf16(acc, ah[mt], wql[j][0], wql[j][1]);
+                            const int a = (2 * warp + j) * 8 + 2 * tq;
+                            const int bA = b0 + mt * 16 + g, bB = bA + 8;
+                            if (bA < B) *reinterpret_cast<float2*>(p.qpart + ((size_t)rb * B + bA) * p.A + a) = make_float2(acc[0], acc[1]);
+                            if (bB < B) *reinterpret_cast<float2*>(p.qpart + ((size_t)rb * B + bB) * p.A + a) = make_float2(acc[2], acc[3]);
+                        }
                 }
             }
         }
@@ -447,7 +497,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             if (is_producer) produce(i + 1, 1);
             if (is_mma) { tc_fence_after(); consume(1, !ATT || p.nkb_h == p.nkb); }
             __syncwarp();
-            if (compute) prefetch(i + 1, false);
+            if (compute) { prefetch(i + 1, false); prefetch_l2(i + 2); }
         }
 
         if (ATT) {
@@ -625,7 +675,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     if (p.prof && tid == 0)
         for (int k = 0; k < 8; ++k) p.prof[(size_t)cta * 8 + k] = prof_acc[k];
 #undef PROF_MARK
-    if (p.prof2 && (is_mma || is_producer))
+    if (p.prof2 && (is_mma || is_producer) && lane == 0)
         for (int k = 0; k < 4; ++k) p.prof2[(size_t)cta * 8 + (is_producer ? 4 : 0) + k] = rp[k];
     tc_fence_before();
     __syncthreads();
@@ -639,7 +689,7 @@ size_t tc_loop_smem_bytes(int nkb, int slot_kb, int A, bool att, int L) {
     size_t b = 1024 + (size_t)nkb * WTILE + (size_t)slot_kb * ATILE + (size_t)BT * (ROWS + 1) * 4;
     if (att) {
         const int L16 = (L + 15) / 16 * 16;
-        b += (size_t)UNITS * (BT + 4) * 4 + (size_t)A * (UNITS + 1) * 4 + (size_t)A * 40 * 2;
+        b += (size_t)UNITS * (BT + 4) * 4 + (size_t)A * 40 * 2;
         b += ((size_t)2 * A + L16 + 64 + 8 * A + 2 * (L16 + 48)) * 4;
     }
     return b;
