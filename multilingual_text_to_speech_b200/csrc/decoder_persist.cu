@@ -99,8 +99,11 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
         atomicAdd(counter, 1u);
         int ok = 1;
         const long long t0 = clock64();
-        while (ld_acquire(counter) < target) {
-            if (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag)) { ok = 0; *abort_flag = 1; break; }
+        unsigned polls = 0;
+        while (ld_acquire(counter) < target) {          // nothing but the counter load in the polling loop: its round trip is the barrier latency
+            if ((++polls & 255u) == 0 && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag))) {
+                ok = 0; *abort_flag = 1; break;
+            }
         }
         __threadfence();
         s_ok = ok;

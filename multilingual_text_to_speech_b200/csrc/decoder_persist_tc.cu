@@ -196,8 +196,11 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
         atomicAdd(counter, 1u);
         int ok = 1;
         const long long t0 = clock64();
-        while (ld_acquire(counter) < target) {
-            if (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag)) { ok = 0; *abort_flag = 1; break; }
+        unsigned polls = 0;
+        while (ld_acquire(counter) < target) {          // nothing but the counter load in the polling loop: its round trip is the barrier latency
+            if ((++polls & 255u) == 0 && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag))) {
+                ok = 0; *abort_flag = 1; break;
+            }
         }
         __threadfence();
         *s_ok = ok;
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             if (is_producer) produce(i + 1, 1);
             if (is_mma) { tc_fence_after(); consume(1, !ATT || p.nkb_h == p.nkb); }
             __syncwarp();
-            if (compute) { prefetch(i + 1, false); prefetch_l2(i + 2); }
+            if (compute) { prefetch_l2(i + 2); if (!ATT) prefetch(i + 1, false); }
         }
 
         if (ATT) {
@@ -505,15 +508,22 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             if (compute && cta < B) {
                 const int b = cta, L = p.L, A = p.A, M = p.M, half = (p.KC - 1) / 2;
                 float* qb = scratch;                       // [A]
-                float* vv = qb + A;                        // [A]
-                float* e = vv + A;                         // [L16]
-                float* red = e + p.MT * 16;                // [64]
+                float* vv = qb + A;                        // [A]   persistent: energy vector
+                float* bias_s = vv + A;                    // [A]   persistent: attention bias
+                float* cum_s = bias_s + A;                 // [L16] persistent: cumulative attention weights of this utterance
+                float* e = cum_s + p.MT * 16;              // [L16]
+                float* e2 = e + p.MT * 16;                 // [L16] energies of the second half of the attention dims
+                float* red = e2 + p.MT * 16;               // [64]
                 float* cred = red + 64;                    // [8][A] query partials
                 uint32_t* Ph = reinterpret_cast<uint32_t*>(cred + 8 * A);     // [L16 + 48] Toeplitz pair arrays (hi / lo bf16 split)
                 uint32_t* Pl = Ph + (p.MT * 16 + 48);
                 int len = p.lengths[b];
                 len = len < 0 ? 0 : (len > L ? L : len);
-                const float* cum_prev = p.cum + ((size_t)i * B + b) * L;
+                if (i == 0) {                              // one-time: constants and the initial cumulative weights into shared memory
+                    for (int a2 = tid; a2 < A; a2 += CT) { vv[a2] = p.v[a2]; bias_s[a2] = p.bias[a2]; }
+                    for (int l = tid; l < p.MT * 16; l += CT) cum_s[l] = l < L ? p.cum[(size_t)b * L + l] : 0.f;
+                    csync();
+                }
                 {   // q[a] = sum over the RB per-CTA partial projections: thread = (4 attention dims, one eighth of the row blocks)
                     const int a4 = tid & 31, sl = tid >> 5;
                     const int per = (p.RB + 7) / 8, r0 = sl * per, r1 = min(p.RB, r0 + per);
@@ -534,8 +544,8 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     for (int x = tid; x < p.MT * 16 + 48; x += CT) {
                         float c0 = 0.f, c1 = 0.f;
                         const int la = x - half, lb = x + 1 - half;
-                        if (la >= 0 && la < L) c0 = __ldcg(cum_prev + la);
-                        if (lb >= 0 && lb < L) c1 = __ldcg(cum_prev + lb);
+                        if (la >= 0 && la < L) c0 = cum_s[la];
+                        if (lb >= 0 && lb < L) c1 = cum_s[lb];
                         const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
                         __nv_bfloat162 hp2; hp2.x = h0; hp2.y = h1;
                         Ph[x] = *reinterpret_cast<uint32_t*>(&hp2);
@@ -547,8 +557,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
 #pragma unroll
                         for (int sl2 = 0; sl2 < 8; ++sl2) q += cred[sl2 * A + a2];
                         p.qsave[((size_t)i * B + b) * A + a2] = q;
-                        qb[a2] = q + p.bias[a2];
-                        vv[a2] = p.v[a2];
+                        qb[a2] = q + bias_s[a2];
                     }
                 }
                 csync();
@@ -557,11 +566,16 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                 {
                     const int g = lane >> 2, tq = lane & 3;
                     const int mtiles = (len + 15) / 16;
-                    for (int mt = warp; mt < mtiles; mt += NCW) {
+                    for (int job = warp; job < 2 * mtiles; job += NCW) {      // job = (position tile, half of the attention dims)
+                        const int mt = job >> 1, hf8 = job & 1;
                         const int l0 = mt * 16;
-                        float sacc[16][4];
+                        const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + mt) * 32 + lane) * 64) + hf8 * 4;
+                        uint4 raw[4];
 #pragma unroll
-                        for (int nt = 0; nt < 16; ++nt)
+                        for (int c4 = 0; c4 < 4; ++c4) raw[c4] = __ldg(mf + c4);
+                        float sacc[8][4];
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
                             for (int e4 = 0; e4 < 4; ++e4) sacc[nt][e4] = 0.f;
 #pragma unroll
@@ -570,25 +584,23 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                             const uint32_t ah[4] = {Ph[x], Ph[x + 8], Ph[x + 8], Ph[x + 16]};
                             const uint32_t al[4] = {Pl[x], Pl[x + 8], Pl[x + 8], Pl[x + 16]};
 #pragma unroll
-                            for (int np = 0; np < 8; ++np) {
+                            for (int np = 0; np < 4; ++np) {
                                 uint32_t bfr[4];
                                 ldmatrix_x4(bfr[0], bfr[1], bfr[2], bfr[3],
-                                            sWcB + (size_t)(np * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
+                                            sWcB + (size_t)((hf8 * 4 + np) * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
                                 mma_bf16(sacc[2 * np], ah, bfr[0], bfr[1]);
                                 mma_bf16(sacc[2 * np], al, bfr[0], bfr[1]);
                                 mma_bf16(sacc[2 * np + 1], ah, bfr[2], bfr[3]);
                                 mma_bf16(sacc[2 * np + 1], al, bfr[2], bfr[3]);
                             }
                         }
-                        const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + mt) * 32 + lane) * 64);
                         float e0 = 0.f, e1 = 0.f;
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const uint4 raw = mf[c4];
-                            const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const uint32_t words[4] = {raw[c4].x, raw[c4].y, raw[c4].z, raw[c4].w};
 #pragma unroll
                             for (int hf = 0; hf < 2; ++hf) {
-                                const int nt = 2 * c4 + hf, a0 = nt * 8 + 2 * tq;
+                                const int nt = 2 * c4 + hf, a0 = (hf8 * 8 + nt) * 8 + 2 * tq;
                                 const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf]));
                                 const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf + 1]));
                                 e0 = fmaf(vv[a0], tanh_fast(sacc[nt][0] + qb[a0] + m01.x), e0);
@@ -599,13 +611,14 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         }
                         e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
                         e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
-                        if (tq == 0) { e[l0 + g] = e0; e[l0 + g + 8] = e1; }
+                        float* eo = hf8 ? e2 : e;
+                        if (tq == 0) { eo[l0 + g] = e0; eo[l0 + g + 8] = e1; }
                     }
                 }
                 csync();
                 PROF_MARK(5);
                 float mx = -INFINITY;
-                for (int l = tid; l < len; l += CT) mx = fmaxf(mx, e[l]);
+                for (int l = tid; l < len; l += CT) { const float ev = e[l] + e2[l]; e[l] = ev; mx = fmaxf(mx, ev); }
                 mx = cblock_max(mx, red);
                 float sum = 0.f;
                 for (int l = tid; l < len; l += CT) { const float ex = expf(e[l] - mx); e[l] = ex; sum += ex; }
@@ -617,7 +630,9 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     e[l] = w;
                     if (l < L) {
                         p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
-                        cum_next[l] = __ldcg(cum_prev + l) + w;
+                        const float cn = cum_s[l] + w;
+                        cum_s[l] = cn;
+                        cum_next[l] = cn;
                     }
                 }
                 csync();
@@ -667,6 +682,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     }
                 }
             }
+            if (compute && i + 1 < p.T) prefetch(i + 1, false);      // L2 hits (prefetched a step ago); they land behind the barrier wait
             PROF_MARK(6);
             if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
             PROF_MARK(7);
@@ -690,7 +706,7 @@ size_t tc_loop_smem_bytes(int nkb, int slot_kb, int A, bool att, int L) {
     if (att) {
         const int L16 = (L + 15) / 16 * 16;
         b += (size_t)UNITS * (BT + 4) * 4 + (size_t)A * 40 * 2;
-        b += ((size_t)2 * A + L16 + 64 + 8 * A + 2 * (L16 + 48)) * 4;
+        b += ((size_t)3 * A + 3 * L16 + 64 + 8 * A + 2 * (L16 + 48)) * 4;
     }
     return b;
 }
