@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=900)
     ap.add_argument('--regularization', default='zoneout', choices=['zoneout', 'dropout'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--breakdown', default='', help='write a per-kernel device-time table of one extra (untimed) step to this file')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help="bf16: tensor-core operands, fp32 master/state (BASELINE configs[1]); fp32: exact parity mode")
     return ap.parse_args()
@@ -274,6 +275,19 @@ def run_b200(a):
     dec_ms = [s.elapsed_time(e) for s, e in F.PROFILE.get('decoder_fwd', [])]
     ms_e2e, loss_val = timed(a.steps, from_host=True)
     clocks = sampler.stop() if rank == 0 else None
+    if a.breakdown and rank == 0:       # CUPTI kernel times of ONE extra step (not part of any reported number)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(resident)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        with open(a.breakdown, 'w') as f:
+            f.write(f'{"kernel":80s} {"n":>6s} {"total_us":>12s} {"avg_us":>10s} {"share":>7s}\n')
+            for e in rows:
+                f.write(f'{e.key[:80]:80s} {e.count:6d} {e.device_time_total:12.1f} {e.device_time_total / max(e.count, 1):10.2f} '
+                        f'{100 * e.device_time_total / max(tot, 1e-9):6.1f}%\n')
+            f.write(f'{"TOTAL":80s} {sum(e.count for e in rows):6d} {tot:12.1f}\n')
 
     if rank == 0:
         frames = world * B * T * a.steps

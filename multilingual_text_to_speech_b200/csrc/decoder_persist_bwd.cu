@@ -372,35 +372,44 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
             // MMA), B = (hi(dctx), lo(dctx)) in columns 0 / 1; warp owns position tiles {warp, warp + 8}
             {
                 const int g = lane >> 2, tq = lane & 3;
+                constexpr int KT = 6;                         // k-tiles (16 memory dims) per register batch
                 for (int lt = warp; lt < p.MT; lt += 8) {
-                    float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+                    float dacc[4] = {0.f, 0.f, 0.f, 0.f}, dacc2[4] = {0.f, 0.f, 0.f, 0.f};
                     if (lt * 16 < len) {
                         const uint4* fr = p.memFb + (((size_t)b * p.MT + lt) * p.M16) * 32 + lane;
-                        for (int kt0 = 0; kt0 < p.M16; kt0 += 6) {
-                            uint4 av[6];
+                        for (int kt0 = 0; kt0 < p.M16; kt0 += KT) {
+                            uint4 av[KT];
 #pragma unroll
-                            for (int j = 0; j < 6; ++j)
+                            for (int j = 0; j < KT; ++j)
                                 if (kt0 + j < p.M16) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
+                            // B fragments: lanes g = 0 hold hi(dctx), g = 1 hold lo(dctx), other columns zero (branch-free)
+                            uint32_t bfr[KT][2];
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) {
+                            for (int j = 0; j < KT; ++j) {
+                                const int m0 = (kt0 + j) * 16 + 2 * tq;
+                                const float w0 = m0 < M ? s_dctx[m0] : 0.f, w1 = m0 + 1 < M ? s_dctx[m0 + 1] : 0.f;
+                                const float w2 = m0 + 8 < M ? s_dctx[m0 + 8] : 0.f, w3 = m0 + 9 < M ? s_dctx[m0 + 9] : 0.f;
+                                const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
+                                const float h2 = __bfloat162float(__float2bfloat16_rn(w2)), h3 = __bfloat162float(__float2bfloat16_rn(w3));
+                                const float s0 = g == 0 ? h0 : (g == 1 ? w0 - h0 : 0.f), s1 = g == 0 ? h1 : (g == 1 ? w1 - h1 : 0.f);
+                                const float s2 = g == 0 ? h2 : (g == 1 ? w2 - h2 : 0.f), s3 = g == 0 ? h3 : (g == 1 ? w3 - h3 : 0.f);
+                                bfr[j][0] = pack2(s0, s1); bfr[j][1] = pack2(s2, s3);
+                            }
+#pragma unroll
+                            for (int j = 0; j < KT; j += 2) {        // two independent accumulation chains
                                 if (kt0 + j < p.M16) {
-                                    uint32_t bb0 = 0u, bb1 = 0u;
-                                    if (g < 2) {
-                                        const int m0 = (kt0 + j) * 16 + 2 * tq;
-                                        float w0 = m0 < M ? s_dctx[m0] : 0.f, w1 = m0 + 1 < M ? s_dctx[m0 + 1] : 0.f;
-                                        float w2 = m0 + 8 < M ? s_dctx[m0 + 8] : 0.f, w3 = m0 + 9 < M ? s_dctx[m0 + 9] : 0.f;
-                                        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
-                                        const __nv_bfloat16 h2 = __float2bfloat16_rn(w2), h3 = __float2bfloat16_rn(w3);
-                                        if (g == 1) { w0 -= __bfloat162float(h0); w1 -= __bfloat162float(h1); w2 -= __bfloat162float(h2); w3 -= __bfloat162float(h3); }
-                                        else { w0 = __bfloat162float(h0); w1 = __bfloat162float(h1); w2 = __bfloat162float(h2); w3 = __bfloat162float(h3); }
-                                        bb0 = pack2(w0, w1); bb1 = pack2(w2, w3);
-                                    }
                                     const uint32_t af[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
-                                    mma_bf16(dacc, af, bb0, bb1);
+                                    mma_bf16(dacc, af, bfr[j][0], bfr[j][1]);
+                                }
+                                if (kt0 + j + 1 < p.M16) {
+                                    const uint32_t af[4] = {av[j + 1].x, av[j + 1].y, av[j + 1].z, av[j + 1].w};
+                                    mma_bf16(dacc2, af, bfr[j + 1][0], bfr[j + 1][1]);
                                 }
                             }
                         }
                     }
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) dacc[q4] += dacc2[q4];
                     if (tq == 0) {
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {

@@ -124,6 +124,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// thread-block cluster (CTA pair) primitives: split arrive / wait barrier and a distributed-shared-memory store
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_peer_f32(const float* local_smem, uint32_t peer_rank, float v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(peer_rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
 // named barrier among the compute warps only
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
@@ -403,7 +411,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             // accumulator [64 gate rows x 32 utterances]: TMEM lane 32 * gate + unit, column = utterance
             mbar_wait(&accum_bar, i & 1);
             tc_fence_after();
-            PROF_MARK(0);
             {
                 const int q = warp & 3, c0 = (warp >> 2) * 16;
                 uint32_t r[16];
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             }
             tc_fence_before();
             csync();
-            PROF_MARK(1);
+            PROF_MARK(0);
             // =================== LSTM cell + regulariser (2 (b, u) pairs per thread) ===================
 #pragma unroll
             for (int e2 = 0; e2 < 2; ++e2) {
@@ -491,11 +498,12 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                 }
             }
         }
-        PROF_MARK(2);
+        PROF_MARK(1);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
-        PROF_MARK(3);
+        PROF_MARK(2);
 
         // =================== h part of step i+1: TMA + tcgen05 run while the attention of step i is computed ===================
+        if (ATT && !compute) cluster_arrive();      // role warps: non-blocking arrival at this step's pair barrier (waited on after the role work)
         if (i + 1 < p.T) {
             if (is_producer) produce(i + 1, 1);
             if (is_mma) { tc_fence_after(); consume(1, !ATT || p.nkb_h == p.nkb); }
@@ -504,44 +512,63 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         }
 
         if (ATT) {
-            // =================== attention of utterance `cta` (CTAs 0 .. B-1, compute warps) ===================
-            if (compute && cta < B) {
-                const int b = cta, L = p.L, A = p.A, M = p.M, half = (p.KC - 1) / 2;
-                float* qb = scratch;                       // [A]
-                float* vv = qb + A;                        // [A]   persistent: energy vector
-                float* bias_s = vv + A;                    // [A]   persistent: attention bias
-                float* cum_s = bias_s + A;                 // [L16] persistent: cumulative attention weights of this utterance
-                float* e = cum_s + p.MT * 16;              // [L16]
-                float* e2 = e + p.MT * 16;                 // [L16] energies of the second half of the attention dims
-                float* red = e2 + p.MT * 16;               // [64]
-                float* cred = red + 64;                    // [8][A] query partials
-                uint32_t* Ph = reinterpret_cast<uint32_t*>(cred + 8 * A);     // [L16 + 48] Toeplitz pair arrays (hi / lo bf16 split)
-                uint32_t* Pl = Ph + (p.MT * 16 + 48);
+            // =================== attention: one CTA PAIR (cluster of 2) per utterance ===================
+            // pair pc = cta >> 1 serves utterance pc; rank hf = cta & 1 owns the attention dims [64 hf, 64 hf + 64) of the energies
+            // (partial sums exchanged through distributed shared memory, one cluster barrier) and one half of the context tiles.
+            const int pc = cta >> 1, hf = cta & 1;
+            if (compute && pc < B) {
+                const int b = pc, L = p.L, A = p.A, AH = p.A / 2, M = p.M, half = (p.KC - 1) / 2, L16 = p.MT * 16;
+                float* qb = scratch;                       // [AH]  query + bias of this rank's attention dims
+                float* vv = qb + AH;                       // [AH]  persistent: energy vector
+                float* bias_s = vv + AH;                   // [AH]  persistent: attention bias
+                float* cum_s = bias_s + AH;                // [L16] persistent: cumulative attention weights of this utterance
+                float* e = cum_s + L16;                    // [L16] energies -> weights
+                float* eq = e + L16;                       // [2][L16] quarter-job partial energies
+                float* epart = eq + 2 * L16;               // [2][L16] per-rank partial energies (slot 1 - hf is written by the peer CTA)
+                float* red = epart + 2 * L16;              // [64]
+                float* cred = red + 64;                    // [16][AH] query partials
+                uint32_t* Ph = reinterpret_cast<uint32_t*>(cred + 16 * AH);   // [L16 + 48] Toeplitz pair arrays (hi / lo bf16 split)
+                uint32_t* Pl = Ph + (L16 + 48);
                 int len = p.lengths[b];
                 len = len < 0 ? 0 : (len > L ? L : len);
+                const int mtiles = (len + 15) / 16, ktiles = mtiles;
                 if (i == 0) {                              // one-time: constants and the initial cumulative weights into shared memory
-                    for (int a2 = tid; a2 < A; a2 += CT) { vv[a2] = p.v[a2]; bias_s[a2] = p.bias[a2]; }
-                    for (int l = tid; l < p.MT * 16; l += CT) cum_s[l] = l < L ? p.cum[(size_t)b * L + l] : 0.f;
+                    for (int a2 = tid; a2 < AH; a2 += CT) { vv[a2] = p.v[hf * AH + a2]; bias_s[a2] = p.bias[hf * AH + a2]; }
+                    for (int l = tid; l < L16; l += CT) cum_s[l] = l < L ? p.cum[(size_t)b * L + l] : 0.f;
                     csync();
                 }
-                {   // q[a] = sum over the RB per-CTA partial projections: thread = (4 attention dims, one eighth of the row blocks)
-                    const int a4 = tid & 31, sl = tid >> 5;
-                    const int per = (p.RB + 7) / 8, r0 = sl * per, r1 = min(p.RB, r0 + per);
+                // memory-projection fragments of this warp's first energy job and memory fragments of its first context tile:
+                // neither depends on this step's state, so they are requested first and land behind the query reduction
+                constexpr int KTMAX = 12;                  // k-tiles (16 positions) per register batch of the context product
+                const int mt_lo = hf * ((p.M16 + 1) / 2), mt_hi = min(p.M16, mt_lo + (p.M16 + 1) / 2);
+                uint4 nraw[2];
+                if (warp < 2 * mtiles) {
+                    const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + (warp >> 1)) * 32 + lane) * 64) + hf * 4 + (warp & 1) * 2;
+                    nraw[0] = __ldg(mf); nraw[1] = __ldg(mf + 1);
+                }
+                uint4 av[KTMAX];
+                if (mt_lo + warp < mt_hi) {
+                    const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt_lo + warp) * p.MT) * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < KTMAX; ++j)
+                        if (j < ktiles) av[j] = __ldg(fr + (size_t)j * 32);
+                }
+                {   // q[a] = sum over the RB per-CTA partial projections: thread = (4 attention dims, one sixteenth of the row blocks)
+                    const int a4 = tid & 15, sl = tid >> 4;
+                    const int per = (p.RB + 15) / 16, r0 = sl * per, r1 = min(p.RB, r0 + per);
                     float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (a4 * 4 < A) {
-                        for (int r = r0; r < r1; r += 8) {
-                            float4 v[8];
+                    for (int r = r0; r < r1; r += 4) {
+                        float4 v[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                v[j] = (r + j < r1) ? __ldcg(reinterpret_cast<const float4*>(p.qpart + ((size_t)(r + j) * B + b) * A) + a4)
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < 4; ++j)
+                            v[j] = (r + j < r1) ? __ldcg(reinterpret_cast<const float4*>(p.qpart + ((size_t)(r + j) * B + b) * A + hf * AH) + a4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { qs.x += v[j].x; qs.y += v[j].y; qs.z += v[j].z; qs.w += v[j].w; }
-                        }
-                        *reinterpret_cast<float4*>(cred + sl * A + a4 * 4) = qs;
+                        for (int j = 0; j < 4; ++j) { qs.x += v[j].x; qs.y += v[j].y; qs.z += v[j].z; qs.w += v[j].w; }
                     }
+                    *reinterpret_cast<float4*>(cred + sl * AH + a4 * 4) = qs;
                     // cumulative weights -> (hi, lo) bf16 pairs: Ph[x] = (c[x], c[x+1]) with c[j] = cum[j - half]
-                    for (int x = tid; x < p.MT * 16 + 48; x += CT) {
+                    for (int x = tid; x < L16 + 48; x += CT) {
                         float c0 = 0.f, c1 = 0.f;
                         const int la = x - half, lb = x + 1 - half;
                         if (la >= 0 && la < L) c0 = cum_s[la];
@@ -552,30 +579,31 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         Pl[x] = pack2(c0 - __bfloat162float(h0), c1 - __bfloat162float(h1));
                     }
                     csync();
-                    for (int a2 = tid; a2 < A; a2 += CT) {
+                    for (int a2 = tid; a2 < AH; a2 += CT) {
                         float q = 0.f;
 #pragma unroll
-                        for (int sl2 = 0; sl2 < 8; ++sl2) q += cred[sl2 * A + a2];
-                        p.qsave[((size_t)i * B + b) * A + a2] = q;
+                        for (int sl2 = 0; sl2 < 16; ++sl2) q += cred[sl2 * AH + a2];
+                        p.qsave[((size_t)i * B + b) * A + hf * AH + a2] = q;
                         qb[a2] = q + bias_s[a2];
                     }
                 }
                 csync();
-                PROF_MARK(4);
-                // energies on the tensor cores: S[l, a] = sum_k cumpad[l + k] * Wcomb[a, k]; warp owns position tiles {warp, warp+8}
+                PROF_MARK(3);
+                // energies on the tensor cores: S[l, a] = sum_k cumpad[l + k] * Wcomb[a, k].  job = (16-position tile, quarter of the
+                // attention dims: 4 n-tiles of 8 within this rank's half) -> 2 mtiles jobs, 3 per warp for L = 180
                 {
                     const int g = lane >> 2, tq = lane & 3;
-                    const int mtiles = (len + 15) / 16;
-                    for (int job = warp; job < 2 * mtiles; job += NCW) {      // job = (position tile, half of the attention dims)
-                        const int mt = job >> 1, hf8 = job & 1;
-                        const int l0 = mt * 16;
-                        const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + mt) * 32 + lane) * 64) + hf8 * 4;
-                        uint4 raw[4];
+                    for (int job = warp; job < 2 * mtiles; job += NCW) {
+                        const int mt = job >> 1, qh = job & 1, l0 = mt * 16;
+                        const uint4 raw[2] = {nraw[0], nraw[1]};
+                        if (job + NCW < 2 * mtiles) {        // next job's fragments: in flight during this job's MMAs
+                            const int nj = job + NCW;
+                            const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + (nj >> 1)) * 32 + lane) * 64) + hf * 4 + (nj & 1) * 2;
+                            nraw[0] = __ldg(mf); nraw[1] = __ldg(mf + 1);
+                        }
+                        float sacc[4][4];
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) raw[c4] = __ldg(mf + c4);
-                        float sacc[8][4];
-#pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
+                        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                             for (int e4 = 0; e4 < 4; ++e4) sacc[nt][e4] = 0.f;
 #pragma unroll
@@ -584,10 +612,10 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                             const uint32_t ah[4] = {Ph[x], Ph[x + 8], Ph[x + 8], Ph[x + 16]};
                             const uint32_t al[4] = {Pl[x], Pl[x + 8], Pl[x + 8], Pl[x + 16]};
 #pragma unroll
-                            for (int np = 0; np < 4; ++np) {
+                            for (int np = 0; np < 2; ++np) {
                                 uint32_t bfr[4];
                                 ldmatrix_x4(bfr[0], bfr[1], bfr[2], bfr[3],
-                                            sWcB + (size_t)((hf8 * 4 + np) * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
+                                            sWcB + (size_t)((hf * 4 + qh * 2 + np) * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
                                 mma_bf16(sacc[2 * np], ah, bfr[0], bfr[1]);
                                 mma_bf16(sacc[2 * np], al, bfr[0], bfr[1]);
                                 mma_bf16(sacc[2 * np + 1], ah, bfr[2], bfr[3]);
@@ -596,13 +624,13 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         }
                         float e0 = 0.f, e1 = 0.f;
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
+                        for (int c4 = 0; c4 < 2; ++c4) {
                             const uint32_t words[4] = {raw[c4].x, raw[c4].y, raw[c4].z, raw[c4].w};
 #pragma unroll
-                            for (int hf = 0; hf < 2; ++hf) {
-                                const int nt = 2 * c4 + hf, a0 = (hf8 * 8 + nt) * 8 + 2 * tq;
-                                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf]));
-                                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * hf + 1]));
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                const int nt = 2 * c4 + h2, a0 = (qh * 4 + nt) * 8 + 2 * tq;      // index inside this rank's 64 dims
+                                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * h2]));
+                                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&words[2 * h2 + 1]));
                                 e0 = fmaf(vv[a0], tanh_fast(sacc[nt][0] + qb[a0] + m01.x), e0);
                                 e0 = fmaf(vv[a0 + 1], tanh_fast(sacc[nt][1] + qb[a0 + 1] + m01.y), e0);
                                 e1 = fmaf(vv[a0], tanh_fast(sacc[nt][2] + qb[a0] + m23.x), e1);
@@ -611,65 +639,87 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         }
                         e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
                         e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
-                        float* eo = hf8 ? e2 : e;
-                        if (tq == 0) { eo[l0 + g] = e0; eo[l0 + g + 8] = e1; }
+                        if (tq == 0) { eq[qh * L16 + l0 + g] = e0; eq[qh * L16 + l0 + g + 8] = e1; }
                     }
                 }
                 csync();
-                PROF_MARK(5);
+                // this rank's partial energies: own copy + the peer's copy through distributed shared memory, then the pair barrier
+                for (int l = tid; l < L16; l += CT) {
+                    const float v = l < mtiles * 16 ? eq[l] + eq[L16 + l] : 0.f;
+                    epart[hf * L16 + l] = v;
+                    st_peer_f32(epart + hf * L16 + l, (uint32_t)(hf ^ 1), v);
+                }
+                cluster_arrive();
+                cluster_wait();
+                PROF_MARK(4);
                 float mx = -INFINITY;
-                for (int l = tid; l < len; l += CT) { const float ev = e[l] + e2[l]; e[l] = ev; mx = fmaxf(mx, ev); }
+                for (int l = tid; l < len; l += CT) { const float ev = epart[l] + epart[L16 + l]; e[l] = ev; mx = fmaxf(mx, ev); }
                 mx = cblock_max(mx, red);
                 float sum = 0.f;
                 for (int l = tid; l < len; l += CT) { const float ex = expf(e[l] - mx); e[l] = ex; sum += ex; }
                 sum = cblock_sum(sum, red + 32);
                 float* cum_next = p.cum + ((size_t)(i + 1) * B + b) * L;
                 const float inv_sum = 1.f / sum;
-                for (int l = tid; l < p.MT * 16; l += CT) {      // the padded tail must be zero: the context MMA reads whole 16-position tiles
+                for (int l = tid; l < L16; l += CT) {       // the padded tail must be zero: the context MMA reads whole 16-position tiles
                     const float w = l < len ? e[l] * inv_sum : 0.f;
                     e[l] = w;
                     if (l < L) {
-                        p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
                         const float cn = cum_s[l] + w;
-                        cum_s[l] = cn;
-                        cum_next[l] = cn;
+                        cum_s[l] = cn;                      // both ranks keep the full cumulative weights; the global stores are shared out
+                        if (hf == 0) p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] = w;
+                        else cum_next[l] = cn;
                     }
                 }
                 csync();
-                // context on the tensor cores: ctx[m] = sum_l memory[l, m] * w[l].  A = memory^T fragments (fragment-major bf16, one
-                // 16-byte load per lane per MMA), B = (hi(w), lo(w)) in columns 0 / 1 -> column 0 + column 1 of D is the fp32-weighted sum.
+                PROF_MARK(5);
+                // context on the tensor cores: ctx[m] = sum_l memory[l, m] * w[l] for this rank's half of the 16-row tiles.  A = memory^T
+                // fragments (fragment-major bf16, one 16-byte load per lane per MMA), B = (hi(w), lo(w)) in columns 0 / 1, so that
+                // column 0 + column 1 of D is the fp32-weighted sum.
                 {
                     const int g = lane >> 2, tq = lane & 3;
-                    const int ktiles = (len + 15) / 16;
-                    for (int mt = warp; mt < p.M16; mt += NCW) {
-                        const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt) * p.MT) * 32 + lane;
-                        float dacc[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int kt0 = 0; kt0 < ktiles; kt0 += 12) {
-                            uint4 av[12];
+                    uint32_t bfr[KTMAX][2];                // B fragments: lanes g = 0 hold hi(w), g = 1 hold lo(w), other columns zero
+                    auto build_b = [&](int kt0) {
 #pragma unroll
-                            for (int j = 0; j < 12; ++j)
-                                if (kt0 + j < ktiles) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
+                        for (int j = 0; j < KTMAX; ++j) {
+                            bfr[j][0] = 0u; bfr[j][1] = 0u;
+                            if (kt0 + j < ktiles) {
+                                const float* wl = e + (kt0 + j) * 16 + 2 * tq;
+                                const float w0 = wl[0], w1 = wl[1], w2 = wl[8], w3 = wl[9];
+                                const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
+                                const float h2 = __bfloat162float(__float2bfloat16_rn(w2)), h3 = __bfloat162float(__float2bfloat16_rn(w3));
+                                const float s0 = g == 0 ? h0 : (g == 1 ? w0 - h0 : 0.f), s1 = g == 0 ? h1 : (g == 1 ? w1 - h1 : 0.f);
+                                const float s2 = g == 0 ? h2 : (g == 1 ? w2 - h2 : 0.f), s3 = g == 0 ? h3 : (g == 1 ? w3 - h3 : 0.f);
+                                bfr[j][0] = pack2(s0, s1); bfr[j][1] = pack2(s2, s3);
+                            }
+                        }
+                    };
+                    const bool single = ktiles <= KTMAX;
+                    if (single) build_b(0);
+                    for (int mt = mt_lo + warp; mt < mt_hi; mt += NCW) {
+                        float dacc[4] = {0.f, 0.f, 0.f, 0.f}, dacc2[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int kt0 = 0; kt0 < ktiles; kt0 += KTMAX) {
+                            if (kt0 > 0 || mt != mt_lo + warp) {      // everything but the prefetched first batch
+                                const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt) * p.MT) * 32 + lane;
 #pragma unroll
-                            for (int j = 0; j < 12; ++j) {
+                                for (int j = 0; j < KTMAX; ++j)
+                                    if (kt0 + j < ktiles) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
+                            }
+                            if (!single) build_b(kt0);
+#pragma unroll
+                            for (int j = 0; j < KTMAX; j += 2) {   // two independent accumulation chains
                                 if (kt0 + j < ktiles) {
-                                    uint32_t bb0 = 0u, bb1 = 0u;
-                                    if (g < 2) {
-                                        const float* wl = e + (kt0 + j) * 16 + 2 * tq;
-                                        float w0 = wl[0], w1 = wl[1], w2 = wl[8], w3 = wl[9];
-                                        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
-                                        const __nv_bfloat16 h2 = __float2bfloat16_rn(w2), h3 = __float2bfloat16_rn(w3);
-                                        if (g == 1) { w0 -= __bfloat162float(h0); w1 -= __bfloat162float(h1); w2 -= __bfloat162float(h2); w3 -= __bfloat162float(h3); }
-                                        else { w0 = __bfloat162float(h0); w1 = __bfloat162float(h1); w2 = __bfloat162float(h2); w3 = __bfloat162float(h3); }
-                                        bb0 = pack2(w0, w1); bb1 = pack2(w2, w3);
-                                    }
                                     const uint32_t af[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
-                                    mma_bf16(dacc, af, bb0, bb1);
+                                    mma_bf16(dacc, af, bfr[j][0], bfr[j][1]);
+                                }
+                                if (kt0 + j + 1 < ktiles) {
+                                    const uint32_t af[4] = {av[j + 1].x, av[j + 1].y, av[j + 1].z, av[j + 1].w};
+                                    mma_bf16(dacc2, af, bfr[j + 1][0], bfr[j + 1][1]);
                                 }
                             }
                         }
                         if (tq == 0) {
                             const int m0 = mt * 16 + g;
-                            const float c0 = dacc[0] + dacc[1], c1 = dacc[2] + dacc[3];
+                            const float c0 = (dacc[0] + dacc2[0]) + (dacc[1] + dacc2[1]), c1 = (dacc[2] + dacc2[2]) + (dacc[3] + dacc2[3]);
                             if (m0 < M) {
                                 p.actf[((size_t)(i + 1) * B + b) * p.ldf + m0] = c0;
                                 p.actb[((size_t)(i + 1) * B + b) * Kp + D + m0] = __float2bfloat16_rn(c0);
@@ -681,6 +731,11 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         }
                     }
                 }
+            } else if (compute) {
+                cluster_arrive();          // idle pairs: every thread of the cluster takes part in the pair barrier
+                cluster_wait();
+            } else {
+                cluster_wait();            // role warps: arrived before their TMA / MMA work (below the cell barrier)
             }
             if (compute && i + 1 < p.T) prefetch(i + 1, false);      // L2 hits (prefetched a step ago); they land behind the barrier wait
             PROF_MARK(6);
@@ -706,7 +761,7 @@ size_t tc_loop_smem_bytes(int nkb, int slot_kb, int A, bool att, int L) {
     if (att) {
         const int L16 = (L + 15) / 16 * 16;
         b += (size_t)UNITS * (BT + 4) * 4 + (size_t)A * 40 * 2;
-        b += ((size_t)3 * A + 3 * L16 + 64 + 8 * A + 2 * (L16 + 48)) * 4;
+        b += ((size_t)3 * (A / 2) + 6 * L16 + 64 + 16 * (A / 2) + 2 * (L16 + 48)) * 4;
     }
     return b;
 }
@@ -754,17 +809,31 @@ bool tc_persist_supported(const b200tts_decoder_shape& s) {
 static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tmH, const CUtensorMap& tmC, size_t smem, cudaStream_t st) {
     void* fn = att ? (void*)lstm_loop_tc_kernel<true> : (void*)lstm_loop_tc_kernel<false>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
-    int dev = 0, sms = 0;
-    B200_CUDA(cudaGetDevice(&dev));
-    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.RB * a.NBH;
-    B200_REQUIRE(per_sm * sms >= grid, "tcgen05 persistent loop: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, sms);
     TcLoopArgs args = a;
     CUtensorMap mapH = tmH, mapC = tmC;
     void* params[] = {&mapH, &mapC, &args};
-    B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
+    cfg.attrs = attrs; cfg.numAttrs = 1;
+    if (att) {      // the attention runs on CTA pairs: clusters of 2 (distributed shared memory + cluster barrier)
+        B200_REQUIRE(grid % 2 == 0 && grid / 2 >= a.B, "tcgen05 attention loop: %d CTAs cannot form %d pairs", grid, a.B);
+        attrs[1].id = cudaLaunchAttributeClusterDimension;
+        attrs[1].val.clusterDim.x = 2; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+        int nclusters = 0;
+        B200_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg));
+        B200_REQUIRE(nclusters * 2 >= grid, "tcgen05 attention loop: only %d CTA pairs can be co-resident, %d needed", nclusters, grid / 2);
+    } else {
+        int per_sm = 0, dev = 0, sms = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
+        B200_CUDA(cudaGetDevice(&dev));
+        B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        B200_REQUIRE(per_sm * sms >= grid, "tcgen05 persistent loop: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, sms);
+    }
+    B200_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
 }

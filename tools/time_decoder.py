@@ -69,7 +69,7 @@ def main():
             off = _lib.load().b200tts_debug_persist_profile_offset(ctypes.byref(F.PROFILE['last_shape']))
             raw4 = F.PROFILE['last_ws'][off:off + 4 * 148 * 8 * 8].view(torch.int64).view(4, 148, 8).cpu().double()
             raw = raw4[:2]
-            names = ['gemm', 'reduce', 'cell+q', 'barrier1', 'attn:q/load', 'attn:energy', 'attn:softmax+ctx', 'barrier2']
+            names = ['gemm+tmem', 'cell+q', 'barrier1', 'attn:q/load', 'attn:energy', 'attn:softmax', 'attn:ctx', 'barrier2']
             for k, loop in enumerate(('att', 'gen')):
                 act = raw[k][raw[k].sum(1) > 0]
                 if len(act):
