@@ -170,6 +170,10 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 
+// gate nonlinearities of the bf16 perf mode: ex2-based, ~1e-6 relative error (the operands of the products are bf16 anyway)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_exp(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+
 // Block-wide max / sum among the CT compute threads (named barrier 1); `scratch` holds >= 33 floats.
 __device__ __forceinline__ float cblock_max(float v, float* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -195,22 +199,26 @@ __device__ __forceinline__ float cblock_sum(float v, float* scratch) {
 }
 
 // Monotonic-counter grid barrier over ALL threads of every CTA.  Returns false if the watchdog fired.
+// Arrival is ONE release-reduction (cumulative: it orders the whole CTA's writes, which the preceding __syncthreads made
+// visible to thread 0); the wait polls with relaxed loads and issues a single acquire fence after the last one.
 __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag, int* s_ok) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += nblocks;
-        __threadfence();
         proxy_fence_global();          // the bf16 operand rows written above are read by other CTAs through TMA (async proxy)
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         int ok = 1;
         const long long t0 = clock64();
         unsigned polls = 0;
-        while (ld_acquire(counter) < target) {          // nothing but the counter load in the polling loop: its round trip is the barrier latency
+        for (;;) {                      // nothing but the counter load in the polling loop: its round trip is the barrier latency
+            unsigned v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
             if ((++polls & 255u) == 0 && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag))) {
                 ok = 0; *abort_flag = 1; break;
             }
         }
-        __threadfence();
+        asm volatile("fence.acquire.gpu;" ::: "memory");
         *s_ok = ok;
     }
     __syncthreads();
@@ -435,11 +443,11 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     const float zf = pre[e2][1] + s_sum[bl * (ROWS + 1) + UNITS + uu];
                     const float zg = pre[e2][2] + s_sum[bl * (ROWS + 1) + 2 * UNITS + uu];
                     const float zo = pre[e2][3] + s_sum[bl * (ROWS + 1) + 3 * UNITS + uu];
-                    const float gi = sigmoidf_acc(zi), gf = sigmoidf_acc(zf), gg = tanhf(zg), go = sigmoidf_acc(zo);
+                    const float gi = sigmoid_fast(zi), gf = sigmoid_fast(zf), gg = tanh_exp(zg), go = sigmoid_fast(zo);
                     const size_t bu = (size_t)b * D + u;
                     const float cp = pre[e2][4];
                     float cn = gf * cp + gi * gg;
-                    float hn = go * tanhf(cn);
+                    float hn = go * tanh_exp(cn);
                     p.gates[g0] = gi; p.gates[g0 + D] = gf; p.gates[g0 + 2 * D] = gg; p.gates[g0 + 3 * D] = go;
                     if (p.kind == B200TTS_CELL_ZONEOUT) {
                         const float hp = pre[e2][5];
@@ -542,29 +550,37 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                 constexpr int KTMAX = 12;                  // k-tiles (16 positions) per register batch of the context product
                 const int mt_lo = hf * ((p.M16 + 1) / 2), mt_hi = min(p.M16, mt_lo + (p.M16 + 1) / 2);
                 uint4 nraw[2];
-                if (warp < 2 * mtiles) {
-                    const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + (warp >> 1)) * 32 + lane) * 64) + hf * 4 + (warp & 1) * 2;
-                    nraw[0] = __ldg(mf); nraw[1] = __ldg(mf + 1);
-                }
                 uint4 av[KTMAX];
-                if (mt_lo + warp < mt_hi) {
-                    const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt_lo + warp) * p.MT) * 32 + lane;
-#pragma unroll
-                    for (int j = 0; j < KTMAX; ++j)
-                        if (j < ktiles) av[j] = __ldg(fr + (size_t)j * 32);
-                }
                 {   // q[a] = sum over the RB per-CTA partial projections: thread = (4 attention dims, one sixteenth of the row blocks)
                     const int a4 = tid & 15, sl = tid >> 4;
                     const int per = (p.RB + 15) / 16, r0 = sl * per, r1 = min(p.RB, r0 + per);
+                    float4 qv[4];                 // first the loads the critical path waits for ...
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        qv[j] = (r0 + j < r1) ? __ldcg(reinterpret_cast<const float4*>(p.qpart + ((size_t)(r0 + j) * B + b) * A + hf * AH) + a4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // ... then (the load-return path is in order) the fragments that do not depend on this step's state: the memory projection
+                    // of this warp's first energy job and the memory tile of its first context product
+                    if (warp < 2 * mtiles) {
+                        const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + (warp >> 1)) * 32 + lane) * 64) + hf * 4 + (warp & 1) * 2;
+                        nraw[0] = __ldg(mf); nraw[1] = __ldg(mf + 1);
+                    }
+                    if (mt_lo + warp < mt_hi) {
+                        const uint4* fr = p.memFf + (((size_t)b * p.M16 + mt_lo + warp) * p.MT) * 32 + lane;
+#pragma unroll
+                        for (int j = 0; j < KTMAX; ++j)
+                            if (j < ktiles) av[j] = __ldg(fr + (size_t)j * 32);
+                    }
                     float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int r = r0; r < r1; r += 4) {
-                        float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { qs.x += qv[j].x; qs.y += qv[j].y; qs.z += qv[j].z; qs.w += qv[j].w; }
+                    for (int r = r0 + 4; r < r1; r += 4) {          // more than 64 row blocks: further rounds
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            v[j] = (r + j < r1) ? __ldcg(reinterpret_cast<const float4*>(p.qpart + ((size_t)(r + j) * B + b) * A + hf * AH) + a4)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { qs.x += v[j].x; qs.y += v[j].y; qs.z += v[j].z; qs.w += v[j].w; }
+                            if (r + j < r1) {
+                                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(p.qpart + ((size_t)(r + j) * B + b) * A + hf * AH) + a4);
+                                qs.x += v4.x; qs.y += v4.y; qs.z += v4.z; qs.w += v4.w;
+                            }
                     }
                     *reinterpret_cast<float4*>(cred + sl * AH + a4 * 4) = qs;
                     // cumulative weights -> (hi, lo) bf16 pairs: Ph[x] = (c[x], c[x+1]) with c[j] = cum[j - half]
