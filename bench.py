@@ -280,15 +280,24 @@ def run_b200(a):
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             step(resident)
             torch.cuda.synchronize()
-        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
-        tot = sum(e.device_time_total for e in rows)
+        import collections
+        import tempfile
+        trace = os.path.join(tempfile.gettempdir(), f'b200tts_trace_{os.getpid()}.json')
+        prof.export_chrome_trace(trace)
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for ev in json.load(open(trace)).get('traceEvents', []):
+            if ev.get('cat') in ('kernel', 'gpu_memcpy', 'gpu_memset') and 'dur' in ev:
+                name = ev['name'].replace('b200tts::(anonymous namespace)::', '').replace('void ', '').split('(')[0][:56]
+                key = (name, str(ev.get('args', {}).get('grid', '')))
+                agg[key][0] += 1
+                agg[key][1] += float(ev['dur'])
+        os.remove(trace)
+        tot = sum(v[1] for v in agg.values())
         with open(a.breakdown, 'w') as f:
-            f.write(f'{"kernel":80s} {"n":>6s} {"total_us":>12s} {"avg_us":>10s} {"share":>7s}\n')
-            for e in rows:
-                f.write(f'{e.key[:80]:80s} {e.count:6d} {e.device_time_total:12.1f} {e.device_time_total / max(e.count, 1):10.2f} '
-                        f'{100 * e.device_time_total / max(tot, 1e-9):6.1f}%\n')
-            f.write(f'{"TOTAL":80s} {sum(e.count for e in rows):6d} {tot:12.1f}\n')
-
+            f.write(f'{"kernel":58s} {"grid":18s} {"n":>5s} {"total_us":>11s} {"avg_us":>10s} {"share":>7s}\n')
+            for (name, grid), v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write(f'{name:58s} {grid:18s} {v[0]:5d} {v[1]:11.1f} {v[1] / v[0]:10.2f} {100 * v[1] / max(tot, 1e-9):6.1f}%\n')
+            f.write(f'{"TOTAL":58s} {"":18s} {sum(v[0] for v in agg.values()):5d} {tot:11.1f}\n')
     if rank == 0:
         frames = world * B * T * a.steps
         value = frames / (ms * 1e-3)

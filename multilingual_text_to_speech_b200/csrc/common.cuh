@@ -104,6 +104,10 @@ struct GemmDesc {
     int splitk = 1;
     float* partial = nullptr;     // required when splitk > 1
     int keep_partials = 0;        // 1: leave the reduction to the consumer kernel (C untouched)
+    // optional: op(A) already available as bf16, K contiguous, row stride lda16 elements (16-byte aligned rows): the tcgen05 path
+    // reads it through TMA directly (no packing pass); A / lda are then ignored by that path
+    const void* A16 = nullptr;
+    int lda16 = 0;
 };
 
 int gemm_f32(const GemmDesc& d, cudaStream_t stream);

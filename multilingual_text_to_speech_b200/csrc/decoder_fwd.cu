@@ -6,6 +6,8 @@
 
 namespace b200tts {
 
+int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled);      // gemm_tc.cu
+
 // =============================================================================================
 // small utility kernels
 // =============================================================================================
@@ -533,7 +535,22 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
         const bool tc = tc_persist_supported(s);         // TMA + tcgen05 + TMEM loops (decoder_persist_tc.cu) when D % 64 == 0
         B200_TRY(persist_att_prep(s, w, in, l, ws, pws, st));
         B200_TRY(tc ? tc_persist_att_loop(s, w, in, l, ws, pws, out.alignments, st) : persist_att_loop(s, w, in, l, ws, pws, out.alignments, st));
-        B200_TRY(gen_input_proj(c, 0, T));
+        if (tc) {
+            // the attention loop left [h_att | ctx] of every step as bf16 operand rows in exactly the column order of W_ih of the
+            // generator LSTM: ONE product, its A operand read by TMA straight from those rows (no packing, no second accumulate pass)
+            const TcPersistGeom g = tc_persist_geom(s);
+            const PersistLayout pl = persist_layout(s);
+            GemmDesc d;
+            d.A = c.at(l.ai); d.lda = MD;           // (unused by the tcgen05 path)
+            d.A16 = pws + pl.aib + (size_t)B * g.Kp_att * 2; d.lda16 = g.Kp_att;      // operand row 1 (bf16)
+            d.B = w.gen_w_ih; d.ldb = D + M; d.transB = 1; d.C = c.at(l.gg); d.ldc = 4 * D; d.bias = c.at(l.bsum_gen);
+            d.M = T * B; d.N = 4 * D; d.K = MD; d.beta = 0.f;
+            bool handled = false;
+            B200_TRY(gemm_tc_try(d, st, &handled));
+            if (!handled) B200_TRY(gen_input_proj(c, 0, T));
+        } else {
+            B200_TRY(gen_input_proj(c, 0, T));
+        }
         B200_TRY(tc ? tc_persist_gen_loop(s, w, in, l, ws, pws, st) : persist_gen_loop(s, w, in, l, ws, pws, st));
         B200_TRY(frame_proj(c, 0, T));
     } else if (!sequential) {

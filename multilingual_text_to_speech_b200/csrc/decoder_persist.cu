@@ -95,17 +95,21 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
     __syncthreads();
     if (threadIdx.x == 0) {
         target += nblocks;
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // arrival = ONE release-reduction (cumulative over the CTA's writes, which the __syncthreads above made visible to thread 0);
+        // the wait polls with relaxed loads and issues a single acquire fence after the last one
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         int ok = 1;
         const long long t0 = clock64();
         unsigned polls = 0;
-        while (ld_acquire(counter) < target) {          // nothing but the counter load in the polling loop: its round trip is the barrier latency
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
             if ((++polls & 255u) == 0 && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag))) {
                 ok = 0; *abort_flag = 1; break;
             }
         }
-        __threadfence();
+        asm volatile("fence.acquire.gpu;" ::: "memory");
         s_ok = ok;
     }
     __syncthreads();

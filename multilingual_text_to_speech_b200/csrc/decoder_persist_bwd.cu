@@ -66,17 +66,21 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
     __syncthreads();
     if (threadIdx.x == 0) {
         target += nblocks;
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // arrival = ONE release-reduction (cumulative over the CTA's writes, which the __syncthreads above made visible to thread 0);
+        // the wait polls with relaxed loads and issues a single acquire fence after the last one
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         int ok = 1;
         const long long t0 = clock64();
         unsigned polls = 0;
-        while (ld_acquire(counter) < target) {          // nothing but the counter load in the polling loop: its round trip is the barrier latency
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
             if ((++polls & 255u) == 0 && (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int*>(abort_flag))) {
                 ok = 0; *abort_flag = 1; break;
             }
         }
-        __threadfence();
+        asm volatile("fence.acquire.gpu;" ::: "memory");
         s_ok = ok;
     }
     __syncthreads();
@@ -544,45 +548,110 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
 
         // =========================== PB: attention-LSTM cell backward ===========================
         if (owner) {
+            // operands of this thread's (b, u) pairs first (DRAM latency hides behind the query-gradient product below)
+            float gi_[MAXE], gf_[MAXE], gg_[MAXE], go_[MAXE], cp_[MAXE], dhs_[MAXE], rec_[MAXE];
+            uint8_t mh_[MAXE], mc_[MAXE];
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) {
+                const int idx = tid + e * PT;
+                gi_[e] = gf_[e] = gg_[e] = go_[e] = cp_[e] = dhs_[e] = rec_[e] = 0.f; mh_[e] = 1; mc_[e] = 1;
+                if (idx < B * UOWN) {
+                    const int b = idx / UOWN, uu = idx % UOWN, u = uo0 + uu;
+                    const size_t bu = (size_t)b * D + u, g0 = ((size_t)i * B + b) * 4 * D + u, mi = (size_t)i * B * D + bu;
+                    gi_[e] = p.gates[g0]; gf_[e] = p.gates[g0 + D]; gg_[e] = p.gates[g0 + 2 * D]; go_[e] = p.gates[g0 + 3 * D];
+                    cp_[e] = p.cstate[mi];
+                    dhs_[e] = p.dh_static[mi];
+                    if (p.training && p.mask_h) mh_[e] = p.mask_h[mi];
+                    if (p.training && p.mask_c) mc_[e] = p.mask_c[mi];
+                    if (!last) {
+                        float r8[KBA];
+#pragma unroll
+                        for (int k2 = 0; k2 < KBA; ++k2) r8[k2] = __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
+                        float rs = 0.f;
+#pragma unroll
+                        for (int k2 = 0; k2 < KBA; ++k2) rs += r8[k2];
+                        rec_[e] = rs;
+                    }
+                }
+            }
+            // d h (query part) = dq[b, :] . Wq[:, u] on the tensor cores: A = dq rows staged in shared memory (bf16 hi + lo),
+            // B = this CTA's 8 columns of Wq (bf16 hi + lo, register resident); hi.hi + lo.hi + hi.lo = fp32-equivalent
+            // (As is idle between PA and P2: [B][A] query gradients, row b rotated by 8 (b & 7) floats against bank conflicts, then [64][8] products)
+            float* s_dq = reinterpret_cast<float*>(As);
+            float* s_dhq = s_dq + (size_t)B * A;
+            {
+                const int nf4 = A / 4;
+                for (int idx = tid; idx < B * nf4; idx += PT) {
+                    const int b = idx / nf4, c4 = idx % nf4;
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(p.dq + ((size_t)i * B + b) * A) + c4);
+                    *reinterpret_cast<float4*>(s_dq + b * A + ((c4 * 4 + 8 * (b & 7)) & (A - 1))) = v;
+                }
+                __syncthreads();
+                const int g = lane >> 2, tq = lane & 3, mt = warp & 3, kh = warp >> 2;      // warp = (16-utterance tile, half of the A range)
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const int ksteps = A / 32;                                // k-steps of 16 per half
+#pragma unroll 4
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int a0 = (kh * ksteps + ks) * 16;
+                    uint32_t ah[4], al[4];
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; ++r4) {
+                        const int br = mt * 16 + g + 8 * (r4 & 1);       // rows >= B read stale shared memory: their products are never used
+                        const float2 x = *reinterpret_cast<const float2*>(s_dq + br * A + ((a0 + 2 * tq + 8 * (r4 >> 1) + 8 * (br & 7)) & (A - 1)));
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y);
+                        __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
+                        ah[r4] = *reinterpret_cast<uint32_t*>(&hp);
+                        al[r4] = pack2(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
+                    }
+                    uint32_t bh[2], bl[2];
+#pragma unroll
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        const int a = a0 + 2 * tq + 8 * r2;
+                        const float x0 = wq8[a * (UOWN + 1) + g], x1 = wq8[(a + 1) * (UOWN + 1) + g];
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                        __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
+                        bh[r2] = *reinterpret_cast<uint32_t*>(&hp);
+                        bl[r2] = pack2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                    }
+                    mma_bf16(acc, ah, bh[0], bh[1]);
+                    mma_bf16(acc, al, bh[0], bh[1]);
+                    mma_bf16(acc, ah, bl[0], bl[1]);
+                }
+                __syncthreads();                                       // every warp is done reading s_dq (s_dhq may overlap its unused tail rows)
+                float* d0 = s_dhq + (mt * 16 + g) * UOWN + 2 * tq;
+                float* d1 = s_dhq + (mt * 16 + g + 8) * UOWN + 2 * tq;
+                if (kh == 0) { d0[0] = acc[0]; d0[1] = acc[1]; d1[0] = acc[2]; d1[1] = acc[3]; }
+                __syncthreads();
+                if (kh == 1) { d0[0] += acc[0]; d0[1] += acc[1]; d1[0] += acc[2]; d1[1] += acc[3]; }
+                __syncthreads();
+            }
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
                 const int idx = tid + e * PT;
                 if (idx < B * UOWN) {
                     const int b = idx / UOWN, uu = idx % UOWN, u = uo0 + uu;
                     const size_t bu = (size_t)b * D + u, g0 = ((size_t)i * B + b) * 4 * D + u;
-                    float dh = p.dh_static[(size_t)i * B * D + bu];
-                    const float* dqr = p.dq + ((size_t)i * B + b) * A;
-                    float dhq = 0.f;
-#pragma unroll 8
-                    for (int a = 0; a < A; a += 4) {
-                        const float4 d4 = __ldcg(reinterpret_cast<const float4*>(dqr + a));
-                        dhq = fmaf(d4.x, wq8[a * (UOWN + 1) + uu], dhq); dhq = fmaf(d4.y, wq8[(a + 1) * (UOWN + 1) + uu], dhq);
-                        dhq = fmaf(d4.z, wq8[(a + 2) * (UOWN + 1) + uu], dhq); dhq = fmaf(d4.w, wq8[(a + 3) * (UOWN + 1) + uu], dhq);
-                    }
-                    dh += dhq;
+                    float dh = dhs_[e] + s_dhq[b * UOWN + uu];
                     float dc_in = 0.f;
                     if (!last) {
-                        float rec = 0.f;
-                        for (int k2 = 0; k2 < KBA; ++k2) rec += __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
-                        dh += rec + dhz_reg[e];
+                        dh += rec_[e] + dhz_reg[e];
                         dc_in = dc_reg[e];
                     }
-                    const float gi = p.gates[g0], gf = p.gates[g0 + D], gg = p.gates[g0 + 2 * D], go = p.gates[g0 + 3 * D];
-                    const float cp = p.cstate[(size_t)i * B * D + bu];
+                    const float gi = gi_[e], gf = gf_[e], gg = gg_[e], go = go_[e];
+                    const float cp = cp_[e];
                     const float tc = tanhf(gf * cp + gi * gg);
-                    const size_t mi = (size_t)i * B * D + bu;
                     float dhn, dcn, dc_prev_direct = 0.f, dh_prev_direct = 0.f;
                     if (p.kind == B200TTS_CELL_ZONEOUT) {
                         float kh, kc;
                         if (p.training) {
-                            kh = (1.f - p.rate_h) * (p.mask_h ? (float)p.mask_h[mi] * inv_h : 1.f);
-                            kc = (1.f - p.rate_c) * (p.mask_c ? (float)p.mask_c[mi] * inv_c : 1.f);
+                            kh = (1.f - p.rate_h) * (p.mask_h ? (float)mh_[e] * inv_h : 1.f);
+                            kc = (1.f - p.rate_c) * (p.mask_c ? (float)mc_[e] * inv_c : 1.f);
                         } else { kh = 1.f - p.rate_h; kc = 1.f - p.rate_c; }
                         dhn = dh * kh; dh_prev_direct = dh - dhn;
                         dcn = dc_in * kc + dhn * go * (1.f - tc * tc);
                         dc_prev_direct = dc_in - dc_in * kc;
                     } else {
-                        dhn = (p.training && p.mask_h) ? dh * (float)p.mask_h[mi] * inv_h : dh;
+                        dhn = (p.training && p.mask_h) ? dh * (float)mh_[e] * inv_h : dh;
                         dcn = dc_in + dhn * go * (1.f - tc * tc);
                     }
                     const float di = dcn * gg * gi * (1.f - gi), df = dcn * cp * gf * (1.f - gf);
@@ -593,6 +662,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                     db[2 * D] = __float2bfloat16_rn(dg); db[3 * D] = __float2bfloat16_rn(dO);
                     dc_reg[e] = dcn * gf + dc_prev_direct;
                     dhz_reg[e] = dh_prev_direct;
+                    (void)bu;
                 }
             }
         }
@@ -901,6 +971,8 @@ bool persist_att_bwd_supported(const b200tts_decoder_shape& s) {
     if (s.A != 128 || s.K > 32 || s.B > 2 * BT || s.B * 8 > 3 * PT || s.D / 8 > KBA * NBA * ((s.B + BT - 1) / BT)) return false;
     const int UK = s.D / KBA, UN = (cdiv(s.M + s.D, NBA) + 15) / 16 * 16;
     const int MT = (s.L + 15) / 16, L16 = MT * 16;
+    // the cell-backward phase stages the query gradients [B][A] fp32 + [64][8] products in the (then idle) activation tile
+    if ((size_t)s.B * s.A * 4 + 64 * 8 * 4 > (size_t)BT * (4 * UK + 8) * 2) return false;
     const size_t fixed = ((size_t)4 * UK * (UN + 8) + (size_t)BT * (4 * UK + 8)) * 2 + (size_t)s.A * 40 * 2 + (size_t)32 * (s.A + 8) * 2 +
                          (size_t)(L16 + 32) * 4 + (size_t)s.A * 9 * 4;
     return fixed <= 227 * 1024 && att_bwd_dqp_mode(s) >= 0;

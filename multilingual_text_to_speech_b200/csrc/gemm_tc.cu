@@ -327,7 +327,8 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     if ((long long)d.M * d.N * d.K * d.batch < (1ll << 24)) return B200TTS_OK;
     const int Kp = (d.K + 7) / 8 * 8;
     const int abatch = d.a_batch_mod > 0 ? d.a_batch_mod : d.batch;
-    const size_t a_bytes = ((size_t)abatch * d.M * Kp * 2 + 1023) / 1024 * 1024;
+    const bool a_ready = d.A16 != nullptr && d.batch == 1 && (d.lda16 % 8) == 0 && (reinterpret_cast<uintptr_t>(d.A16) & 15) == 0;
+    const size_t a_bytes = a_ready ? 0 : ((size_t)abatch * d.M * Kp * 2 + 1023) / 1024 * 1024;
     const size_t b_bytes = ((size_t)d.batch * d.N * Kp * 2 + 1023) / 1024 * 1024;
     if (a_bytes + b_bytes > g_scratch.bytes) return B200TTS_OK;
     if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
@@ -346,11 +347,12 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
         B200_LAUNCH_CHECK();
         return B200TTS_OK;
     };
-    B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch));
+    if (!a_ready) B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch));
     B200_TRY(pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch));
 
     CUtensorMap tmA, tmB;
-    B200_TRY(make_map(&tmA, pa, d.M, d.K, Kp, abatch, TBM));
+    if (a_ready) B200_TRY(make_map(&tmA, static_cast<const __nv_bfloat16*>(d.A16), d.M, d.K, d.lda16, 1, TBM));
+    else B200_TRY(make_map(&tmA, pa, d.M, d.K, Kp, abatch, TBM));
     B200_TRY(make_map(&tmB, pb, d.N, d.K, Kp, d.batch, TBN));
     TcArgs a;
     a.C = d.C; a.bias = d.bias; a.M = d.M; a.N = d.N; a.K = d.K; a.ldc = d.ldc; a.alpha = d.alpha; a.beta = d.beta;
