@@ -87,6 +87,8 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
     return s_ok != 0;
 }
 
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 #define BPROF_DECL long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
 #define BPROF_MARK(slot)                                                                                         \
     do {                                                                                                         \
@@ -358,6 +360,16 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
         // =========================== PA: attention backward of utterance `cta` ===========================
         if (cta < B) {
             const int b = cta, half = (p.KC - 1) / 2;
+            if (i > 0) {       // DRAM -> L2 one step ahead: the rows of step i-1 this phase starts with (alignment, query, cumulative weights, d ctx)
+                const size_t r1 = (size_t)(i - 1) * B + b;
+                const char* rows[5] = {reinterpret_cast<const char*>(p.align + (size_t)b * p.align_bstride + (size_t)(i - 1) * L),
+                                       reinterpret_cast<const char*>(p.q + r1 * A), reinterpret_cast<const char*>(p.cum + r1 * L),
+                                       reinterpret_cast<const char*>(p.dctx_static + r1 * M),
+                                       p.dalign ? reinterpret_cast<const char*>(p.dalign + (size_t)b * p.dalign_bstride + (size_t)(i - 1) * L) : nullptr};
+                const int bytes[5] = {L * 4, A * 4, L * 4, M * 4, L * 4};
+                const int which = tid >> 4, line = tid & 15;           // up to 16 lines of 128 B per row
+                if (which < 5 && rows[which] && line * 128 < bytes[which] + 127) l2_prefetch(rows[which] + line * 128);
+            }
             int len = p.lengths[b];
             len = len < 0 ? 0 : (len > L ? L : len);
             const int mtiles = (len + 15) / 16;
@@ -662,7 +674,13 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                     db[2 * D] = __float2bfloat16_rn(dg); db[3 * D] = __float2bfloat16_rn(dO);
                     dc_reg[e] = dcn * gf + dc_prev_direct;
                     dhz_reg[e] = dh_prev_direct;
-                    (void)bu;
+                    if (i > 0 && (uu & 7) == 0) {      // DRAM -> L2 one step ahead (8 units x 4 B = one 32-byte sector per row)
+                        const size_t g1 = g0 - (size_t)B * 4 * D, m1 = (size_t)(i - 1) * B * D + bu;
+                        l2_prefetch(p.gates + g1); l2_prefetch(p.gates + g1 + D); l2_prefetch(p.gates + g1 + 2 * D); l2_prefetch(p.gates + g1 + 3 * D);
+                        l2_prefetch(p.cstate + m1); l2_prefetch(p.dh_static + m1);
+                        if (p.training && p.mask_h) l2_prefetch(p.mask_h + m1);
+                        if (p.training && p.mask_c) l2_prefetch(p.mask_c + m1);
+                    }
                 }
             }
         }
