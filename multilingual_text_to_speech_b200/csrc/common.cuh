@@ -108,6 +108,10 @@ struct GemmDesc {
     // reads it through TMA directly (no packing pass); A / lda are then ignored by that path
     const void* A16 = nullptr;
     int lda16 = 0;
+    // optional two-level K (tcgen05 path only; needs !transA && transB): K = kouter * kin, element (row, q * kin + l) of op(A) lives at
+    // A[q * kosA + row * lda + l] (op(B) likewise with kosB): sums a product over `kouter` separately stored slabs in ONE GEMM
+    int kin = 0;
+    long long kosA = 0, kosB = 0;
 };
 
 int gemm_f32(const GemmDesc& d, cudaStream_t stream);

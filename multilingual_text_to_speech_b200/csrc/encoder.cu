@@ -8,6 +8,8 @@
 
 namespace b200tts {
 
+int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled);      // gemm_tc.cu
+
 namespace {
 
 inline int grid_for(size_t n) {
@@ -326,8 +328,19 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
     }
     const int R = s.Cin * s.k;
     if (dweight) {
-        // dW[g] (+)= sum_rows dconv[row, g] . col[row, g]^T    (one batched GEMM per sample row, accumulating)
-        for (int q = 0; q < s.NB; ++q) {
+        // dW[g] (+)= sum_rows dconv[row, g] . col[row, g]^T
+        bool fused = false;
+        if (precision_mode() != 0 && s.NB > 1) {
+            // bf16 perf mode: ONE batched tcgen05 GEMM whose K runs over (sample row, position): K = NB * L (two-level K of the packer)
+            GemmDesc g;
+            g.A = dz; g.lda = s.L; g.transA = 0; g.strideA = (long long)s.Cout * s.L; g.kosA = (long long)d.Ct * s.L;
+            g.B = colr; g.ldb = s.L; g.transB = 1; g.strideB = (long long)R * s.L; g.kosB = (long long)s.G * R * s.L;
+            g.C = dweight; g.ldc = R; g.strideC = (long long)s.Cout * R; g.beta = 1.f;
+            g.M = s.Cout; g.N = R; g.K = s.NB * s.L; g.kin = s.L; g.batch = s.G;
+            B200_TRY(gemm_tc_try(g, st, &fused));
+        }
+        // otherwise one batched GEMM per sample row, accumulating
+        for (int q = 0; q < s.NB && !fused; ++q) {
             GemmDesc g;
             g.A = dz + (size_t)q * d.Ct * s.L; g.lda = s.L; g.transA = 0; g.strideA = (long long)s.Cout * s.L;
             g.B = colr + (size_t)q * s.G * R * s.L; g.ldb = s.L; g.transB = 1; g.strideB = (long long)R * s.L;

@@ -224,14 +224,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // operand packing: fp32 (either orientation) -> bf16 [batch][rows][Kp], K contiguous, Kp % 8 == 0
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kcontig_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int ld, long long bstride, int rows,
-                                    int K, int Kp) {
+                                    int K, int Kp, int kin, long long kos) {
     const size_t per = (size_t)rows * Kp;
     const float* s = src + (size_t)blockIdx.y * bstride;
     __nv_bfloat16* d = dst + (size_t)blockIdx.y * per;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < per; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t r = idx / Kp;
         const int k = idx % Kp;
-        d[idx] = __float2bfloat16_rn(k < K ? s[r * ld + k] : 0.f);
+        float v = 0.f;
+        if (k < K) v = kin > 0 ? s[(size_t)(k / kin) * kos + r * ld + (k % kin)] : s[r * ld + k];      // kin > 0: two-level K (slab q = k / kin)
+        d[idx] = __float2bfloat16_rn(v);
     }
 }
 // source element (r, k) at src[k*ld + r]: 32 x 32 tile transpose through shared memory
@@ -323,6 +325,7 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     *handled = false;
     if (!g_tc_enabled || g_scratch.ptr == nullptr) return B200TTS_OK;
     if (d.splitk != 1 || d.keep_partials) return B200TTS_OK;
+    if (d.kin > 0 && (d.transA || !d.transB || d.K % d.kin != 0 || d.A16)) return B200TTS_OK;      // two-level K: K-contiguous operands only
     if (d.M < 64 || d.N < 64 || d.K < 32) return B200TTS_OK;                 // tiny problems: not worth packing
     if ((long long)d.M * d.N * d.K * d.batch < (1ll << 24)) return B200TTS_OK;
     const int Kp = (d.K + 7) / 8 * 8;
@@ -335,11 +338,11 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
     __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
 
-    auto pack = [&](__nv_bfloat16* dst, const float* src, int ld, long long bstride, int rows, bool kcontig, int nb) -> int {
+    auto pack = [&](__nv_bfloat16* dst, const float* src, int ld, long long bstride, int rows, bool kcontig, int nb, long long kos) -> int {
         if (kcontig) {
             size_t per = (size_t)rows * Kp;
             int gx = (int)((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
-            pack_kcontig_kernel<<<dim3(gx, nb), 256, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp);
+            pack_kcontig_kernel<<<dim3(gx, nb), 256, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp, d.kin, kos);
         } else {
             dim3 grid(cdiv(rows, 32), cdiv(Kp, 32), nb), block(32, 8);
             pack_transpose_kernel<<<grid, block, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp);
@@ -347,8 +350,8 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
         B200_LAUNCH_CHECK();
         return B200TTS_OK;
     };
-    if (!a_ready) B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch));
-    B200_TRY(pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch));
+    if (!a_ready) B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch, d.kosA));
+    B200_TRY(pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch, d.kosB));
 
     CUtensorMap tmA, tmB;
     if (a_ready) B200_TRY(make_map(&tmA, static_cast<const __nv_bfloat16*>(d.A16), d.M, d.K, d.lda16, 1, TBM));
