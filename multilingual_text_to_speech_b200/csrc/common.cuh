@@ -114,6 +114,10 @@ struct GemmDesc {
     long long kosA = 0, kosB = 0;
 };
 
+// pack cache of the tcgen05 GEMM (gemm_tc.cu): operands packed inside a begin / end scope are reused by later products of the scope
+void tc_pack_cache_begin();
+void tc_pack_cache_end();
+
 int gemm_f32(const GemmDesc& d, cudaStream_t stream);
 int gemm_bf16(const GemmDesc& d, cudaStream_t stream);
 // Precision mode of the library (b200tts_set_precision): 0 = fp32-exact (parity mode), 1 = bf16 tensor-core operands.

@@ -568,6 +568,11 @@ BwdLayout bwd_layout(const b200tts_decoder_shape& s) {
 }
 
 // C (+)= op(A) . op(B), split-K chosen from the tile count; partial scratch shared by all calls
+struct PackScope {
+    PackScope() { tc_pack_cache_begin(); }
+    ~PackScope() { tc_pack_cache_end(); }
+};
+
 int wgemm(cudaStream_t st, const BwdLayout& l, float* ws, int transA, int transB, int M, int N, int K, const float* A, int lda,
           const float* B, int ldb, float* C, int ldc, float beta, int batch = 1, long long sA = 0, long long sB = 0,
           long long sC = 0) {
@@ -655,14 +660,18 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
             }
         }
     }
-    // time-batched generator gradients
-    B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, F(fl.hg), D, dw.gen_w_hh, D, 1.f));
-    B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, ai1 + M, MD, dw.gen_w_ih, D + M, 1.f));
-    B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dgg), 4 * D, ai1, MD, dw.gen_w_ih + D, D + M, 1.f));
-    B200_TRY(colsum_add(dw.gen_b_ih, dw.gen_b_hh, W(l.dgg), TB, 4 * D, 4 * D, W(l.gpart), st));
-    // d h_att (static part) and d ctx (generator-input part, accumulated onto the projection part)
-    B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, D, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih, D + M, W(l.dhas), D, 0.f));
-    B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, M, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih + D, D + M, W(l.dctxs), M, 1.f));
+    {
+        // time-batched generator gradients.  The gate gradients are final now: their packed (transposed / K-contiguous) bf16 copies are
+        // made once and shared by the three weight-gradient and the two input-gradient products (pack cache of the tcgen05 GEMM).
+        PackScope pack_scope;
+        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, F(fl.hg), D, dw.gen_w_hh, D, 1.f));
+        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, ai1 + M, MD, dw.gen_w_ih, D + M, 1.f));
+        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dgg), 4 * D, ai1, MD, dw.gen_w_ih + D, D + M, 1.f));
+        B200_TRY(colsum_add(dw.gen_b_ih, dw.gen_b_hh, W(l.dgg), TB, 4 * D, 4 * D, W(l.gpart), st));
+        // d h_att (static part) and d ctx (generator-input part, accumulated onto the projection part)
+        B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, D, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih, D + M, W(l.dhas), D, 0.f));
+        B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, M, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih + D, D + M, W(l.dctxs), M, 1.f));
+    }
 
     // ---- 3. attention LSTM + attention reverse loop ----
     const bool persist_att = precision_mode() == B200TTS_PRECISION_BF16 && s.training && persist_supported(s) && persist_att_bwd_supported(s);
@@ -715,9 +724,12 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     }
 
     // ---- 4. time-batched gradients of the attention LSTM, attention parameters, prenet, memory ----
-    B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, P, (int)TB, W(l.dga), 4 * D, F(fl.p1), P, dw.att_w_ih, P + M, 1.f));
-    B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dga), 4 * D, ai, MD, dw.att_w_ih + P, P + M, 1.f));
-    B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dga), 4 * D, ai + M, MD, dw.att_w_hh, D, 1.f));
+    {
+        PackScope pack_scope;       // one transposed bf16 copy of the attention-LSTM gate gradients for the three weight-gradient products
+        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, P, (int)TB, W(l.dga), 4 * D, F(fl.p1), P, dw.att_w_ih, P + M, 1.f));
+        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dga), 4 * D, ai, MD, dw.att_w_ih + P, P + M, 1.f));
+        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dga), 4 * D, ai + M, MD, dw.att_w_hh, D, 1.f));
+    }
     {
         B200_TRY(colsum_add(dw.att_b_ih, dw.att_b_hh, W(l.dga), TB, 4 * D, 4 * D, W(l.gpart), st));
         B200_TRY(colsum_add(dw.attn_bias, nullptr, W(l.dq), TB, A, A, W(l.gpart), st));

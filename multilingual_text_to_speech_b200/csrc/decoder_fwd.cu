@@ -552,7 +552,32 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
             B200_TRY(gen_input_proj(c, 0, T));
         }
         B200_TRY(tc ? tc_persist_gen_loop(s, w, in, l, ws, pws, st) : persist_gen_loop(s, w, in, l, ws, pws, st));
-        B200_TRY(frame_proj(c, 0, T));
+        bool fp_done = false;
+        if (tc) {       // frame / stop projection straight from the bf16 operand rows of the two loops (h_gen, then ctx accumulated on top)
+            const TcPersistGeom g = tc_persist_geom(s);
+            const PersistLayout pl = persist_layout(s);
+            const int N1 = N + 1;
+            GemmDesc d;
+            d.A = c.at(l.hg) + BD; d.lda = D;
+            d.A16 = pws + pl.hgb + (size_t)B * g.Kp_gen * 2; d.lda16 = g.Kp_gen;
+            d.B = c.at(l.wfs); d.ldb = D + M; d.transB = 1; d.C = c.at(l.fs); d.ldc = N1; d.bias = c.at(l.bfs);
+            d.M = T * B; d.N = N1; d.K = D; d.beta = 0.f;
+            bool h1 = false, h2 = false;
+            B200_TRY(gemm_tc_try(d, st, &h1));
+            if (h1) {
+                GemmDesc e;
+                e.A = c.at(l.ai) + (size_t)B * MD; e.lda = MD;
+                e.A16 = pws + pl.aib + ((size_t)B * g.Kp_att + D) * 2; e.lda16 = g.Kp_att;
+                e.B = c.at(l.wfs) + D; e.ldb = D + M; e.transB = 1; e.C = c.at(l.fs); e.ldc = N1;
+                e.M = T * B; e.N = N1; e.K = M; e.beta = 1.f;
+                B200_TRY(gemm_tc_try(e, st, &h2));
+                if (!h2) {      // second half on the generic path
+                    B200_TRY(run_gemm(c.st, T * B, N1, M, c.at(l.ai) + (size_t)B * MD, MD, c.at(l.wfs) + D, D + M, true, c.at(l.fs), N1, nullptr, 1.f));
+                }
+                fp_done = true;
+            }
+        }
+        if (!fp_done) B200_TRY(frame_proj(c, 0, T));
     } else if (!sequential) {
         for (int i = 0; i < T; ++i) B200_TRY(att_step(c, i, out.alignments));
         B200_TRY(gen_input_proj(c, 0, T));

@@ -355,6 +355,8 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
     float* s_stage = reinterpret_cast<float*>(s_Pl);      // [L16]: d cum staging (Pl is dead by then)
     BPROF_DECL
 
+    int pa_len = 0;
+    if (cta < B) { const int l0 = p.lengths[cta]; pa_len = l0 < 0 ? 0 : (l0 > L ? L : l0); }
     for (int i = p.T - 1; i >= 0; --i) {
         const bool last = (i == p.T - 1);
         // =========================== PA: attention backward of utterance `cta` ===========================
@@ -370,8 +372,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                 const int which = tid >> 4, line = tid & 15;           // up to 16 lines of 128 B per row
                 if (which < 5 && rows[which] && line * 128 < bytes[which] + 127) l2_prefetch(rows[which] + line * 128);
             }
-            int len = p.lengths[b];
-            len = len < 0 ? 0 : (len > L ? L : len);
+            const int len = pa_len;                        // loaded once, before the loop
             const int mtiles = (len + 15) / 16;
             for (int m = tid; m < M; m += PT) {
                 float g = p.dctx_static[((size_t)i * B + b) * M + m];

@@ -407,6 +407,8 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     };
     if (compute) { prefetch_l2(0); prefetch(0, true); prefetch_l2(1); }
 
+    int att_len = 0;               // ATT: clamped text length of the utterance this CTA pair serves
+    if (ATT && (cta >> 1) < B) { const int l0 = p.lengths[cta >> 1]; att_len = l0 < 0 ? 0 : (l0 > p.L ? p.L : l0); }
     bool alive = true;
     for (int i = 0; i < p.T && alive; ++i) {
         // =================== ctx part of the gate product (the context of step i-1 is visible now) ===================
@@ -537,8 +539,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                 float* cred = red + 64;                    // [16][AH] query partials
                 uint32_t* Ph = reinterpret_cast<uint32_t*>(cred + 16 * AH);   // [L16 + 48] Toeplitz pair arrays (hi / lo bf16 split)
                 uint32_t* Pl = Ph + (L16 + 48);
-                int len = p.lengths[b];
-                len = len < 0 ? 0 : (len > L ? L : len);
+                const int len = att_len;                   // text length of this pair's utterance (loaded once, before the loop)
                 const int mtiles = (len + 15) / 16, ktiles = mtiles;
                 if (i == 0) {                              // one-time: constants and the initial cumulative weights into shared memory
                     for (int a2 = tid; a2 < AH; a2 += CT) { vv[a2] = p.v[hf * AH + a2]; bias_s[a2] = p.bias[hf * AH + a2]; }

@@ -292,6 +292,23 @@ int make_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int K, int K
 
 struct Scratch { unsigned char* ptr = nullptr; size_t bytes = 0; };
 Scratch g_scratch;
+
+// Pack cache: inside a begin / end scope (one backward pass over buffers that do not change) a packed operand is kept in the scratch
+// and reused by every later product that reads the same source view (e.g. the transposed gate gradients feed three weight-gradient
+// GEMMs).  Outside a scope every call packs into the start of the scratch.
+struct PackKey {
+    const void* src; int ld, rows, K, Kp, kcontig, nb, kin; long long bstride, kos;
+    bool operator==(const PackKey& o) const {
+        return src == o.src && ld == o.ld && rows == o.rows && K == o.K && Kp == o.Kp && kcontig == o.kcontig && nb == o.nb && kin == o.kin &&
+               bstride == o.bstride && kos == o.kos;
+    }
+};
+struct PackEntry { PackKey key; __nv_bfloat16* dst; };
+constexpr int MAX_CACHE = 32;
+PackEntry g_cache[MAX_CACHE];
+int g_ncache = 0;
+bool g_cache_on = false;
+size_t g_cache_off = 0;
 int g_tc_enabled = 1;
 
 }  // namespace
@@ -316,7 +333,9 @@ int tc_make_map3_bf16(void* map, const void* base, int d0, int d1, int d2, size_
     return B200TTS_OK;
 }
 
-void set_tc_scratch(void* ptr, size_t bytes) { g_scratch.ptr = static_cast<unsigned char*>(ptr); g_scratch.bytes = bytes; }
+void set_tc_scratch(void* ptr, size_t bytes) { g_scratch.ptr = static_cast<unsigned char*>(ptr); g_scratch.bytes = bytes; g_ncache = 0; g_cache_off = 0; }
+void tc_pack_cache_begin() { g_cache_on = true; g_ncache = 0; g_cache_off = 0; }
+void tc_pack_cache_end() { g_cache_on = false; g_ncache = 0; g_cache_off = 0; }
 void set_tc_enabled(int on) { g_tc_enabled = on; }
 int tc_enabled() { return g_tc_enabled; }
 
@@ -333,10 +352,31 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     const bool a_ready = d.A16 != nullptr && d.batch == 1 && (d.lda16 % 8) == 0 && (reinterpret_cast<uintptr_t>(d.A16) & 15) == 0;
     const size_t a_bytes = a_ready ? 0 : ((size_t)abatch * d.M * Kp * 2 + 1023) / 1024 * 1024;
     const size_t b_bytes = ((size_t)d.batch * d.N * Kp * 2 + 1023) / 1024 * 1024;
-    if (a_bytes + b_bytes > g_scratch.bytes) return B200TTS_OK;
     if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
-    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
-    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
+    const PackKey ka{d.A, d.lda, d.M, d.K, Kp, !d.transA, abatch, d.kin, d.strideA, d.kosA};
+    const PackKey kb{d.B, d.ldb, d.N, d.K, Kp, d.transB != 0, d.batch, d.kin, d.strideB, d.kosB};
+    auto cached = [&](const PackKey& k) -> __nv_bfloat16* {
+        if (!g_cache_on) return nullptr;
+        for (int e = 0; e < g_ncache; ++e)
+            if (g_cache[e].key == k) return g_cache[e].dst;
+        return nullptr;
+    };
+    __nv_bfloat16* pa = a_ready ? nullptr : cached(ka);
+    __nv_bfloat16* pb = cached(kb);
+    const bool pack_a = !a_ready && pa == nullptr, pack_b = pb == nullptr;
+    {   // place what has to be packed now: behind the cached operands (kept, when a scope is open and there is room for more)
+        size_t off = g_cache_on ? g_cache_off : 0;
+        const size_t need = (pack_a ? a_bytes : 0) + (pack_b ? b_bytes : 0);
+        if (off + need > g_scratch.bytes) return B200TTS_OK;
+        if (pack_a) { pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + off); off += a_bytes; }
+        if (pack_b) { pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + off); off += b_bytes; }
+        // keep them only if the largest operand of this backward pass would still fit behind (otherwise the region is reused as scratch)
+        if (g_cache_on && g_ncache + 2 <= MAX_CACHE && off + (g_scratch.bytes >> 2) <= g_scratch.bytes) {
+            if (pack_a) g_cache[g_ncache++] = PackEntry{ka, pa};
+            if (pack_b) g_cache[g_ncache++] = PackEntry{kb, pb};
+            g_cache_off = off;
+        }
+    }
 
     auto pack = [&](__nv_bfloat16* dst, const float* src, int ld, long long bstride, int rows, bool kcontig, int nb, long long kos) -> int {
         if (kcontig) {
@@ -350,8 +390,8 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
         B200_LAUNCH_CHECK();
         return B200TTS_OK;
     };
-    if (!a_ready) B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch, d.kosA));
-    B200_TRY(pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch, d.kosB));
+    if (pack_a) B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch, d.kosA));
+    if (pack_b) B200_TRY(pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch, d.kosB));
 
     CUtensorMap tmA, tmB;
     if (a_ready) B200_TRY(make_map(&tmA, static_cast<const __nv_bfloat16*>(d.A16), d.M, d.K, d.lda16, 1, TBM));
