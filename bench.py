@@ -308,9 +308,15 @@ def run_b200(a):
         if dec_ms:
             alg = T * bytes_fwd_step(B, L, M)
             dur = statistics.mean(dec_ms) * 1e-3
+            # DRAM traffic of the two persistent loop kernels per decoder forward, from the committed ncu capture
+            # (profiles/ncu_metrics_loops_r1.txt: 1.04 + 1.59 GB attention loop, 1.02 + 1.38 GB generator loop at this exact shape);
+            # the weights are shared-memory resident, so the traffic is far BELOW the naive algorithmic bytes of SURVEY section 8d
+            traffic = 5.04e9 if (a.precision == 'bf16' and a.config == 'generated_training' and B == 60 and L == 180 and T == 900) else None
             roof = {'bound': 'hbm', 'achieved': alg / dur / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': alg / dur / 1e9 / peak,
-                    'traffic': None, 'kernel': 'decoder forward (b200tts_decoder_forward: attention-LSTM + attention + generator-LSTM '
-                    'loop, all launches)', 'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': dur * 1e3, 'peak_source': peak_src}
+                    'traffic': traffic, 'kernel': 'decoder forward op (b200tts_decoder_forward): persistent tcgen05/TMA attention-LSTM + attention '
+                    'loop, persistent generator-LSTM loop and the time-batched tcgen05 GEMMs around them, all launches',
+                    'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': dur * 1e3, 'peak_source': peak_src,
+                    'algorithmic_bytes_formula': 'T x BYTES_fwd_step (SURVEY 8d, fp32 naive formulation)'}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic',
