@@ -636,7 +636,10 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     const bool zone = s.cell_kind == B200TTS_CELL_ZONEOUT;
     if (precision_mode() == B200TTS_PRECISION_BF16 && persist_bwd_supported(s)) {
         // bf16 perf mode: one cooperative weight-stationary kernel for the whole reverse recurrence
-        B200_TRY(persist_gen_bwd_loop(s, w, in, fl, fws, W(l.dhgd), W(l.dgg), reinterpret_cast<unsigned char*>(W(l.pextra)), st));
+        if (tc_persist_gen_bwd_supported(s))      // TMA + tcgen05 + TMEM variant (decoder_persist_bwd_tc.cu)
+            B200_TRY(tc_persist_gen_bwd_loop(s, w, in, fl, fws, W(l.dhgd), W(l.dgg), reinterpret_cast<unsigned char*>(W(l.pextra)), st));
+        else
+            B200_TRY(persist_gen_bwd_loop(s, w, in, fl, fws, W(l.dhgd), W(l.dgg), reinterpret_cast<unsigned char*>(W(l.pextra)), st));
     } else {
     for (int i = T - 1; i >= 0; --i) {
             CellBwdArgs ca{};

@@ -127,6 +127,10 @@ size_t persist_bwd_gen_extra_bytes(const b200tts_decoder_shape& s);
 int persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                          const DecoderLayout& fl, const float* fws, const float* dh_static, float* dgates, unsigned char* extra,
                          cudaStream_t st);
+bool tc_persist_gen_bwd_supported(const b200tts_decoder_shape& s);
+int tc_persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
+                            const DecoderLayout& fl, const float* fws, const float* dh_static, float* dgates, unsigned char* extra,
+                            cudaStream_t st);
 int persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                      const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st);
 

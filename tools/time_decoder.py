@@ -55,7 +55,7 @@ def main():
             torch.cuda.synchronize()
             if not a.fwd_only:
                 shp = F.PROFILE['last_shape']
-                bnames = [['cell', 'barrier1', 'mma', 'barrier2', '-', '-', '-', '-'],
+                bnames = [['cell', 'barrier1', 'tma+tcgen05', 'tmem+store', 'barrier2', '-', '-', '-'],
                           ['attn:dw/softmax', 'attn:mma+dcum', 'barrier1', 'cell', 'barrier2', 'mma', 'barrier3', '-']]
                 for which, loop in enumerate(('gen-bwd', 'att-bwd')):
                     boff = _lib.load().b200tts_debug_persist_bwd_profile_offset(ctypes.byref(shp), which)
