@@ -45,21 +45,37 @@ __global__ void col2im1d_kernel(float* __restrict__ dx, const float* __restrict_
     }
 }
 
+// Sum over the (NB, L) slab of channel c of f(x): rows are contiguous, so every thread walks whole rows with 16-byte loads and
+// four independent accumulators (no div / mod, plenty of loads in flight).  blockDim = 256.
+template <class F>
+__device__ __forceinline__ float channel_sum(const float* __restrict__ x, int c, int NB, int Ct, int L, F f) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const bool vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    for (int q = 0; q < NB; ++q) {
+        const float* row = x + ((size_t)q * Ct + c) * L;
+        if (vec) {
+            const float4* r4 = reinterpret_cast<const float4*>(row);
+            for (int l4 = threadIdx.x; l4 < (L >> 2); l4 += blockDim.x) {
+                const float4 v = r4[l4];
+                a0 += f(v.x, q, 4 * l4); a1 += f(v.y, q, 4 * l4 + 1); a2 += f(v.z, q, 4 * l4 + 2); a3 += f(v.w, q, 4 * l4 + 3);
+            }
+        } else {
+            for (int l = threadIdx.x; l < L; l += blockDim.x) a0 += f(row[l], q, l);
+        }
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
 // per-channel batch statistics over (NB, L); x [NB, Ct, L].  One CTA per channel, two passes (mean, then variance).
-__global__ void __launch_bounds__(128) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ invstd,
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ invstd,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var, int NB,
                                                        int Ct, int L, float eps, float momentum) {
     __shared__ float red[64];
     const int c = blockIdx.x;
     const int n = NB * L;
-    float s = 0.f;
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) s += x[((size_t)(idx / L) * Ct + c) * L + idx % L];
+    const float s = channel_sum(x, c, NB, Ct, L, [](float v, int, int) { return v; });
     const float mu = block_sum(s, red) / (float)n;
-    float v = 0.f;
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const float d = x[((size_t)(idx / L) * Ct + c) * L + idx % L] - mu;
-        v = fmaf(d, d, v);
-    }
+    const float v = channel_sum(x, c, NB, Ct, L, [mu](float xv, int, int) { const float d = xv - mu; return d * d; });
     const float var = block_sum(v, red) / (float)n;
     if (threadIdx.x == 0) {
         mean[c] = mu;
@@ -152,20 +168,15 @@ __global__ void block_bwd_prep_kernel(const BlockArgs p, const float* __restrict
 }
 
 // per channel: s1 = sum dz, s2 = sum dz * xhat  -> dbeta += s1, dgamma += s2; keeps s1, s2 for the apply pass
-__global__ void __launch_bounds__(128) bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ conv,
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ conv,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             float* __restrict__ s1o, float* __restrict__ s2o, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int affine_gstride, int NB, int G, int Cout, int L) {
     __shared__ float red[64];
-    const int ch = blockIdx.x, Ct = G * Cout, n = NB * L;
+    const int ch = blockIdx.x, Ct = G * Cout;
     const float mu = mean[ch], is = invstd[ch];
-    float s1 = 0.f, s2 = 0.f;
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const size_t ci = ((size_t)(idx / L) * Ct + ch) * L + idx % L;
-        const float d = dz[ci];
-        s1 += d;
-        s2 = fmaf(d, (conv[ci] - mu) * is, s2);
-    }
+    float s1 = channel_sum(dz, ch, NB, Ct, L, [](float d, int, int) { return d; });
+    float s2 = channel_sum(dz, ch, NB, Ct, L, [=](float d, int q, int l) { return d * (conv[((size_t)q * Ct + ch) * L + l] - mu) * is; });
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
     if (threadIdx.x == 0) {
@@ -203,18 +214,114 @@ __global__ void embedding_fwd_kernel(float* __restrict__ out, int ldo, const flo
     }
 }
 
-// dtable[v, :] += sum over tokens with id v of dout[token, :]   (one CTA per vocabulary row: deterministic order)
+// dtable[v, :] += sum over tokens with id v of dout[token, :]   (one CTA per vocabulary row: deterministic token order).
+// The ids are staged through shared memory 1024 at a time, so the scan over all tokens costs one shared-memory read per token.
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(float* __restrict__ dtable, const float* __restrict__ dout, int ldo,
                                                             const int* __restrict__ ids, int ntok, int E, int padding_idx) {
+    __shared__ int s_ids[1024];
     const int v = blockIdx.x;
     if (v == padding_idx) return;
-    for (int e0 = 0; e0 < E; e0 += blockDim.x) {
-        const int e = e0 + threadIdx.x;
-        float acc = 0.f;
-        for (int t = 0; t < ntok; ++t)
-            if (ids[t] == v && e < E) acc += dout[(size_t)t * ldo + e];
-        if (e < E) dtable[(size_t)v * E + e] += acc;
+    constexpr int EPT = 4;                                   // embedding columns per thread (E <= 1024)
+    float acc[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) acc[j] = 0.f;
+    for (int t0 = 0; t0 < ntok; t0 += 1024) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 1024; t += blockDim.x) s_ids[t] = t0 + t < ntok ? ids[t0 + t] : -1;
+        __syncthreads();
+        const int n = min(1024, ntok - t0);
+        for (int t = 0; t < n; t += 8) {                      // 8 tokens at a time: all matching rows in flight, added in token order
+            float val[8][EPT];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool hit = t + u < n && s_ids[t + u] == v;          // uniform over the CTA
+                const float* row = dout + (size_t)(t0 + t + u) * ldo;
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) {
+                    const int e = threadIdx.x + j * 256;
+                    val[u][j] = (hit && e < E) ? row[e] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) acc[j] += val[u][j];
+        }
     }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const int e = threadIdx.x + j * 256;
+        if (e < E) dtable[(size_t)v * E + e] += acc[j];
+    }
+}
+
+// ---- parameter generator: skinny products with one huge dimension R (the generated kernel) ----
+constexpr int GEN_MAXG = 16, GEN_MAXBN = 16;
+// out[g, r] = sum_j eb[g, j] Wk[r, j] + bk[r]
+__global__ void generator_expand_kernel(float* __restrict__ out, const float* __restrict__ eb, const float* __restrict__ Wk,
+                                        const float* __restrict__ bk, int G, int bn, size_t R) {
+    __shared__ float s_eb[GEN_MAXG * GEN_MAXBN];
+    for (int i = threadIdx.x; i < G * bn; i += blockDim.x) s_eb[i] = eb[i];
+    __syncthreads();
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < R; r += (size_t)gridDim.x * blockDim.x) {
+        float w[GEN_MAXBN];
+#pragma unroll
+        for (int j = 0; j < GEN_MAXBN; ++j) w[j] = j < bn ? Wk[r * bn + j] : 0.f;
+        const float b = bk ? bk[r] : 0.f;
+        for (int g = 0; g < G; ++g) {
+            float a = b;
+#pragma unroll
+            for (int j = 0; j < GEN_MAXBN; ++j) if (j < bn) a = fmaf(s_eb[g * bn + j], w[j], a);
+            out[(size_t)g * R + r] = a;
+        }
+    }
+}
+// dWk[r, j] += sum_g dout[g, r] eb[g, j];  dbk[r] += sum_g dout[g, r]
+__global__ void generator_dwk_kernel(float* __restrict__ dWk, float* __restrict__ dbk, const float* __restrict__ dout,
+                                     const float* __restrict__ eb, int G, int bn, size_t R) {
+    __shared__ float s_eb[GEN_MAXG * GEN_MAXBN];
+    for (int i = threadIdx.x; i < G * bn; i += blockDim.x) s_eb[i] = eb[i];
+    __syncthreads();
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < R; r += (size_t)gridDim.x * blockDim.x) {
+        float acc[GEN_MAXBN];
+#pragma unroll
+        for (int j = 0; j < GEN_MAXBN; ++j) acc[j] = 0.f;
+        float sb = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const float d = dout[(size_t)g * R + r];
+            sb += d;
+#pragma unroll
+            for (int j = 0; j < GEN_MAXBN; ++j) if (j < bn) acc[j] = fmaf(d, s_eb[g * bn + j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < GEN_MAXBN; ++j) if (j < bn) dWk[r * bn + j] += acc[j];
+        if (dbk) dbk[r] += sb;
+    }
+}
+// partial[blk][g, j] = sum over this block's r-chunk of dout[g, r] Wk[r, j]   (thread = (g, j); fixed chunking: deterministic)
+__global__ void generator_deb_partial_kernel(float* __restrict__ partial, const float* __restrict__ dout, const float* __restrict__ Wk,
+                                             int G, int bn, size_t R, size_t chunk) {
+    const int t = threadIdx.x;
+    if (t >= G * bn) return;
+    const int g = t / bn, j = t % bn;
+    const size_t r0 = blockIdx.x * chunk, r1 = r0 + chunk < R ? r0 + chunk : R;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    size_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+        a0 = fmaf(dout[(size_t)g * R + r], Wk[r * bn + j], a0);
+        a1 = fmaf(dout[(size_t)g * R + r + 1], Wk[(r + 1) * bn + j], a1);
+        a2 = fmaf(dout[(size_t)g * R + r + 2], Wk[(r + 2) * bn + j], a2);
+        a3 = fmaf(dout[(size_t)g * R + r + 3], Wk[(r + 3) * bn + j], a3);
+    }
+    for (; r < r1; ++r) a0 = fmaf(dout[(size_t)g * R + r], Wk[r * bn + j], a0);
+    partial[(size_t)blockIdx.x * G * bn + t] = (a0 + a1) + (a2 + a3);
+}
+__global__ void generator_deb_finish_kernel(float* __restrict__ deb, const float* __restrict__ partial, int nblk, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + t];
+    deb[t] = s;
 }
 
 __global__ void colsum_rows_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, size_t cols) {
@@ -283,7 +390,7 @@ int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, con
     g.M = s.Cout; g.N = s.L; g.K = s.Cin * s.k; g.batch = s.NB * s.G;
     B200_TRY(gemm_run(g, st));
     if (s.training) {
-        bn_stats_kernel<<<(int)d.Ct, 128, 0, st>>>(conv, mean, invstd, running_mean, running_var, s.NB, (int)d.Ct, s.L, s.eps, s.momentum);
+        bn_stats_kernel<<<(int)d.Ct, 256, 0, st>>>(conv, mean, invstd, running_mean, running_var, s.NB, (int)d.Ct, s.L, s.eps, s.momentum);
     } else {
         B200_REQUIRE(running_mean && running_var, "convblock: eval mode needs running statistics");
         bn_eval_stats_kernel<<<cdiv(d.Ct, 256), 256, 0, st>>>(mean, invstd, running_mean, running_var, (int)d.Ct, s.eps);
@@ -315,7 +422,7 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
                 1.f / (1.f - s.dropout), x, s.NB, s.G, s.Cout, s.L, s.activation, s.highway};
     block_bwd_prep_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, dout, dz, dx);
     B200_LAUNCH_CHECK();
-    bn_bwd_reduce_kernel<<<(int)d.Ct, 128, 0, st>>>(dz, conv, mean, invstd, s1, s2, dgamma, dbeta, affine_gstride, s.NB, s.G, s.Cout, s.L);
+    bn_bwd_reduce_kernel<<<(int)d.Ct, 256, 0, st>>>(dz, conv, mean, invstd, s1, s2, dgamma, dbeta, affine_gstride, s.NB, s.G, s.Cout, s.L);
     B200_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<grid_for(d.conv_elems), 256, 0, st>>>(dz, conv, mean, invstd, gamma, affine_gstride, s1, s2, s.NB, s.G, s.Cout,
                                                                 s.L, s.training);
@@ -380,6 +487,11 @@ int generator_forward_impl(int G, int gd, int bn, long long R, const float* e, c
     GemmDesc a;
     a.A = e; a.lda = gd; a.B = Wb; a.ldb = gd; a.transB = 1; a.C = eb; a.ldc = bn; a.bias = bb; a.M = G; a.N = bn; a.K = gd;
     B200_TRY(gemm_f32(a, st));
+    if (G <= GEN_MAXG && bn <= GEN_MAXBN) {      // skinny product, bound by reading Wk / writing the generated kernel once
+        generator_expand_kernel<<<grid_for((size_t)R), 256, 0, st>>>(out, eb, Wk, bk, G, bn, (size_t)R);
+        B200_LAUNCH_CHECK();
+        return B200TTS_OK;
+    }
     GemmDesc b;
     b.A = eb; b.lda = bn; b.B = Wk; b.ldb = bn; b.transB = 1; b.C = out; b.ldc = (int)R; b.bias = bk; b.M = G; b.N = (int)R; b.K = bn;
     return gemm_f32(b, st);
@@ -389,15 +501,28 @@ int generator_backward_impl(int G, int gd, int bn, long long R, const float* e, 
                             const float* dout, float* de, float* dWb, float* dbb, float* dWk, float* dbk, float* ws, cudaStream_t st) {
     float* deb = ws;
     float* scratch = ws + align_up_sz((size_t)G * bn, 64);
-    GemmDesc a;     // dWk [R, bn] += dout^T . eb
-    a.A = dout; a.lda = (int)R; a.transA = 1; a.B = eb; a.ldb = bn; a.transB = 0; a.C = dWk; a.ldc = bn; a.beta = 1.f;
-    a.M = (int)R; a.N = bn; a.K = G;
-    B200_TRY(gemm_f32(a, st));
-    colsum_rows_add_kernel<<<grid_for((size_t)R), 256, 0, st>>>(dbk, dout, G, (size_t)R);
-    B200_LAUNCH_CHECK();
-    GemmDesc b;     // deb [G, bn] = dout . Wk   (long K: split)
-    b.A = dout; b.lda = (int)R; b.B = Wk; b.ldb = bn; b.transB = 0; b.C = deb; b.ldc = bn; b.M = G; b.N = bn; b.K = (int)R;
-    B200_TRY(gemm_f32_auto(b, scratch, kGemmScratch, st));
+    const size_t chunk = 256;
+    const int nblk = (int)((R + chunk - 1) / chunk);
+    if (G <= GEN_MAXG && bn <= GEN_MAXBN && (size_t)nblk * G * bn <= kGemmScratch && G * bn <= 256) {
+        // dWk [R, bn] += dout^T . eb and dbk += column sums of dout, in one pass over dout
+        generator_dwk_kernel<<<grid_for((size_t)R), 256, 0, st>>>(dWk, dbk, dout, eb, G, bn, (size_t)R);
+        B200_LAUNCH_CHECK();
+        // deb [G, bn] = dout . Wk: per-chunk partial sums, then a fixed-order reduction
+        generator_deb_partial_kernel<<<nblk, 256, 0, st>>>(scratch, dout, Wk, G, bn, (size_t)R, chunk);
+        B200_LAUNCH_CHECK();
+        generator_deb_finish_kernel<<<cdiv(G * bn, 128), 128, 0, st>>>(deb, scratch, nblk, G * bn);
+        B200_LAUNCH_CHECK();
+    } else {
+        GemmDesc a;     // dWk [R, bn] += dout^T . eb
+        a.A = dout; a.lda = (int)R; a.transA = 1; a.B = eb; a.ldb = bn; a.transB = 0; a.C = dWk; a.ldc = bn; a.beta = 1.f;
+        a.M = (int)R; a.N = bn; a.K = G;
+        B200_TRY(gemm_f32(a, st));
+        colsum_rows_add_kernel<<<grid_for((size_t)R), 256, 0, st>>>(dbk, dout, G, (size_t)R);
+        B200_LAUNCH_CHECK();
+        GemmDesc b;     // deb [G, bn] = dout . Wk   (long K: split)
+        b.A = dout; b.lda = (int)R; b.B = Wk; b.ldb = bn; b.transB = 0; b.C = deb; b.ldc = bn; b.M = G; b.N = bn; b.K = (int)R;
+        B200_TRY(gemm_f32_auto(b, scratch, kGemmScratch, st));
+    }
     GemmDesc c;     // dWb [bn, gd] += deb^T . e
     c.A = deb; c.lda = bn; c.transA = 1; c.B = e; c.ldb = gd; c.transB = 0; c.C = dWb; c.ldc = gd; c.beta = 1.f; c.M = bn; c.N = gd; c.K = G;
     B200_TRY(gemm_f32(c, st));
@@ -415,6 +540,7 @@ int embedding_forward_impl(float* out, int ldo, const float* table, const int* i
 }
 int embedding_backward_impl(float* dtable, int V, const float* dout, int ldo, const int* ids, long long ntok, int E, int padding_idx,
                             cudaStream_t st) {
+    B200_REQUIRE(E <= 1024, "embedding_backward: embedding dimension %d > 1024 is not supported", E);
     embedding_bwd_kernel<<<V, 256, 0, st>>>(dtable, dout, ldo, ids, (int)ntok, E, padding_idx);
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
