@@ -9,6 +9,10 @@
 namespace b200tts {
 
 int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled);      // gemm_tc.cu
+int gemm_tc_conv(const float* weight, const float* in, float* out, int NB, int G, int Cout, int Cin, int L, int k, int dil, int pad, int bwd,
+                 float beta, cudaStream_t st, bool* handled);
+int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int G, int Cout, int Cin, int L, int k, int dil, int pad,
+                    cudaStream_t st, bool* handled);
 
 namespace {
 
@@ -377,18 +381,23 @@ int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, con
     float* conv = saved;
     float* mean = saved + align_up_sz(d.conv_elems, 64);
     float* invstd = mean + align_up_sz(d.Ct, 64);
-    const float* col = x;
-    if (s.k > 1) {
-        im2col1d_kernel<<<grid_for(d.col_elems), 256, 0, st>>>(ws, x, (size_t)s.NB * s.G, s.Cin, s.L, s.k, s.dilation, d.pad);
-        B200_LAUNCH_CHECK();
-        col = ws;
+    bool implicit = false;
+    if (precision_mode() != 0 && s.k > 1)       // bf16 perf mode: implicit convolution on the tcgen05 GEMM (TMA row shifts per tap, no im2col)
+        B200_TRY(gemm_tc_conv(weight, x, conv, s.NB, s.G, s.Cout, s.Cin, s.L, s.k, s.dilation, d.pad, 0, 0.f, st, &implicit));
+    if (!implicit) {
+        const float* col = x;
+        if (s.k > 1) {
+            im2col1d_kernel<<<grid_for(d.col_elems), 256, 0, st>>>(ws, x, (size_t)s.NB * s.G, s.Cin, s.L, s.k, s.dilation, d.pad);
+            B200_LAUNCH_CHECK();
+            col = ws;
+        }
+        GemmDesc g;
+        g.A = weight; g.lda = s.Cin * s.k; g.transA = 0; g.a_batch_mod = s.G; g.strideA = (long long)s.Cout * s.Cin * s.k;
+        g.B = col; g.ldb = s.L; g.transB = 0; g.strideB = (long long)s.Cin * s.k * s.L;
+        g.C = conv; g.ldc = s.L; g.strideC = (long long)s.Cout * s.L;
+        g.M = s.Cout; g.N = s.L; g.K = s.Cin * s.k; g.batch = s.NB * s.G;
+        B200_TRY(gemm_run(g, st));
     }
-    GemmDesc g;
-    g.A = weight; g.lda = s.Cin * s.k; g.transA = 0; g.a_batch_mod = s.G; g.strideA = (long long)s.Cout * s.Cin * s.k;
-    g.B = col; g.ldb = s.L; g.transB = 0; g.strideB = (long long)s.Cin * s.k * s.L;
-    g.C = conv; g.ldc = s.L; g.strideC = (long long)s.Cout * s.L;
-    g.M = s.Cout; g.N = s.L; g.K = s.Cin * s.k; g.batch = s.NB * s.G;
-    B200_TRY(gemm_run(g, st));
     if (s.training) {
         bn_stats_kernel<<<(int)d.Ct, 256, 0, st>>>(conv, mean, invstd, running_mean, running_var, s.NB, (int)d.Ct, s.L, s.eps, s.momentum);
     } else {
@@ -428,17 +437,25 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
                                                                 s.L, s.training);
     B200_LAUNCH_CHECK();
     const float* colr = x;
-    if (s.k > 1) {
-        im2col1d_kernel<<<grid_for(d.col_elems), 256, 0, st>>>(col, x, (size_t)s.NB * s.G, s.Cin, s.L, s.k, s.dilation, d.pad);
-        B200_LAUNCH_CHECK();
-        colr = col;
-    }
+    bool have_col = (s.k == 1);
+    auto ensure_col = [&]() -> int {         // im2col only for the paths that still need the materialised matrix
+        if (!have_col) {
+            im2col1d_kernel<<<grid_for(d.col_elems), 256, 0, st>>>(col, x, (size_t)s.NB * s.G, s.Cin, s.L, s.k, s.dilation, d.pad);
+            B200_LAUNCH_CHECK();
+            colr = col;
+            have_col = true;
+        }
+        return B200TTS_OK;
+    };
     const int R = s.Cin * s.k;
     if (dweight) {
         // dW[g] (+)= sum_rows dconv[row, g] . col[row, g]^T
         bool fused = false;
-        if (precision_mode() != 0 && s.NB > 1) {
-            // bf16 perf mode: ONE batched tcgen05 GEMM whose K runs over (sample row, position): K = NB * L (two-level K of the packer)
+        if (precision_mode() != 0 && s.k > 1)   // bf16 perf mode: K over (sample row, position), the shifted-input operand packed straight from x
+            B200_TRY(gemm_tc_conv_dw(dz, x, dweight, s.NB, s.G, s.Cout, s.Cin, s.L, s.k, s.dilation, d.pad, st, &fused));
+        if (!fused && precision_mode() != 0 && s.NB > 1) {
+            // ONE batched tcgen05 GEMM whose K runs over (sample row, position): K = NB * L (two-level K of the packer)
+            B200_TRY(ensure_col());
             GemmDesc g;
             g.A = dz; g.lda = s.L; g.transA = 0; g.strideA = (long long)s.Cout * s.L; g.kosA = (long long)d.Ct * s.L;
             g.B = colr; g.ldb = s.L; g.transB = 1; g.strideB = (long long)R * s.L; g.kosB = (long long)s.G * R * s.L;
@@ -446,6 +463,7 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
             g.M = s.Cout; g.N = R; g.K = s.NB * s.L; g.kin = s.L; g.batch = s.G;
             B200_TRY(gemm_tc_try(g, st, &fused));
         }
+        if (!fused) B200_TRY(ensure_col());
         // otherwise one batched GEMM per sample row, accumulating
         for (int q = 0; q < s.NB && !fused; ++q) {
             GemmDesc g;
@@ -465,6 +483,11 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
             g.C = dx; g.ldc = s.L; g.strideC = (long long)s.Cin * s.L; g.beta = s.highway ? 1.f : 0.f;
             B200_TRY(gemm_run(g, st));
         } else {
+            bool implicit = false;
+            if (precision_mode() != 0)      // input gradient as an implicit (transposed) convolution of d conv: no dcol, no col2im
+                B200_TRY(gemm_tc_conv(weight, dz, dx, s.NB, s.G, s.Cout, s.Cin, s.L, s.k, s.dilation, d.pad, 1, s.highway ? 1.f : 0.f, st, &implicit));
+            if (implicit) return B200TTS_OK;
+            B200_TRY(ensure_col());
             g.C = dcol; g.ldc = s.L; g.strideC = (long long)R * s.L;
             B200_TRY(gemm_run(g, st));
             col2im1d_kernel<<<grid_for((size_t)s.NB * s.G * s.Cin * s.L), 256, 0, st>>>(dx, dcol, (size_t)s.NB * s.G, s.Cin, s.L, s.k,

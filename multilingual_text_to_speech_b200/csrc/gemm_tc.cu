@@ -103,6 +103,10 @@ struct TcArgs {
     float alpha, beta;
     int batch, a_batch_mod;
     long long strideC;
+    // implicit 1-D convolution (conv_cb > 0): k-block kb = (tap t = kb / conv_cb, channel block cb = kb % conv_cb); the B tile is
+    // rows [n0 + t * conv_dil - conv_pad, + 128) x channels [g * conv_cin + 64 cb, + 64) of sample bz / conv_G in the position-major
+    // bf16 copy of the input (TMA zero-fills the rows outside [0, L))
+    int conv_cb, conv_dil, conv_pad, conv_G, conv_cin;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -141,7 +145,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 uint8_t* sa = ring + (size_t)s * STAGE_BYTES;
                 tma_load_3d(sa, &tmA, &full_bar[s], kb * TBK, m0, az);
-                tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], kb * TBK, n0, bz);
+                if (p.conv_cb > 0) {
+                    const int t = kb / p.conv_cb, cb = kb % p.conv_cb;
+                    tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], (bz % p.conv_G) * p.conv_cin + cb * TBK, n0 + t * p.conv_dil - p.conv_pad,
+                                bz / p.conv_G);
+                } else {
+                    tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], kb * TBK, n0, bz);
+                }
             }
         }
     } else if (warp == 5) {
@@ -251,6 +261,41 @@ __global__ void pack_transpose_kernel(__nv_bfloat16* __restrict__ dst, const flo
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int r = r0 + j, k = k0 + threadIdx.x;
         if (r < rows && k < Kp) d[(size_t)r * Kp + k] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+}
+
+// Convolution weights W[g][co][ci][t] (fp32) -> bf16 A operands with K ordered (tap, channel):
+//   forward : dst[g][co][t * Cin + ci]            (rows = output channels)
+//   backward: dst[g][ci][t * Cout + co]           (rows = input channels: the input-gradient convolution)
+__global__ void pack_conv_weight_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ w, int G, int Cout, int Cin, int k, int bwd) {
+    const size_t total = (size_t)G * Cout * Cin * k;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        // idx enumerates dst: [g][row][t][col]
+        const int rows = bwd ? Cin : Cout, cols = bwd ? Cout : Cin;
+        const int col = idx % cols, t = (idx / cols) % k, row = (idx / ((size_t)cols * k)) % rows, g = idx / ((size_t)cols * k * rows);
+        const int co = bwd ? col : row, ci = bwd ? row : col;
+        dst[idx] = __float2bfloat16_rn(w[(((size_t)g * Cout + co) * Cin + ci) * k + t]);
+    }
+}
+
+// B operand of a convolution's weight gradient, straight from the block input (no materialised im2col):
+//   dst[g][ci * k + t][q * L + l] = x[q][g * Cin + ci][l + t * dil - pad]   (zero outside [0, L)), bf16, K = NB * L contiguous (padded to Kp)
+__global__ void pack_im2col_kcontig_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ x, int NB, int G, int Cin, int L, int k,
+                                           int dil, int pad, int Kp) {
+    const int R = Cin * k;
+    const size_t per = (size_t)R * Kp;
+    const int g = blockIdx.y;
+    __nv_bfloat16* d = dst + (size_t)g * per;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < per; idx += (size_t)gridDim.x * blockDim.x) {
+        const int kk = idx % Kp;
+        const int r = idx / Kp;
+        float v = 0.f;
+        if (kk < NB * L) {
+            const int q = kk / L, l = kk % L, ci = r / k, t = r % k;
+            const int ls = l + t * dil - pad;
+            if (ls >= 0 && ls < L) v = x[((size_t)q * G * Cin + (size_t)g * Cin + ci) * L + ls];
+        }
+        d[idx] = __float2bfloat16_rn(v);
     }
 }
 
@@ -400,6 +445,7 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     TcArgs a;
     a.C = d.C; a.bias = d.bias; a.M = d.M; a.N = d.N; a.K = d.K; a.ldc = d.ldc; a.alpha = d.alpha; a.beta = d.beta;
     a.batch = d.batch; a.a_batch_mod = d.a_batch_mod; a.strideC = d.strideC;
+    a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     static bool configured = false;
     if (!configured) {
@@ -407,6 +453,92 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
         configured = true;
     }
     dim3 grid(cdiv(d.N, TBN), cdiv(d.M, TBM), d.batch);
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    B200_LAUNCH_CHECK();
+    *handled = true;
+    return B200TTS_OK;
+}
+
+
+// Implicit 1-D convolution on the tcgen05 GEMM (no im2col):  out[row, g][m, l] (+)= sum_{t, c} Wp[g][m][t * Cred + c] . in[row][g * Cred + c][l + t * dil - pad]
+//   forward        : Wp = weights packed (co, t, ci), in = x,        Cred = Cin,  rows m = Cout, dil/pad as given
+//   input gradient : Wp = weights packed (ci, t, co), in = d conv,   Cred = Cout, rows m = Cin,  dil -> -dil, pad -> -pad
+// `in` is [NB, G * Cred, L] fp32; its position-major bf16 copy [NB][L][G * Cred] is made here (one transposing pass, 1x the activation).
+// out is [NB * G][Mrows][L] fp32 with row stride L.  Declines (handled = false) when the shape does not fit the tiling.
+int gemm_tc_conv(const float* weight, const float* in, float* out, int NB, int G, int Cout, int Cin, int L, int k, int dil, int pad, int bwd,
+                 float beta, cudaStream_t st, bool* handled) {
+    *handled = false;
+    const int Cred = bwd ? Cout : Cin, Mrows = bwd ? Cin : Cout;
+    if (!g_tc_enabled || g_scratch.ptr == nullptr || g_cache_on) return B200TTS_OK;
+    if (Cred % TBK != 0 || Mrows < 64 || L < 64 || k < 1) return B200TTS_OK;
+    if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
+    const int K = k * Cred, Ctot = G * Cred;
+    const size_t a_bytes = ((size_t)G * Mrows * K * 2 + 1023) / 1024 * 1024;
+    const size_t b_bytes = ((size_t)NB * L * Ctot * 2 + 1023) / 1024 * 1024;
+    if (a_bytes + b_bytes > g_scratch.bytes) return B200TTS_OK;
+    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
+    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
+    {
+        const size_t total = (size_t)G * Cout * Cin * k;
+        int gx = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+        pack_conv_weight_kernel<<<gx, 256, 0, st>>>(pa, weight, G, Cout, Cin, k, bwd);
+        B200_LAUNCH_CHECK();
+        // position-major copy: element (row = l, k = channel) of sample n at in[n][channel][l]
+        dim3 grid(cdiv(L, 32), cdiv(Ctot, 32), NB), block(32, 8);
+        pack_transpose_kernel<<<grid, block, 0, st>>>(pb, in, L, (long long)Ctot * L, L, Ctot, Ctot);
+        B200_LAUNCH_CHECK();
+    }
+    CUtensorMap tmA, tmB;
+    B200_TRY(make_map(&tmA, pa, Mrows, K, K, G, TBM));
+    B200_TRY(make_map(&tmB, pb, L, Ctot, Ctot, NB, TBN));
+    TcArgs a;
+    a.C = out; a.bias = nullptr; a.M = Mrows; a.N = L; a.K = K; a.ldc = L; a.alpha = 1.f; a.beta = beta;
+    a.batch = NB * G; a.a_batch_mod = G; a.strideC = (long long)Mrows * L;
+    a.conv_cb = Cred / TBK; a.conv_dil = bwd ? -dil : dil; a.conv_pad = bwd ? -pad : pad; a.conv_G = G; a.conv_cin = Cred;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(L, TBN), cdiv(Mrows, TBM), NB * G);
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    B200_LAUNCH_CHECK();
+    *handled = true;
+    return B200TTS_OK;
+}
+
+
+// Weight gradient of a 1-D convolution in ONE batched tcgen05 GEMM:  dW[g][co][ci * k + t] += sum_{q, l} dz[q][g, co][l] . x[q][g, ci][l + t dil - pad].
+// A = dz packed with a two-level K (sample row, position); B = the shifted input packed straight from x (pack_im2col_kcontig_kernel).
+int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int G, int Cout, int Cin, int L, int k, int dil, int pad,
+                    cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (!g_tc_enabled || g_scratch.ptr == nullptr || g_cache_on) return B200TTS_OK;
+    const int R = Cin * k, K = NB * L, Kp = (K + 7) / 8 * 8;
+    if (Cout < 64 || R < 64 || K < 64) return B200TTS_OK;
+    if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
+    const size_t a_bytes = ((size_t)G * Cout * Kp * 2 + 1023) / 1024 * 1024;
+    const size_t b_bytes = ((size_t)G * R * Kp * 2 + 1023) / 1024 * 1024;
+    if (a_bytes + b_bytes > g_scratch.bytes) return B200TTS_OK;
+    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
+    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
+    {
+        const size_t per = (size_t)Cout * Kp;
+        int gx = (int)((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
+        pack_kcontig_kernel<<<dim3(gx, G), 256, 0, st>>>(pa, dz, L, (long long)Cout * L, Cout, K, Kp, L, (long long)G * Cout * L);
+        B200_LAUNCH_CHECK();
+        const size_t perb = (size_t)R * Kp;
+        int gb = (int)((perb + 255) / 256 > 148 * 16 ? 148 * 16 : (perb + 255) / 256);
+        pack_im2col_kcontig_kernel<<<dim3(gb, G), 256, 0, st>>>(pb, x, NB, G, Cin, L, k, dil, pad, Kp);
+        B200_LAUNCH_CHECK();
+    }
+    CUtensorMap tmA, tmB;
+    B200_TRY(make_map(&tmA, pa, Cout, K, Kp, G, TBM));
+    B200_TRY(make_map(&tmB, pb, R, K, Kp, G, TBN));
+    TcArgs a;
+    a.C = dweight; a.bias = nullptr; a.M = Cout; a.N = R; a.K = K; a.ldc = R; a.alpha = 1.f; a.beta = 1.f;
+    a.batch = G; a.a_batch_mod = 0; a.strideC = (long long)Cout * R;
+    a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(R, TBN), cdiv(Cout, TBM), G);
     gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
     B200_LAUNCH_CHECK();
     *handled = true;
