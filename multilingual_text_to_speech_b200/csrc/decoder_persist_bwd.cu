@@ -87,6 +87,14 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
     return s_ok != 0;
 }
 
+// thread-block cluster (CTA pair) primitives: split arrive / wait barrier and a distributed-shared-memory store
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_peer_f32(const float* local_smem, uint32_t peer_rank, float v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((uint32_t)__cvta_generic_to_shared(local_smem)), "r"(peer_rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 #define BPROF_DECL long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
@@ -350,18 +358,25 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
     uint32_t* s_Ph = reinterpret_cast<uint32_t*>(s_vv + A);   // [L16 + 48]
     uint32_t* s_Pl = s_Ph + (L16 + 48);
     float* s_red = reinterpret_cast<float*>(s_Pl + (L16 + 48));   // [64]
-    float* s_G = s_red + 64;                              // [L16][GLD]
-    float* s_dqp = p.dqp_after_g ? s_G + (size_t)L16 * GLD : scr;   // [8][A]: after G if it fits, else aliases s_dctx .. s_Ph (dead by then)
-    float* s_stage = reinterpret_cast<float*>(s_Pl);      // [L16]: d cum staging (Pl is dead by then)
+    // attention backward runs on CTA PAIRS (cluster of 2): rank hf = cta & 1 owns the position tiles [t_lo, t_hi) of utterance cta >> 1
+    const int hf = cta & 1, HT0 = (p.MT + 1) / 2;
+    const int t_lo = hf ? HT0 : 0, t_hi = hf ? p.MT : HT0;
+    const int g_lo = hf ? (HT0 - 1) * 16 : 0;             // first G row held locally: the own tiles plus ONE halo tile of the peer
+    float* s_G = s_red + 64;                              // [(HT0 + 1) * 16][GLD], row l stored at l - g_lo
+    float* s_dqp = s_G + (size_t)(HT0 + 1) * 16 * GLD;    // [8][A] per-warp query-gradient partials
+    float* s_dqx = s_dqp + 8 * A;                         // [A]  the peer's partial (written through distributed shared memory)
+    float* s_dotx = s_dqx + A;                            // [4]  the peer's partial softmax dot
+    float* s_stage = s_dotx + 4;                          // [L16] d cum staging
     BPROF_DECL
 
+    const int pc = cta >> 1;
     int pa_len = 0;
-    if (cta < B) { const int l0 = p.lengths[cta]; pa_len = l0 < 0 ? 0 : (l0 > L ? L : l0); }
+    if (pc < B) { const int l0 = p.lengths[pc]; pa_len = l0 < 0 ? 0 : (l0 > L ? L : l0); }
     for (int i = p.T - 1; i >= 0; --i) {
         const bool last = (i == p.T - 1);
-        // =========================== PA: attention backward of utterance `cta` ===========================
-        if (cta < B) {
-            const int b = cta, half = (p.KC - 1) / 2;
+        // =========================== PA: attention backward of utterance `pc` on the CTA pair (2 pc, 2 pc + 1) ===========================
+        if (pc < B) {
+            const int b = pc, half = (p.KC - 1) / 2;
             if (i > 0) {       // DRAM -> L2 one step ahead: the rows of step i-1 this phase starts with (alignment, query, cumulative weights, d ctx)
                 const size_t r1 = (size_t)(i - 1) * B + b;
                 const char* rows[5] = {reinterpret_cast<const char*>(p.align + (size_t)b * p.align_bstride + (size_t)(i - 1) * L),
@@ -379,7 +394,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                 if (!last)
                     for (int k2 = 0; k2 < KBA; ++k2) g += __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + m);
                 s_dctx[m] = g;
-                p.dctx_tot[((size_t)i * B + b) * M + m] = g;
+                if (hf == 0) p.dctx_tot[((size_t)i * B + b) * M + m] = g;
             }
             for (int l = tid; l < L16; l += PT) s_w[l] = l < L ? p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] : 0.f;
             for (int a = tid; a < A; a += PT) { s_qb[a] = p.q[((size_t)i * B + b) * A + a] + p.bias[a]; s_vv[a] = p.v[a]; }
@@ -390,7 +405,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
             {
                 const int g = lane >> 2, tq = lane & 3;
                 constexpr int KT = 6;                         // k-tiles (16 memory dims) per register batch
-                for (int lt = warp; lt < p.MT; lt += 8) {
+                for (int lt = t_lo + warp; lt < t_hi; lt += 8) {
                     float dacc[4] = {0.f, 0.f, 0.f, 0.f}, dacc2[4] = {0.f, 0.f, 0.f, 0.f};
                     if (lt * 16 < len) {
                         const uint4* fr = p.memFb + (((size_t)b * p.MT + lt) * p.M16) * 32 + lane;
@@ -442,10 +457,15 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                 }
             }
             __syncthreads();
-            float dot = 0.f;
-            for (int l = tid; l < len; l += PT) dot = fmaf(s_w[l], s_de[l], dot);
-            dot = block_sum(dot, s_red);
-            for (int l = tid; l < L16; l += PT) {
+            // softmax backward: dot = sum_l w[l] dw[l] over ALL positions = own partial + the peer's (exchanged through DSMEM)
+            float pdot = 0.f;
+            for (int l = t_lo * 16 + tid; l < t_hi * 16 && l < len; l += PT) pdot = fmaf(s_w[l], s_de[l], pdot);
+            pdot = block_sum(pdot, s_red);
+            if (tid == 0) st_peer_f32(s_dotx, (uint32_t)(hf ^ 1), pdot);
+            cluster_arrive();
+            cluster_wait();
+            const float dot = pdot + s_dotx[0];           // a + b == b + a: both ranks get the same value
+            for (int l = t_lo * 16 + tid; l < t_hi * 16; l += PT) {
                 const float d = l < len ? s_w[l] * (s_de[l] - dot) : 0.f;
                 s_de[l] = d;
                 if (l < L) p.de[((size_t)i * B + b) * L + l] = d;
@@ -457,7 +477,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
 #pragma unroll
             for (int nt = 0; nt < 16; ++nt) { dqacc[nt][0] = 0.f; dqacc[nt][1] = 0.f; }
             const int g = lane >> 2, tq = lane & 3;
-            for (int mt = warp; mt < mtiles; mt += 8) {
+            for (int mt = t_lo + warp; mt < t_hi && mt < mtiles; mt += 8) {
                 const int l0 = mt * 16;
                 float sacc[16][4];
 #pragma unroll
@@ -522,7 +542,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) s_G[(l0 + g + 8 * (e >> 1)) * GLD + nt * 8 + 2 * tq + (e & 1)] = gacc[nt][e];
+                    for (int e = 0; e < 4; ++e) s_G[(l0 - g_lo + g + 8 * (e >> 1)) * GLD + nt * 8 + 2 * tq + (e & 1)] = gacc[nt][e];
             }
             // dq[a] = sum_l ds[l, a]: reduce over the 8 row lanes, then over warps
             __syncthreads();                               // every warp is done with s_de / s_qb / s_vv / Ph / Pl
@@ -537,23 +557,38 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                     if (g == 0) s_dqp[warp * A + nt * 8 + 2 * tq + c] = v;
                 }
             __syncthreads();
-            for (int a = tid; a < A; a += PT) {
-                float sdq = 0.f;
+            float pdq = 0.f;                                // this rank's partial of dq[a] (a = tid < A)
+            if (tid < A) {
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) sdq += s_dqp[w8 * A + a];
-                p.dq[((size_t)i * B + b) * A + a] = sdq;
+                for (int w8 = 0; w8 < 8; ++w8) pdq += s_dqp[w8 * A + tid];
+                st_peer_f32(s_dqx + tid, (uint32_t)(hf ^ 1), pdq);
             }
-            // d cum_{i-1}[j] = d cum_i[j] + sum_k G[j + half - k, k]
-            for (int j = tid; j < L; j += PT) {
+            {   // the boundary tile of G goes to the peer's halo rows (rank 0 sends its last tile, rank 1 its first)
+                const int ht = hf ? HT0 : HT0 - 1;             // tile sent
+                const int peer_g_lo = hf ? 0 : (HT0 - 1) * 16;
+                if (ht >= t_lo && ht < t_hi)
+                    for (int idx = tid; idx < 16 * GLD; idx += PT) {
+                        const int l = ht * 16 + idx / GLD, k = idx % GLD;
+                        st_peer_f32(s_G + (size_t)(l - peer_g_lo) * GLD + k, (uint32_t)(hf ^ 1), s_G[(size_t)(l - g_lo) * GLD + k]);
+                    }
+            }
+            cluster_arrive();
+            cluster_wait();
+            if (hf == 0 && tid < A) p.dq[((size_t)i * B + b) * A + tid] = pdq + s_dqx[tid];
+            // d cum_{i-1}[j] = d cum_i[j] + sum_k G[j + half - k, k] for the own positions (their G rows: own tiles + the halo tile)
+            for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) {
                 float acc = last ? 0.f : dcum[j];
                 for (int k = 0; k < p.KC; ++k) {
                     const int l = j + half - k;
-                    if (l >= 0 && l < mtiles * 16) acc += s_G[l * GLD + k];
+                    if (l >= 0 && l < mtiles * 16) acc += s_G[(size_t)(l - g_lo) * GLD + k];
                 }
                 s_stage[j] = acc;                           // staged: dcum is still being read by other threads
             }
             __syncthreads();
-            for (int j = tid; j < L; j += PT) dcum[j] = s_stage[j];
+            for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) dcum[j] = s_stage[j];
+        } else {
+            cluster_arrive(); cluster_wait();               // idle pairs: every thread of the cluster takes part in the two pair barriers
+            cluster_arrive(); cluster_wait();
         }
         BPROF_MARK(1);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
@@ -990,6 +1025,13 @@ bool persist_att_bwd_supported(const b200tts_decoder_shape& s) {
     if (s.A != 128 || s.K > 32 || s.B > 2 * BT || s.B * 8 > 3 * PT || s.D / 8 > KBA * NBA * ((s.B + BT - 1) / BT)) return false;
     const int UK = s.D / KBA, UN = (cdiv(s.M + s.D, NBA) + 15) / 16 * 16;
     const int MT = (s.L + 15) / 16, L16 = MT * 16;
+    {   // attention-backward scratch of one CTA of the pair (aliases the activation tile)
+        const int HT0 = (MT + 1) / 2;
+        const size_t fl = (size_t)((s.M + 3) & ~3) + 3 * (size_t)L16 + 2 * s.A + 2 * (size_t)(L16 + 48) + 64 + (size_t)(HT0 + 1) * 16 * GLD +
+                          8 * (size_t)s.A + s.A + 4;
+        if (fl * 4 > (size_t)BT * (4 * UK + 8) * 2) return false;
+        if ((KBA * NBA * ((s.B + BT - 1) / BT)) / 2 < s.B) return false;       // one CTA pair per utterance
+    }
     // the cell-backward phase stages the query gradients [B][A] fp32 + [64][8] products in the (then idle) activation tile
     if ((size_t)s.B * s.A * 4 + 64 * 8 * 4 > (size_t)BT * (4 * UK + 8) * 2) return false;
     const size_t fixed = ((size_t)4 * UK * (UN + 8) + (size_t)BT * (4 * UK + 8)) * 2 + (size_t)s.A * 40 * 2 + (size_t)32 * (s.A + 8) * 2 +
@@ -1040,9 +1082,19 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    B200_REQUIRE(per_sm * sms >= grid && grid >= B, "persistent attention backward: %d CTAs cannot be co-resident", grid);
+    B200_REQUIRE(per_sm * sms >= grid && grid % 2 == 0 && grid / 2 >= B, "persistent attention backward: %d CTAs cannot be co-resident / paired", grid);
     void* params[] = {&a};
-    B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;          // the attention backward of an utterance runs on a CTA pair
+    attrs[1].val.clusterDim.x = 2; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+    cfg.attrs = attrs; cfg.numAttrs = 2;
+    int nclusters = 0;
+    B200_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg));
+    B200_REQUIRE(nclusters * 2 >= grid, "persistent attention backward: only %d CTA pairs can be co-resident, %d needed", nclusters, grid / 2);
+    B200_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
     B200_LAUNCH_CHECK();
     // parallel post pass
     AttPostArgs pp{};

@@ -320,12 +320,14 @@ __global__ void generator_deb_partial_kernel(float* __restrict__ partial, const 
     for (; r < r1; ++r) a0 = fmaf(dout[(size_t)g * R + r], Wk[r * bn + j], a0);
     partial[(size_t)blockIdx.x * G * bn + t] = (a0 + a1) + (a2 + a3);
 }
-__global__ void generator_deb_finish_kernel(float* __restrict__ deb, const float* __restrict__ partial, int nblk, int n) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+// deb[t] = sum over the chunk partials, one CTA per output element (fixed tree: deterministic)
+__global__ void __launch_bounds__(128) generator_deb_finish_kernel(float* __restrict__ deb, const float* __restrict__ partial, int nblk, int n) {
+    __shared__ float red[64];
+    const int t = blockIdx.x;
     float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + t];
-    deb[t] = s;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[(size_t)b * n + t];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) deb[t] = s;
 }
 
 __global__ void colsum_rows_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, size_t cols) {
@@ -533,7 +535,7 @@ int generator_backward_impl(int G, int gd, int bn, long long R, const float* e, 
         // deb [G, bn] = dout . Wk: per-chunk partial sums, then a fixed-order reduction
         generator_deb_partial_kernel<<<nblk, 256, 0, st>>>(scratch, dout, Wk, G, bn, (size_t)R, chunk);
         B200_LAUNCH_CHECK();
-        generator_deb_finish_kernel<<<cdiv(G * bn, 128), 128, 0, st>>>(deb, scratch, nblk, G * bn);
+        generator_deb_finish_kernel<<<G * bn, 128, 0, st>>>(deb, scratch, nblk, G * bn);
         B200_LAUNCH_CHECK();
     } else {
         GemmDesc a;     // dWk [R, bn] += dout^T . eb

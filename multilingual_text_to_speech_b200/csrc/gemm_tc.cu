@@ -233,17 +233,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // operand packing: fp32 (either orientation) -> bf16 [batch][rows][Kp], K contiguous, Kp % 8 == 0
 // ------------------------------------------------------------------------------------------------
+// One CTA row-slice per (row, 1024-column chunk): no per-element 64-bit division; two-level K resolved per element with 32-bit math.
 __global__ void pack_kcontig_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int ld, long long bstride, int rows,
                                     int K, int Kp, int kin, long long kos) {
-    const size_t per = (size_t)rows * Kp;
-    const float* s = src + (size_t)blockIdx.y * bstride;
-    __nv_bfloat16* d = dst + (size_t)blockIdx.y * per;
-    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < per; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = idx / Kp;
-        const int k = idx % Kp;
-        float v = 0.f;
-        if (k < K) v = kin > 0 ? s[(size_t)(k / kin) * kos + r * ld + (k % kin)] : s[r * ld + k];      // kin > 0: two-level K (slab q = k / kin)
-        d[idx] = __float2bfloat16_rn(v);
+    const float* s = src + (size_t)blockIdx.z * bstride;
+    __nv_bfloat16* d = dst + (size_t)blockIdx.z * rows * Kp;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        const float* srow = s + (size_t)r * ld;
+        __nv_bfloat16* drow = d + (size_t)r * Kp;
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Kp; k += gridDim.x * blockDim.x) {
+            float v = 0.f;
+            if (k < K) {
+                if (kin > 0) { const unsigned q = (unsigned)k / (unsigned)kin; v = srow[(size_t)q * kos + (k - (int)q * kin)]; }   // slab q = k / kin
+                else v = srow[k];
+            }
+            drow[k] = __float2bfloat16_rn(v);
+        }
     }
 }
 // source element (r, k) at src[k*ld + r]: 32 x 32 tile transpose through shared memory
@@ -282,20 +287,21 @@ __global__ void pack_conv_weight_kernel(__nv_bfloat16* __restrict__ dst, const f
 //   dst[g][ci * k + t][q * L + l] = x[q][g * Cin + ci][l + t * dil - pad]   (zero outside [0, L)), bf16, K = NB * L contiguous (padded to Kp)
 __global__ void pack_im2col_kcontig_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ x, int NB, int G, int Cin, int L, int k,
                                            int dil, int pad, int Kp) {
-    const int R = Cin * k;
-    const size_t per = (size_t)R * Kp;
-    const int g = blockIdx.y;
-    __nv_bfloat16* d = dst + (size_t)g * per;
-    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < per; idx += (size_t)gridDim.x * blockDim.x) {
-        const int kk = idx % Kp;
-        const int r = idx / Kp;
-        float v = 0.f;
-        if (kk < NB * L) {
-            const int q = kk / L, l = kk % L, ci = r / k, t = r % k;
-            const int ls = l + t * dil - pad;
-            if (ls >= 0 && ls < L) v = x[((size_t)q * G * Cin + (size_t)g * Cin + ci) * L + ls];
+    const int R = Cin * k, g = blockIdx.z;
+    __nv_bfloat16* d = dst + (size_t)g * R * Kp;
+    for (int r = blockIdx.y; r < R; r += gridDim.y) {
+        const int ci = r / k, t = r % k, shift = t * dil - pad;
+        const float* xrow = x + ((size_t)g * Cin + ci) * L;             // + q * G * Cin * L per sample row
+        __nv_bfloat16* drow = d + (size_t)r * Kp;
+        for (int kk = blockIdx.x * blockDim.x + threadIdx.x; kk < Kp; kk += gridDim.x * blockDim.x) {
+            float v = 0.f;
+            if (kk < NB * L) {
+                const unsigned q = (unsigned)kk / (unsigned)L;
+                const int ls = kk - (int)q * L + shift;
+                if (ls >= 0 && ls < L) v = xrow[(size_t)q * G * Cin * L + ls];
+            }
+            drow[kk] = __float2bfloat16_rn(v);
         }
-        d[idx] = __float2bfloat16_rn(v);
     }
 }
 
@@ -425,9 +431,8 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
 
     auto pack = [&](__nv_bfloat16* dst, const float* src, int ld, long long bstride, int rows, bool kcontig, int nb, long long kos) -> int {
         if (kcontig) {
-            size_t per = (size_t)rows * Kp;
-            int gx = (int)((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
-            pack_kcontig_kernel<<<dim3(gx, nb), 256, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp, d.kin, kos);
+            const int gx = Kp > 16384 ? 16 : cdiv(Kp, 1024) > 0 ? cdiv(Kp, 1024) : 1;
+            pack_kcontig_kernel<<<dim3(gx, rows < 32768 ? rows : 32768, nb), 256, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp, d.kin, kos);
         } else {
             dim3 grid(cdiv(rows, 32), cdiv(Kp, 32), nb), block(32, 8);
             pack_transpose_kernel<<<grid, block, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp);
@@ -520,13 +525,10 @@ int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int
     __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
     __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
     {
-        const size_t per = (size_t)Cout * Kp;
-        int gx = (int)((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
-        pack_kcontig_kernel<<<dim3(gx, G), 256, 0, st>>>(pa, dz, L, (long long)Cout * L, Cout, K, Kp, L, (long long)G * Cout * L);
+        pack_kcontig_kernel<<<dim3(Kp > 16384 ? 16 : cdiv(Kp, 1024), Cout, G), 256, 0, st>>>(pa, dz, L, (long long)Cout * L, Cout, K, Kp, L,
+                                                                                             (long long)G * Cout * L);
         B200_LAUNCH_CHECK();
-        const size_t perb = (size_t)R * Kp;
-        int gb = (int)((perb + 255) / 256 > 148 * 16 ? 148 * 16 : (perb + 255) / 256);
-        pack_im2col_kcontig_kernel<<<dim3(gb, G), 256, 0, st>>>(pb, x, NB, G, Cin, L, k, dil, pad, Kp);
+        pack_im2col_kcontig_kernel<<<dim3(Kp > 16384 ? 16 : cdiv(Kp, 1024), R, G), 256, 0, st>>>(pb, x, NB, G, Cin, L, k, dil, pad, Kp);
         B200_LAUNCH_CHECK();
     }
     CUtensorMap tmA, tmB;
