@@ -370,6 +370,27 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
     BPROF_DECL
 
     const int pc = cta >> 1;
+    // cell-backward operands of this thread's (b, u) pairs (owner CTAs): fetched a whole reverse step ahead, at the end of the previous
+    // cell phase, so that their DRAM latency never sits on the critical path
+    float gi_[MAXE], gf_[MAXE], gg_[MAXE], go_[MAXE], cp_[MAXE], dhs_[MAXE];
+    uint8_t mh_[MAXE], mc_[MAXE];
+    auto pb_prefetch = [&](int step) {
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            const int idx = tid + e * PT;
+            gi_[e] = gf_[e] = gg_[e] = go_[e] = cp_[e] = dhs_[e] = 0.f; mh_[e] = 1; mc_[e] = 1;
+            if (owner && idx < B * UOWN && step >= 0) {
+                const int b = idx / UOWN, u = uo0 + idx % UOWN;
+                const size_t bu = (size_t)b * D + u, g0 = ((size_t)step * B + b) * 4 * D + u, mi = (size_t)step * B * D + bu;
+                gi_[e] = p.gates[g0]; gf_[e] = p.gates[g0 + D]; gg_[e] = p.gates[g0 + 2 * D]; go_[e] = p.gates[g0 + 3 * D];
+                cp_[e] = p.cstate[mi];
+                dhs_[e] = p.dh_static[mi];
+                if (p.training && p.mask_h) mh_[e] = p.mask_h[mi];
+                if (p.training && p.mask_c) mc_[e] = p.mask_c[mi];
+            }
+        }
+    };
+    pb_prefetch(p.T - 1);
     int pa_len = 0;
     if (pc < B) { const int l0 = p.lengths[pc]; pa_len = l0 < 0 ? 0 : (l0 > L ? L : l0); }
     for (int i = p.T - 1; i >= 0; --i) {
@@ -596,30 +617,21 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
 
         // =========================== PB: attention-LSTM cell backward ===========================
         if (owner) {
-            // operands of this thread's (b, u) pairs first (DRAM latency hides behind the query-gradient product below)
-            float gi_[MAXE], gf_[MAXE], gg_[MAXE], go_[MAXE], cp_[MAXE], dhs_[MAXE], rec_[MAXE];
-            uint8_t mh_[MAXE], mc_[MAXE];
+            // recurrent partial sums of this thread's (b, u) pairs (written by the product of the previous reverse step)
+            float rec_[MAXE];
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
                 const int idx = tid + e * PT;
-                gi_[e] = gf_[e] = gg_[e] = go_[e] = cp_[e] = dhs_[e] = rec_[e] = 0.f; mh_[e] = 1; mc_[e] = 1;
-                if (idx < B * UOWN) {
-                    const int b = idx / UOWN, uu = idx % UOWN, u = uo0 + uu;
-                    const size_t bu = (size_t)b * D + u, g0 = ((size_t)i * B + b) * 4 * D + u, mi = (size_t)i * B * D + bu;
-                    gi_[e] = p.gates[g0]; gf_[e] = p.gates[g0 + D]; gg_[e] = p.gates[g0 + 2 * D]; go_[e] = p.gates[g0 + 3 * D];
-                    cp_[e] = p.cstate[mi];
-                    dhs_[e] = p.dh_static[mi];
-                    if (p.training && p.mask_h) mh_[e] = p.mask_h[mi];
-                    if (p.training && p.mask_c) mc_[e] = p.mask_c[mi];
-                    if (!last) {
-                        float r8[KBA];
+                rec_[e] = 0.f;
+                if (idx < B * UOWN && !last) {
+                    const int b = idx / UOWN, u = uo0 + idx % UOWN;
+                    float r8[KBA];
 #pragma unroll
-                        for (int k2 = 0; k2 < KBA; ++k2) r8[k2] = __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
-                        float rs = 0.f;
+                    for (int k2 = 0; k2 < KBA; ++k2) r8[k2] = __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
+                    float rs = 0.f;
 #pragma unroll
-                        for (int k2 = 0; k2 < KBA; ++k2) rs += r8[k2];
-                        rec_[e] = rs;
-                    }
+                    for (int k2 = 0; k2 < KBA; ++k2) rs += r8[k2];
+                    rec_[e] = rs;
                 }
             }
             // d h (query part) = dq[b, :] . Wq[:, u] on the tensor cores: A = dq rows staged in shared memory (bf16 hi + lo),
@@ -710,8 +722,8 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                     db[2 * D] = __float2bfloat16_rn(dg); db[3 * D] = __float2bfloat16_rn(dO);
                     dc_reg[e] = dcn * gf + dc_prev_direct;
                     dhz_reg[e] = dh_prev_direct;
-                    if (i > 0 && (uu & 7) == 0) {      // DRAM -> L2 one step ahead (8 units x 4 B = one 32-byte sector per row)
-                        const size_t g1 = g0 - (size_t)B * 4 * D, m1 = (size_t)(i - 1) * B * D + bu;
+                    if (i > 1 && (uu & 7) == 0) {      // DRAM -> L2 two steps ahead (the register prefetch below runs one step ahead)
+                        const size_t g1 = g0 - (size_t)2 * B * 4 * D, m1 = (size_t)(i - 2) * B * D + bu;
                         l2_prefetch(p.gates + g1); l2_prefetch(p.gates + g1 + D); l2_prefetch(p.gates + g1 + 2 * D); l2_prefetch(p.gates + g1 + 3 * D);
                         l2_prefetch(p.cstate + m1); l2_prefetch(p.dh_static + m1);
                         if (p.training && p.mask_h) l2_prefetch(p.mask_h + m1);
@@ -720,6 +732,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
                 }
             }
         }
+        pb_prefetch(i - 1);
         BPROF_MARK(3);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
         BPROF_MARK(4);

@@ -110,15 +110,23 @@ struct BlockArgs {
     int NB, G, Cout, L, act, highway;
 };
 
+// idx -> (nb, g, c, l) of a [NB, G, Cf, L] tensor; 32-bit arithmetic whenever the tensor has fewer than 2^32 elements
+__device__ __forceinline__ void split_index(size_t idx, bool small, int L, int Cf, int G, int& l, int& c, int& g, size_t& nb) {
+    if (small) {
+        const unsigned i = (unsigned)idx, r = i / (unsigned)L, r2 = r / (unsigned)Cf, r3 = r2 / (unsigned)G;
+        l = (int)(i - r * (unsigned)L); c = (int)(r - r2 * (unsigned)Cf); g = (int)(r2 - r3 * (unsigned)G); nb = r3;
+    } else {
+        l = idx % L; c = (idx / L) % Cf; g = (idx / ((size_t)L * Cf)) % G; nb = idx / ((size_t)L * Cf * G);
+    }
+}
+
 // y = dropout(act(bn(conv)));  highway: out[g, c] = y[g, C + c] * sigmoid(y[g, c]) + xin[g, c] * (1 - sigmoid(y[g, c]))
 __global__ void block_fwd_kernel(const BlockArgs p, float* __restrict__ out) {
     const int Cf = p.highway ? p.Cout / 2 : p.Cout;
     const size_t total = (size_t)p.NB * p.G * Cf * p.L;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int l = idx % p.L;
-        const int c = (idx / p.L) % Cf;
-        const int g = (idx / ((size_t)p.L * Cf)) % p.G;
-        const size_t nb = idx / ((size_t)p.L * Cf * p.G);
+        int l, c, g; size_t nb;
+        split_index(idx, total <= 0xffffffffull, p.L, Cf, p.G, l, c, g, nb);
         auto value = [&](int o) {
             const int ch = g * p.Cout + o;
             const size_t ci = (nb * p.G * p.Cout + ch) * p.L + l;
@@ -143,10 +151,8 @@ __global__ void block_bwd_prep_kernel(const BlockArgs p, const float* __restrict
     const int Cf = p.highway ? p.Cout / 2 : p.Cout;
     const size_t total = (size_t)p.NB * p.G * Cf * p.L;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int l = idx % p.L;
-        const int c = (idx / p.L) % Cf;
-        const int g = (idx / ((size_t)p.L * Cf)) % p.G;
-        const size_t nb = idx / ((size_t)p.L * Cf * p.G);
+        int l, c, g; size_t nb;
+        split_index(idx, total <= 0xffffffffull, p.L, Cf, p.G, l, c, g, nb);
         float zs[2], as[2], ks[2];
         size_t cis[2];
         const int nch = p.highway ? 2 : 1;
@@ -199,7 +205,7 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restr
     const size_t total = (size_t)NB * Ct * L;
     const float inv_n = 1.f / (float)(NB * L);
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int ch = (idx / L) % Ct;
+        const int ch = total <= 0xffffffffull ? (int)(((unsigned)idx / (unsigned)L) % (unsigned)Ct) : (int)((idx / L) % Ct);
         const float gm = gamma[(ch / Cout) * affine_gstride + ch % Cout] * invstd[ch];
         float d = dz[idx];
         if (training) d = d - s1[ch] * inv_n - (conv[idx] - mean[ch]) * invstd[ch] * s2[ch] * inv_n;
