@@ -233,39 +233,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // operand packing: fp32 (either orientation) -> bf16 [batch][rows][Kp], K contiguous, Kp % 8 == 0
 // ------------------------------------------------------------------------------------------------
-// One CTA row-slice per (row, 1024-column chunk): no per-element 64-bit division; two-level K resolved per element with 32-bit math.
+// Thread = 8 consecutive k of one row -> ONE 16-byte store (Kp % 8 == 0); rows ride on blockIdx.y: no per-element 64-bit division.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 __global__ void pack_kcontig_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int ld, long long bstride, int rows,
                                     int K, int Kp, int kin, long long kos) {
     const float* s = src + (size_t)blockIdx.z * bstride;
     __nv_bfloat16* d = dst + (size_t)blockIdx.z * rows * Kp;
+    const bool vec = kin == 0 && (ld & 3) == 0 && (bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     for (int r = blockIdx.y; r < rows; r += gridDim.y) {
         const float* srow = s + (size_t)r * ld;
         __nv_bfloat16* drow = d + (size_t)r * Kp;
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Kp; k += gridDim.x * blockDim.x) {
-            float v = 0.f;
-            if (k < K) {
-                if (kin > 0) { const unsigned q = (unsigned)k / (unsigned)kin; v = srow[(size_t)q * kos + (k - (int)q * kin)]; }   // slab q = k / kin
-                else v = srow[k];
+        for (int k = (blockIdx.x * blockDim.x + threadIdx.x) * 8; k < Kp; k += gridDim.x * blockDim.x * 8) {
+            float v[8];
+            if (vec && k + 7 < K) {
+                const float4 a = *reinterpret_cast<const float4*>(srow + k), b = *reinterpret_cast<const float4*>(srow + k + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int kk = k + j;
+                    v[j] = 0.f;
+                    if (kk < K) {
+                        if (kin > 0) { const unsigned q = (unsigned)kk / (unsigned)kin; v[j] = srow[(size_t)q * kos + (kk - (int)q * kin)]; }   // slab q = k / kin
+                        else v[j] = srow[kk];
+                    }
+                }
             }
-            drow[k] = __float2bfloat16_rn(v);
+            *reinterpret_cast<uint4*>(drow + k) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
     }
 }
-// source element (r, k) at src[k*ld + r]: 32 x 32 tile transpose through shared memory
+// source element (r, k) at src[k*ld + r]: 32 (r) x 64 (k) tile transpose through shared memory; reads are 128-byte rows along r,
+// writes are 128-byte rows along k (one bf16 pair per thread).  grid = (ceil(rows / 32), ceil(Kp / 64), batch), block = (32, 8).
 __global__ void pack_transpose_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int ld, long long bstride, int rows,
                                       int K, int Kp) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][33];
     const float* s = src + (size_t)blockIdx.z * bstride;
     __nv_bfloat16* d = dst + (size_t)blockIdx.z * rows * Kp;
-    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 64;
+    for (int j = threadIdx.y; j < 64; j += blockDim.y) {
         const int k = k0 + j, r = r0 + threadIdx.x;
         tile[j][threadIdx.x] = (k < K && r < rows) ? s[(size_t)k * ld + r] : 0.f;
     }
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int r = r0 + j, k = k0 + threadIdx.x;
-        if (r < rows && k < Kp) d[(size_t)r * Kp + k] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+        const int r = r0 + j, k = k0 + 2 * threadIdx.x;
+        if (r < rows && k < Kp)        // Kp is even: the pair (k, k + 1) is inside the padded row
+            *reinterpret_cast<uint32_t*>(d + (size_t)r * Kp + k) = pack_bf16x2(tile[2 * threadIdx.x][j], tile[2 * threadIdx.x + 1][j]);
     }
 }
 
@@ -293,14 +310,17 @@ __global__ void pack_im2col_kcontig_kernel(__nv_bfloat16* __restrict__ dst, cons
         const int ci = r / k, t = r % k, shift = t * dil - pad;
         const float* xrow = x + ((size_t)g * Cin + ci) * L;             // + q * G * Cin * L per sample row
         __nv_bfloat16* drow = d + (size_t)r * Kp;
-        for (int kk = blockIdx.x * blockDim.x + threadIdx.x; kk < Kp; kk += gridDim.x * blockDim.x) {
-            float v = 0.f;
-            if (kk < NB * L) {
-                const unsigned q = (unsigned)kk / (unsigned)L;
-                const int ls = kk - (int)q * L + shift;
-                if (ls >= 0 && ls < L) v = xrow[(size_t)q * G * Cin * L + ls];
+        for (int kk0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8; kk0 < Kp; kk0 += gridDim.x * blockDim.x * 8) {
+            float v[8];
+            unsigned q = (unsigned)kk0 / (unsigned)L;
+            int l = kk0 - (int)q * L;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ls = l + shift;
+                v[j] = (kk0 + j < NB * L && ls >= 0 && ls < L) ? xrow[(size_t)q * G * Cin * L + ls] : 0.f;
+                if (++l == L) { l = 0; ++q; }
             }
-            drow[kk] = __float2bfloat16_rn(v);
+            *reinterpret_cast<uint4*>(drow + kk0) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
     }
 }
@@ -431,10 +451,10 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
 
     auto pack = [&](__nv_bfloat16* dst, const float* src, int ld, long long bstride, int rows, bool kcontig, int nb, long long kos) -> int {
         if (kcontig) {
-            const int gx = Kp > 16384 ? 16 : cdiv(Kp, 1024) > 0 ? cdiv(Kp, 1024) : 1;
+            const int gx = Kp > 32768 ? 16 : cdiv(Kp, 2048);
             pack_kcontig_kernel<<<dim3(gx, rows < 32768 ? rows : 32768, nb), 256, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp, d.kin, kos);
         } else {
-            dim3 grid(cdiv(rows, 32), cdiv(Kp, 32), nb), block(32, 8);
+            dim3 grid(cdiv(rows, 32), cdiv(Kp, 64), nb), block(32, 8);
             pack_transpose_kernel<<<grid, block, 0, st>>>(dst, src, ld, bstride, rows, d.K, Kp);
         }
         B200_LAUNCH_CHECK();
@@ -489,7 +509,7 @@ int gemm_tc_conv(const float* weight, const float* in, float* out, int NB, int G
         pack_conv_weight_kernel<<<gx, 256, 0, st>>>(pa, weight, G, Cout, Cin, k, bwd);
         B200_LAUNCH_CHECK();
         // position-major copy: element (row = l, k = channel) of sample n at in[n][channel][l]
-        dim3 grid(cdiv(L, 32), cdiv(Ctot, 32), NB), block(32, 8);
+        dim3 grid(cdiv(L, 32), cdiv(Ctot, 64), NB), block(32, 8);
         pack_transpose_kernel<<<grid, block, 0, st>>>(pb, in, L, (long long)Ctot * L, L, Ctot, Ctot);
         B200_LAUNCH_CHECK();
     }
@@ -525,10 +545,10 @@ int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int
     __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
     __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
     {
-        pack_kcontig_kernel<<<dim3(Kp > 16384 ? 16 : cdiv(Kp, 1024), Cout, G), 256, 0, st>>>(pa, dz, L, (long long)Cout * L, Cout, K, Kp, L,
+        pack_kcontig_kernel<<<dim3(Kp > 32768 ? 16 : cdiv(Kp, 2048), Cout, G), 256, 0, st>>>(pa, dz, L, (long long)Cout * L, Cout, K, Kp, L,
                                                                                              (long long)G * Cout * L);
         B200_LAUNCH_CHECK();
-        pack_im2col_kcontig_kernel<<<dim3(Kp > 16384 ? 16 : cdiv(Kp, 1024), R, G), 256, 0, st>>>(pb, x, NB, G, Cin, L, k, dil, pad, Kp);
+        pack_im2col_kcontig_kernel<<<dim3(Kp > 32768 ? 16 : cdiv(Kp, 2048), R, G), 256, 0, st>>>(pb, x, NB, G, Cin, L, k, dil, pad, Kp);
         B200_LAUNCH_CHECK();
     }
     CUtensorMap tmA, tmB;
