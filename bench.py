@@ -175,6 +175,15 @@ def cpu_oracle_frames_per_s(a, steps, warmup, sample_frames=24):
     return B * T / med, med, cores, sample
 
 
+def config_dict(a, world, B, L, T):
+    """`config` of the JSON line: the same for this framework's arm and the reference arm."""
+    return {'workload': f'{a.config} train fwd+bwd, B={B}/GPU L={L} T={T} ({a.regularization} cells), tf=1.0',
+            'global_batch': world * B, 'parallelism': f'dp{world}',
+            'precision': 'bf16 tensor-core operands, fp32 accumulate / master weights / states' if a.precision == 'bf16' else 'fp32',
+            'l2': 'per-step working set (~5 GB of activations) >> 126 MB L2, no flush needed',
+            'note': 'batch 64 is invalid for the 10-language grouped encoder (B % G == 0); shipped batch 60 used'}
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -183,7 +192,7 @@ def run_reference(a):
     hp, B, L, T = workload(a)
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic', 'config': {'workload': f'{a.config} train fwd+bwd, B={B} L={L} T={T} ({a.regularization} cells)'},
+            'data': 'synthetic', 'config': dict(config_dict(a, 1, B, L, T), precision='fp32 (reference arm: CPU oracle port)'),
             'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -320,11 +329,7 @@ def run_b200(a):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': {'workload': f'{a.config} train fwd+bwd, B={B}/GPU L={L} T={T} ({a.regularization} cells), tf=1.0',
-                           'global_batch': world * B, 'parallelism': f'dp{world}',
-                           'precision': 'bf16 tensor-core operands, fp32 accumulate / master weights / states' if a.precision == 'bf16' else 'fp32',
-                           'l2': 'per-step working set (~5 GB of activations) >> 126 MB L2, no flush needed',
-                           'note': 'batch 64 is invalid for the 10-language grouped encoder (B % G == 0); shipped batch 60 used'},
+                'config': config_dict(a, world, B, L, T),
                 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
                         'loss': loss_val},
