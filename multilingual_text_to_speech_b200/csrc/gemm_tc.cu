@@ -107,6 +107,10 @@ struct TcArgs {
     // rows [n0 + t * conv_dil - conv_pad, + 128) x channels [g * conv_cin + 64 cb, + 64) of sample bz / conv_G in the position-major
     // bf16 copy of the input (TMA zero-fills the rows outside [0, L))
     int conv_cb, conv_dil, conv_pad, conv_G, conv_cin;
+    // split-K (batch == 1 only): blockIdx.z = split; each split multiplies k-blocks [z * kper, (z + 1) * kper) and stores its raw fp32
+    // tile into partial[z][M][N]; a fixed-order reduction kernel applies alpha / beta / bias afterwards
+    int ksplit, kper;
+    float* partial;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -118,9 +122,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN, bz = blockIdx.z;
+    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+    const int bz = p.ksplit > 1 ? 0 : blockIdx.z;
     const int az = p.a_batch_mod > 0 ? bz % p.a_batch_mod : bz;
-    const int nk = (p.K + TBK - 1) / TBK;
+    const int nk_all = (p.K + TBK - 1) / TBK;
+    const int kb_lo = p.ksplit > 1 ? blockIdx.z * p.kper : 0;
+    const int nk = p.ksplit > 1 ? min(p.kper, nk_all - kb_lo) : nk_all;       // k-blocks of this CTA: [kb_lo, kb_lo + nk)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -144,13 +151,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 uint8_t* sa = ring + (size_t)s * STAGE_BYTES;
-                tma_load_3d(sa, &tmA, &full_bar[s], kb * TBK, m0, az);
+                tma_load_3d(sa, &tmA, &full_bar[s], (kb_lo + kb) * TBK, m0, az);
                 if (p.conv_cb > 0) {
-                    const int t = kb / p.conv_cb, cb = kb % p.conv_cb;
+                    const int t = (kb_lo + kb) / p.conv_cb, cb = (kb_lo + kb) % p.conv_cb;
                     tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], (bz % p.conv_G) * p.conv_cin + cb * TBK, n0 + t * p.conv_dil - p.conv_pad,
                                 bz / p.conv_G);
                 } else {
-                    tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], kb * TBK, n0, bz);
+                    tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], (kb_lo + kb) * TBK, n0, bz);
                 }
             }
         }
@@ -189,34 +196,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      __uint_as_float(r[4 * j + 3]));
         }
         __syncwarp();
-        float* cbase = p.C + (size_t)bz * p.strideC;
+        const bool part = p.ksplit > 1;
+        float* cbase = part ? p.partial + (size_t)blockIdx.z * p.M * p.N : p.C + (size_t)bz * p.strideC;
+        const int ldc = part ? p.N : p.ldc;
+        const float alpha = part ? 1.f : p.alpha, beta = part ? 0.f : p.beta;
+        const float* bias = part ? nullptr : p.bias;
         const int rows = min(32, p.M - (m0 + warp * 32));
         const int n = n0 + 4 * lane;
-        const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0) && (n0 + TBN <= p.N);   // warp-uniform
+        const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0) && (n0 + TBN <= p.N);   // warp-uniform
         if (vec) {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) bv = make_float4(p.bias[n], p.bias[n + 1], p.bias[n + 2], p.bias[n + 3]);
+            if (bias) bv = make_float4(bias[n], bias[n + 1], bias[n + 2], bias[n + 3]);
 #pragma unroll 4
             for (int rr = 0; rr < rows; ++rr) {
                 const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)rr * STG_LD + 4 * lane);
-                float4* cp = reinterpret_cast<float4*>(cbase + (size_t)(m0 + warp * 32 + rr) * p.ldc + n);
-                float4 v = make_float4(fmaf(p.alpha, a.x, bv.x), fmaf(p.alpha, a.y, bv.y), fmaf(p.alpha, a.z, bv.z), fmaf(p.alpha, a.w, bv.w));
-                if (p.beta != 0.f) {
+                float4* cp = reinterpret_cast<float4*>(cbase + (size_t)(m0 + warp * 32 + rr) * ldc + n);
+                float4 v = make_float4(fmaf(alpha, a.x, bv.x), fmaf(alpha, a.y, bv.y), fmaf(alpha, a.z, bv.z), fmaf(alpha, a.w, bv.w));
+                if (beta != 0.f) {
                     const float4 o = *cp;
-                    v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y); v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+                    v.x = fmaf(beta, o.x, v.x); v.y = fmaf(beta, o.y, v.y); v.z = fmaf(beta, o.z, v.z); v.w = fmaf(beta, o.w, v.w);
                 }
                 *cp = v;
             }
         } else {
             for (int rr = 0; rr < rows; ++rr) {
-                float* crow = cbase + (size_t)(m0 + warp * 32 + rr) * p.ldc;
+                float* crow = cbase + (size_t)(m0 + warp * 32 + rr) * ldc;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int nn = n0 + j * 32 + lane;
                     if (nn < p.N) {
-                        float v = p.alpha * stg[(size_t)rr * STG_LD + j * 32 + lane];
-                        if (p.bias) v += p.bias[nn];
-                        if (p.beta != 0.f) v += p.beta * crow[nn];
+                        float v = alpha * stg[(size_t)rr * STG_LD + j * 32 + lane];
+                        if (bias) v += bias[nn];
+                        if (beta != 0.f) v += beta * crow[nn];
                         crow[nn] = v;
                     }
                 }
@@ -283,6 +294,23 @@ __global__ void pack_transpose_kernel(__nv_bfloat16* __restrict__ dst, const flo
         const int r = r0 + j, k = k0 + 2 * threadIdx.x;
         if (r < rows && k < Kp)        // Kp is even: the pair (k, k + 1) is inside the padded row
             *reinterpret_cast<uint32_t*>(d + (size_t)r * Kp + k) = pack_bf16x2(tile[2 * threadIdx.x][j], tile[2 * threadIdx.x + 1][j]);
+    }
+}
+
+// C = alpha * sum_z partial[z] + beta * C + bias   (fixed order over the splits: deterministic)
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, const float* __restrict__ bias, int M, int N,
+                                        int ldc, int ksplit, float alpha, float beta) {
+    const size_t total = (size_t)M * N;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int n = idx % N;
+        const size_t m = idx / N;
+        float s = 0.f;
+        for (int z = 0; z < ksplit; ++z) s += partial[(size_t)z * total + idx];
+        s *= alpha;
+        if (bias) s += bias[n];
+        float* c = C + m * ldc + n;
+        if (beta != 0.f) s += beta * *c;
+        *c = s;
     }
 }
 
@@ -471,15 +499,41 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     a.C = d.C; a.bias = d.bias; a.M = d.M; a.N = d.N; a.K = d.K; a.ldc = d.ldc; a.alpha = d.alpha; a.beta = d.beta;
     a.batch = d.batch; a.a_batch_mod = d.a_batch_mod; a.strideC = d.strideC;
     a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
+    a.ksplit = 1; a.kper = 0; a.partial = nullptr;
+    {   // few output tiles and a long K (weight gradients over all (step, utterance) rows): split K over the idle SMs
+        const int tiles = cdiv(d.N, TBN) * cdiv(d.M, TBM), nk = cdiv(d.K, TBK);
+        if (d.batch == 1 && tiles <= 37 && nk >= 64) {
+            int want = 148 / tiles;
+            if (want > nk / 16) want = nk / 16;
+            if (want > 32) want = 32;
+            if (want >= 2) {
+                const int kper = cdiv(nk, want), splits = cdiv(nk, kper);
+                const size_t pbytes = (size_t)splits * d.M * d.N * 4;
+                // the partial tiles live at the END of the scratch, clear of the packed (and cached) operands
+                const size_t hi = (g_cache_on ? g_cache_off : 0) + (pack_a ? a_bytes : 0) + (pack_b ? b_bytes : 0);
+                if (splits >= 2 && hi + pbytes + 1024 <= g_scratch.bytes) {
+                    a.ksplit = splits; a.kper = kper;
+                    a.partial = reinterpret_cast<float*>(g_scratch.ptr + ((g_scratch.bytes - pbytes) & ~(size_t)1023));
+                }
+            }
+        }
+    }
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     static bool configured = false;
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid(cdiv(d.N, TBN), cdiv(d.M, TBM), d.batch);
+    dim3 grid(cdiv(d.N, TBN), cdiv(d.M, TBM), a.ksplit > 1 ? a.ksplit : d.batch);
     gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
     B200_LAUNCH_CHECK();
+    if (a.ksplit > 1) {
+        const size_t total = (size_t)d.M * d.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(a.partial, d.C, d.bias, d.M, d.N, d.ldc, a.ksplit, d.alpha, d.beta);
+        B200_LAUNCH_CHECK();
+    }
     *handled = true;
     return B200TTS_OK;
 }
@@ -520,6 +574,7 @@ int gemm_tc_conv(const float* weight, const float* in, float* out, int NB, int G
     a.C = out; a.bias = nullptr; a.M = Mrows; a.N = L; a.K = K; a.ldc = L; a.alpha = 1.f; a.beta = beta;
     a.batch = NB * G; a.a_batch_mod = G; a.strideC = (long long)Mrows * L;
     a.conv_cb = Cred / TBK; a.conv_dil = bwd ? -dil : dil; a.conv_pad = bwd ? -pad : pad; a.conv_G = G; a.conv_cin = Cred;
+    a.ksplit = 1; a.kper = 0; a.partial = nullptr;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(L, TBN), cdiv(Mrows, TBM), NB * G);
@@ -558,6 +613,7 @@ int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int
     a.C = dweight; a.bias = nullptr; a.M = Cout; a.N = R; a.K = K; a.ldc = R; a.alpha = 1.f; a.beta = 1.f;
     a.batch = G; a.a_batch_mod = 0; a.strideC = (long long)Cout * R;
     a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
+    a.ksplit = 1; a.kper = 0; a.partial = nullptr;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(R, TBN), cdiv(Cout, TBM), G);

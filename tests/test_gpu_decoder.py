@@ -148,6 +148,7 @@ def test_decoder_bf16_perf_mode(kw):
 @pytest.mark.parametrize('M,N,K,ta,tb', [
     (256, 256, 256, False, True), (256, 384, 512, False, True), (300, 260, 513, False, True), (1000, 4096, 1312, False, True),
     (4096, 288, 640, True, False), (513, 130, 2000, True, True), (200, 1000, 96, False, False),
+    (128, 1024, 20000, True, False), (81, 1312, 9000, True, False),        # few tiles, long K: split-K over the idle SMs (+ reduction launch)
 ])
 def test_gemm_tcgen05_path(M, N, K, ta, tb):
     """tcgen05 / TMEM / TMA GEMM (gemm_tc.cu) against fp64 on bf16-rounded operands, and against the mma.sync kernel."""
@@ -171,6 +172,6 @@ def test_gemm_tcgen05_path(M, N, K, ta, tb):
     finally:
         _lib.set_tensor_core_gemm(True)
         _lib.set_precision('fp32')
-    assert used == 3, f'expected pack + pack + tcgen05 kernel, saw {used} launches'
+    assert used in (3, 4), f'expected pack + pack + tcgen05 kernel (+ split-K reduction), saw {used} launches'
     assert_close(out, ref, 1e-4, 2e-4 * (K ** 0.5), f'tcgen05 gemm {M}x{N}x{K}')
     assert_close(out, out2, 1e-4, 2e-4 * (K ** 0.5), 'tcgen05 vs mma.sync')
