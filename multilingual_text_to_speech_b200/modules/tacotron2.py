@@ -128,9 +128,29 @@ class Decoder(torch.nn.Module):
                 masks[name] = MaskSource.keep_mask(name, (T, B, D), rate, device)
         return {k: v for k, v in masks.items() if v is not None}
 
+    @staticmethod
+    def _stop_cut(stop_logits, stop_frames):
+        """Number of frames the reference's inference loop returns (tacotron2.py:201-207): the frame on which the stop
+        token (sigmoid >= 0.5, i.e. logit >= 0) has fired for the (stop_frames + 1)-th time, else all frames."""
+        remaining = -1
+        for i, fired in enumerate((stop_logits >= 0).tolist()):
+            if not fired:
+                continue
+            if remaining == -1:
+                remaining = stop_frames
+                continue
+            remaining -= 1
+            if remaining == 0:
+                return i + 1
+        return len(stop_logits)
+
     def _decode(self, encoded_input, mask, target, teacher_forcing_ratio, speaker, language):
-        if target is None:
-            raise NotImplementedError('batch-1 free-running inference with early stop is a "next" row (SURVEY 8f.2)')
+        inference = target is None
+        if inference:
+            # free-running decode over max_frames (every step feeds its own previous frame through the prenet inside the fused op),
+            # trimmed afterwards exactly where the reference's loop stops: frames up to the cut do not depend on later ones
+            target = torch.zeros(encoded_input.shape[0], self._output_dim, self._max_frames, device=encoded_input.device)
+            teacher_forcing_ratio = 0.0
         if hp.multi_speaker and self._speaker_embedding is not None:
             encoded_input = self._add_conditional_embedding(encoded_input, self._speaker_embedding, speaker)
         if hp.multi_language and self._language_embedding is not None:
@@ -144,11 +164,17 @@ class Decoder(torch.nn.Module):
         else:
             teacher = (np.random.default_rng(MaskSource.seed + MaskSource.counter).random(T) > (1 - teacher_forcing_ratio)).astype(np.uint8)
             MaskSource.counter += 1
+        if inference:
+            teacher = np.zeros(T, dtype=np.uint8)
         teacher = None if teacher.all() else teacher
         kind, rate_h, rate_c = self._cell_config()
         cfg = F.DecoderConfig(kind, self.training, rate_h, rate_c, self._prenet._dropout_rate, self._masks(B, T, device, teacher), teacher)
         lengths = mask.sum(dim=1).to(torch.int32)
-        return F.decoder_forward(cfg, encoded_input, target, lengths, self._param_list())
+        spectrogram, stop, alignment = F.decoder_forward(cfg, encoded_input, target, lengths, self._param_list())
+        if inference and B == 1:
+            cut = self._stop_cut(stop[0].detach().float().cpu(), hp.stop_frames)
+            spectrogram, stop, alignment = spectrogram[:, :cut], stop[:, :cut], alignment[:, :cut]
+        return spectrogram, stop, alignment
 
     def forward(self, encoded_input, encoded_lenghts, target, teacher_forcing_ratio, speaker, language):
         ml = encoded_input.size(1)
@@ -157,7 +183,8 @@ class Decoder(torch.nn.Module):
 
     def inference(self, encoded_input, speaker, language):
         mask = lengths_to_mask(torch.LongTensor([encoded_input.size(1)]).to(encoded_input.device))
-        spectrogram, _, _ = self._decode(encoded_input, mask, None, 0.0, speaker, language)
+        with torch.no_grad():
+            spectrogram, _, _ = self._decode(encoded_input, mask, None, 0.0, speaker, language)
         return spectrogram
 
 
@@ -246,7 +273,21 @@ class Tacotron(torch.nn.Module):
         return post_prediction, pre_prediction, stop_token, alignment, speaker_prediction, encoder_output
 
     def inference(self, text, speaker=None, language=None):
-        raise NotImplementedError('synthesize.py-style batch-1 inference is a "next" row (SURVEY 8f.2)')
+        """synthesize.py entry point (tacotron2.py:387-408): text int64 [L], speaker int64 [1] | None, language int64 [1] |
+        float [1, L, G] (per-character language mixing) | None -> post-net spectrogram [num_mels, T']."""
+        text = text.unsqueeze(0)                     # pretend having a batch of size 1
+        if speaker is not None and speaker.dim() == 1:
+            speaker = speaker.unsqueeze(1).expand((-1, text.size(1)))
+        if language is not None and language.dim() == 1:
+            language = language.unsqueeze(1).expand((-1, text.size(1)))
+        embedded = F.embedding(self._embedding.weight, text, padding_idx=0)
+        encoded = self._encoder(embedded, torch.LongTensor([text.size(1)]).to(text.device), language)
+        if language is not None and language.dim() == 3:
+            language = torch.argmax(language, dim=2)  # one-hot into indices for the decoder's language embedding
+        prediction = self._decoder.inference(encoded, speaker, language)
+        prediction = prediction.transpose(1, 2)
+        post_prediction = self._postnet(prediction, torch.LongTensor([prediction.size(2)]))
+        return post_prediction.squeeze(0)
 
 
 class TacotronLoss(torch.nn.Module):
