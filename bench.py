@@ -264,11 +264,13 @@ def run_b200(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), loss_val
 
-    for _ in range(max(a.warmup, 3)):
-        step(resident)
+    # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up: its NVML initialisation briefly contends with
+    # the CUDA driver, which must not land inside the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(a.warmup, 3)):
+        step(resident)
     F.PROFILE.clear()
     F.PROFILE['enabled'] = True
     n0 = _lib.launch_count()
