@@ -229,6 +229,14 @@ int b200tts_bilstm_backward(const b200tts_bilstm_shape* shape, const b200tts_bil
 /* ---- dropout-mask generation (counter-based RNG; replaces the Philox draws inside F.dropout) ---- */
 int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream);
 
+/* ---- optimizer step on flat buffers: clip_grad_norm_ + torch.optim.Adam with coupled L2 decay (train.py:84-85, 260-271) ----
+ * p, g, m, v: n fp32 elements each (the flat parameter buffer, the flat all-reduced gradient, Adam moments); g is overwritten with
+ * the clipped gradient; max_norm <= 0 disables clipping; step counts from 1; scratch holds b200tts_adam_clip_scratch_floats()
+ * floats, scratch[0] = gradient norm before clipping, scratch[1] = applied clip coefficient (device values after the call). */
+size_t b200tts_adam_clip_scratch_floats(void);
+int b200tts_adam_clip_step(float* p, float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, float max_norm, int step, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,9 @@ SIGNATURES = {
     'b200tts_generator_backward': (c_int, [c_int, c_int, c_int, c_longlong] + [c_void_p] * 12),
     'b200tts_embedding_forward': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     'b200tts_embedding_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    'b200tts_adam_clip_scratch_floats': (c_size_t, []),
+    'b200tts_adam_clip_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float, c_float,
+                                       c_int, c_void_p, c_void_p]),
     'b200tts_bilstm_saved_bytes': (c_size_t, [POINTER(BiLSTMShape)]),
     'b200tts_bilstm_workspace_bytes': (c_size_t, [POINTER(BiLSTMShape)]),
     'b200tts_bilstm_forward': (c_int, [POINTER(BiLSTMShape), POINTER(BiLSTMParams), c_void_p, c_void_p, c_void_p, c_void_p,

@@ -104,6 +104,9 @@ __global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsi
 namespace b200tts {
 size_t decoder_bwd_profile_offset(const b200tts_decoder_shape& s, int which);
 void set_tc_scratch(void* ptr, size_t bytes);
+size_t adam_clip_scratch_floats();
+int adam_clip_step_impl(float* p, float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        float max_norm, int step, float* scratch, cudaStream_t st);
 void set_tc_enabled(int on);
 int tc_enabled();
 }
@@ -271,6 +274,13 @@ int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t se
     fill_keep_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, key);
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
+}
+
+size_t b200tts_adam_clip_scratch_floats(void) { return adam_clip_scratch_floats(); }
+int b200tts_adam_clip_step(float* p, float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, float max_norm, int step, float* scratch, void* stream) {
+    B200_TRY(require_device());
+    return adam_clip_step_impl(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, max_norm, step, scratch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

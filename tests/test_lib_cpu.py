@@ -48,3 +48,19 @@ def test_compute_without_gpu_fails_loudly(lib):
     from multilingual_text_to_speech_b200 import functional as F
     with pytest.raises(_lib.B200TTSError):
         F.gemm(a, a)
+
+
+def test_fused_adam_needs_gpu():
+    """The optimizer step has no CPU fallback either."""
+    import pytest
+    import torch
+    from multilingual_text_to_speech_b200 import _lib
+    from multilingual_text_to_speech_b200.optim import FlatParams, FusedAdam
+    from multilingual_text_to_speech_b200.distributed import GradBucket
+    model = torch.nn.Linear(4, 3)
+    flat, bucket = FlatParams(model), GradBucket(model, 1)
+    assert model.weight.data_ptr() == flat.flat.data_ptr() and model.weight.grad.data_ptr() == bucket.flat.data_ptr()
+    opt = FusedAdam(flat, bucket, lr=1e-3, lr_decay_every=10, lr_decay=0.5)
+    assert opt.current_lr() == 1e-3
+    with pytest.raises(_lib.B200TTSError):
+        opt.step()
