@@ -42,10 +42,25 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ for sm_100a and link libb200tts.so next to the package."""
+    """Compile every .cu under csrc/ for sm_100a and link libb200tts.so next to the package.
+
+    Safe under concurrent callers (torchrun starts one process per GPU, each of which calls build()): an exclusive file lock
+    serialises the builders and staleness is re-checked under the lock, so at most one of them compiles."""
     if not force and not is_stale():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    import fcntl
+    with open(os.path.join(OBJ, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     nvcc = _nvcc()
     hdr_time = max(os.path.getmtime(h) for h in headers() + [os.path.abspath(__file__)])
 
