@@ -7,16 +7,18 @@ from ..params.params import Params as hp
 
 
 def lengths_to_mask(lengths, max_length=None):
-    """Boolean mask [B, max_length] with True at positions < length."""
-    ml = torch.max(lengths) if max_length is None else max_length
-    return torch.arange(ml, device=lengths.device)[None, :] < lengths[:, None]
+    """Boolean mask [B, max_length] with True at positions < length (the kernels take the lengths themselves; the mask only
+    exists for callers of the module surface)."""
+    width = int(lengths.max()) if max_length is None else int(max_length)
+    positions = torch.arange(width, device=lengths.device)
+    return positions.unsqueeze(0).lt(lengths.unsqueeze(1))
 
 
 def to_gpu(x):
-    if x is None:
-        return x
-    x = x.contiguous()
-    return x.cuda(non_blocking=True) if torch.cuda.is_available() else x
+    """Contiguous copy on the current CUDA device (asynchronous for pinned sources); None and CPU-only hosts pass through."""
+    if x is None or not torch.cuda.is_available():
+        return x if x is None else x.contiguous()
+    return x.contiguous().cuda(non_blocking=True)
 
 
 def remove_dataparallel_prefix(state_dict):
