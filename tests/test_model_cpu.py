@@ -42,3 +42,30 @@ def test_no_cpu_fallback():
     i = g.inputs
     with pytest.raises(_lib.B200TTSError):
         model(i['text'], i['text_length'], i['target'], i['target_length'], None, None, 1.0)
+
+
+def test_inference_stop_rule_matches_reference_loop():
+    """Decoder._stop_cut reproduces where the reference's inference loop returns (modules/tacotron2.py:201-207): the frame on which
+    the stop token fires for the (stop_frames + 1)-th time -- not necessarily consecutively -- else all frames."""
+    import torch
+    from multilingual_text_to_speech_b200.modules.tacotron2 import Decoder
+
+    def reference_loop(stop_logits, stop_frames_hp):
+        stop_frames = -1
+        for i in range(len(stop_logits)):
+            if torch.sigmoid(stop_logits[i]).ge(0.5):
+                if stop_frames == -1:
+                    stop_frames = stop_frames_hp
+                    continue
+                stop_frames -= 1
+                if stop_frames == 0:
+                    return i + 1
+        return len(stop_logits)
+
+    g = torch.Generator().manual_seed(11)
+    for trial in range(100):
+        x = torch.randn(80, generator=g) * 2 + (torch.arange(80) - 40) * 0.15
+        for sf in (1, 5):
+            assert Decoder._stop_cut(x, sf) == reference_loop(x, sf)
+    assert Decoder._stop_cut(torch.full((10,), -3.0), 5) == 10                      # never fires: all frames
+    assert Decoder._stop_cut(torch.tensor([-1.0, 2.0, 2.0, -1.0, 2.0, 2.0]), 3) == 6   # fires at 1 (arms), 2, 4, 5 -> cut after frame 5
