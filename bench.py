@@ -3,7 +3,7 @@
 
     python bench.py --gpus 1 --steps 5 --warmup 3                    # this framework, 1 GPU
     torchrun --nproc-per-node N ... bench.py --gpus N ...             # data parallel, one rank per GPU, NCCL all-reduce
-    python bench.py --impl reference --steps 2 --warmup 1             # CPU reference arm (oracle port, host cores)
+    python bench.py --impl reference --steps 2 --warmup 1             # CPU reference arm (unmodified reference from baseline/_ref, host cores)
 
 A "step" is one training step of the named configuration on one synthetic batch per GPU: embedding -> encoder ->
 fused decoder -> postnet -> TacotronLoss -> backward (-> gradient all-reduce when N > 1).  Optimizer, data loading
@@ -37,6 +37,10 @@ def parse():
     ap.add_argument('--frames', type=int, default=900)
     ap.add_argument('--regularization', default='zoneout', choices=['zoneout', 'dropout'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-frames', type=int, default=100,
+                    help='frames per utterance of the CPU reference sample (reference arm / cpu_baseline): the first N of --frames')
+    ap.add_argument('--no-extra-baselines', action='store_true',
+                    help='skip the cfg-1 CPU timing and the eager-PyTorch-on-B200 timing of the unmodified reference (N=1 only)')
     ap.add_argument('--breakdown', default='', help='write a per-kernel device-time table of one extra (untimed) step to this file')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help="bf16: tensor-core operands, fp32 master/state (BASELINE configs[1]); fp32: exact parity mode")
@@ -81,11 +85,58 @@ def synth_batch(hp, B, L, T, seed, device, pin=False):
 # --------------------------------------------------------------------------------------------------
 # roofline bookkeeping (SURVEY.md section 8d formula: naive algorithmic bytes of one decoder step, forward)
 # --------------------------------------------------------------------------------------------------
-def bytes_fwd_step(B, L, M, D=1024, P=256, A=128, C=32, K=31, N=80, w=4, a=4):
-    W = (4 * D * (P + M) + 4 * D * D + 8 * D) + (4 * D * (D + M) + 4 * D * D + 8 * D) + (A * D + A * C + C * K + 2 * A) + \
-        (N * (D + M) + N + (D + M) + 1)
-    act = B * ((L * A + L * M + 2 * L + P + 4 * D) + (4 * D + N + 1 + 2 * L))
-    return w * W + a * act
+def step_elements(B, L, M, D=1024, P=256, A=128, C=32, K=31, N=80):
+    """SURVEY.md section 8d, ELEMENTS touched by one decoder step (forward, whole batch, naive formulation), split by the persistent
+    loop that owns them: (weights, activations) of the attention loop (attention-LSTM + location-sensitive attention) and of the
+    generator loop (generator LSTM + frame / stop projections).  Their sum is W_step / ACT_step of the survey."""
+    w_att = (4 * D * (P + M) + 4 * D * D + 8 * D) + (A * D + A * C + C * K + 2 * A)
+    a_att = B * ((L * A + L * M + 2 * L + P + 2 * D) + (2 * D + 2 * L))
+    w_gen = (4 * D * (D + M) + 4 * D * D + 8 * D) + (N * (D + M) + N + (D + M) + 1)
+    a_gen = B * (2 * D + (2 * D + N + 1))
+    return {'att': (w_att, a_att), 'gen': (w_gen, a_gen)}
+
+
+def bytes_fwd_step(B, L, M, D=1024, P=256, A=128, C=32, K=31, N=80, w=4, a=4, part=None):
+    el = step_elements(B, L, M, D, P, A, C, K, N)
+    parts = [part] if part else ['att', 'gen']
+    return sum(w * el[p][0] + a * el[p][1] for p in parts)
+
+
+# which share of the per-step bytes a timed kernel is responsible for, and how many forward-equivalents it is (SURVEY 8d convention:
+# the backward pass counts as 2 x forward -- one pass for dX, one for dW)
+KERNEL_SHARE = {'lstm_loop_tc_kernel<att>': ('att', 1), 'lstm_loop_tc_kernel<gen>': ('gen', 1),
+                'att_bwd_loop_kernel': ('att', 2), 'lstm_bwd_loop_tc_kernel': ('gen', 2), 'lstm_bwd_loop_kernel': ('gen', 2)}
+
+
+def roofline_entry(name, ms, T, dims, peak, precision, traffic=None, fwd_equiv=1, part=None, note=None):
+    """Fractions of the measured HBM peak for `ms` of device time against T x (share of BYTES_fwd_step) x fwd_equiv, at three element
+    widths: the run's own (`frac`: bf16 runs are judged against the bf16 column of SURVEY 8d, w = a = 2), bf16 weights + fp32
+    activations (`frac_mixed`), and the fp32-naive figure (`frac_fp32_naive`)."""
+    def alg(w, a):
+        return fwd_equiv * T * bytes_fwd_step(*dims, w=w, a=a, part=part)
+    sec = ms * 1e-3
+    own = (2, 2) if precision == 'bf16' else (4, 4)
+    e = {'kernel': name, 'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'avg_launch_ms': ms,
+         'algorithmic_bytes_per_launch': alg(*own), 'achieved': alg(*own) / sec / 1e9, 'frac': alg(*own) / sec / 1e9 / peak,
+         'frac_mixed': alg(2, 4) / sec / 1e9 / peak if precision == 'bf16' else None,
+         'frac_fp32_naive': alg(4, 4) / sec / 1e9 / peak, 'traffic': traffic,
+         'element_width': 'w=a=2 B (bf16 column of SURVEY 8d)' if precision == 'bf16' else 'w=a=4 B (fp32)',
+         'algorithmic_bytes_formula': f'{fwd_equiv} x T x BYTES_fwd_step' + (f'[{part} loop share]' if part else '') + ' (SURVEY 8d)'}
+    if note:
+        e['note'] = note
+    return e
+
+
+def ncu_traffic(B, L, T):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the loop kernels from the committed ncu capture of the
+    CURRENT kernels at this shape (profiles/r2/ncu_traffic.json, written by tools/ncu_traffic.py from the raw capture); {} if none."""
+    path = os.path.join(ROOT, 'profiles', 'r2', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return {}
+    d = json.load(open(path))
+    if (d.get('B'), d.get('L'), d.get('T')) != (B, L, T):
+        return {}
+    return {k: v['dram_read'] + v['dram_write'] for k, v in d.get('kernels', {}).items()}
 
 
 def measured_peaks():
@@ -184,18 +235,79 @@ def config_dict(a, world, B, L, T):
             'note': 'batch 64 is invalid for the 10-language grouped encoder (B % G == 0); shipped batch 60 used'}
 
 
+def reference_cpu(a, steps, warmup):
+    """The reference's own CPU implementation of the path on the host cores, on a BOUNDED sample of the workload: the same batch
+    size / text length, but only the first `--ref-frames` of the T frames per utterance (a full T = 900 step of B = 60 takes ~1 min).
+    baseline/_ref (the unmodified reference) when installed, else the oracle port."""
+    hp, B, L, T = workload(a)
+    Ts = min(a.ref_frames, T)
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import reference_runner as R
+    if R.available():
+        r = R.time_cpu(a.config, a.regularization, B, L, Ts, steps, warmup)
+        # second point at half the frames -> fixed (encoder, per-call) and per-frame cost -> what the full-T step would run at; the
+        # truncated sample UNDER-states the reference by the share of the fixed cost (reported, never used as `value`)
+        extra = None
+        if Ts >= 20:
+            r2 = R.time_cpu(a.config, a.regularization, B, L, Ts // 2, 1, 1, threads=r['cores'])
+            per_frame = (r['s_per_step'] - r2['s_per_step']) / (Ts - Ts // 2)
+            fixed = r['s_per_step'] - per_frame * Ts
+            if per_frame > 0:
+                extra = {'second_sample_frames': Ts // 2, 'second_sample_s_per_step': r2['s_per_step'], 'fixed_s': fixed,
+                         's_per_frame_step': per_frame, 'extrapolated_full_T_frames_per_s': B * T / (fixed + per_frame * T)}
+        sample = (f'UNMODIFIED reference (baseline/_ref: Tacotron.forward + TacotronLoss + backward, torch {_torch_version()} CPU fp32), '
+                  f'{a.config} B={B} L={L}, first {Ts} of T={T} frames per utterance, {steps} timed step(s), threads scanned {r["thread_scan"]}')
+        return {'value': r['frames_per_s'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'reference', 'sample': sample,
+                'host_cores': os.cpu_count(), 'sample_frames': Ts, 'extrapolation': extra}, r['s_per_step']
+    fps, med, cores, sample = cpu_oracle_frames_per_s(a, steps, warmup, sample_frames=min(Ts, 24))
+    return {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample + ' (baseline/_ref not installed)',
+            'host_cores': os.cpu_count(), 'sample_frames': min(Ts, 24)}, med
+
+
+def _torch_version():
+    import torch
+    return torch.__version__
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    fps, med, cores, sample = cpu_oracle_frames_per_s(a, a.steps, a.warmup)
+    base, med = reference_cpu(a, a.steps, a.warmup)
     hp, B, L, T = workload(a)
-    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+    cfg = dict(config_dict(a, 1, B, L, T), precision='fp32 (reference arm: CPU)')
+    cfg['workload'] += f' -- reference arm: bounded sample, first {base["sample_frames"]} of the T={T} frames per utterance'
+    cfg['reference_sample_frames'] = base['sample_frames']
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic', 'config': dict(config_dict(a, 1, B, L, T), precision='fp32 (reference arm: CPU oracle port)'),
-            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
-            'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+            'data': 'synthetic', 'config': cfg, 'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
+
+
+def extra_baselines(a, threads):
+    """the mandated cfg-1 CPU timing (default Params = LJ Speech, B = 16, L = 180, T = 900, full length) and the
+    unmodified reference in eager PyTorch on the B200 (the competitor on the same box) at this run's own workload."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import reference_runner as R
+    if not R.available():
+        return {'unavailable': 'baseline/_ref not installed'}
+    out = {}
+    hp, B, L, T = workload(a)
+    try:
+        r = R.time_cpu('ljspeech', 'dropout', 16, 180, 900, 1, 1, threads=threads)
+        out['cpu_cfg1_ljspeech_B16'] = {'value': r['frames_per_s'], 'unit': UNIT, 'cores': r['cores'], 's_per_step': r['s_per_step'],
+                                        'sample': 'unmodified reference, default Params (LJ Speech), B=16 L=180 T=900 (full), fwd+loss+bwd, 1 warm-up + 1 timed step'}
+    except Exception as exc:      # noqa: BLE001 -- a baseline must never take the bench line down
+        out['cpu_cfg1_ljspeech_B16'] = {'error': repr(exc)[:200]}
+    try:
+        r = R.time_gpu_eager(a.config, a.regularization, B, L, T, steps=1, warmup=1)
+        out['eager_pytorch_b200'] = {'value': r['frames_per_s'], 'unit': UNIT, 's_per_step': r['s_per_step'],
+                                     'sample': f'unmodified reference, eager PyTorch fp32 (ATen / cuDNN / cuBLAS) on cuda:0, {a.config} B={B} L={L} T={T} (full), '
+                                               'fwd+loss+bwd, 1 warm-up + 1 timed step'}
+    except Exception as exc:      # noqa: BLE001
+        out['eager_pytorch_b200'] = {'error': repr(exc)[:200]}
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -273,6 +385,7 @@ def run_b200(a):
         step(resident)
     F.PROFILE.clear()
     F.PROFILE['enabled'] = True
+    _lib.kernel_timing(True)              # CUDA events on the launching stream around the dominant kernels, inside the timed steps
     n0 = _lib.launch_count()
     ncu_range = bool(os.environ.get('B200TTS_NCU_RANGE'))   # `ncu --profile-from-start off`: capture exactly the timed steps
     if ncu_range:
@@ -283,7 +396,10 @@ def run_b200(a):
     launches = _lib.launch_count() - n0
     F.PROFILE['enabled'] = False
     torch.cuda.synchronize()
+    ktimes = _lib.kernel_timing_read()    # {kernel: (total ms, launches)} over the a.steps timed steps
+    _lib.kernel_timing(False)
     dec_ms = [s.elapsed_time(e) for s, e in F.PROFILE.get('decoder_fwd', [])]
+    decb_ms = [s.elapsed_time(e) for s, e in F.PROFILE.get('decoder_bwd', [])]
     ms_e2e, loss_val = timed(a.steps, from_host=True)
     clocks = sampler.stop() if rank == 0 else None
     if a.breakdown and rank == 0:       # CUPTI kernel times of ONE extra step (not part of any reported number)
@@ -315,19 +431,28 @@ def run_b200(a):
         M = hp.encoder_dimension + (hp.speaker_embedding_dimension if hp.multi_speaker else 0) + \
             (hp.language_embedding_dimension if hp.multi_language else 0)
         peak, peak_src = measured_peaks()
-        roof = None
+        dims = (B, L, M, hp.decoder_dimension, hp.prenet_dimension, hp.attention_dimension, hp.attention_location_dimension,
+                hp.attention_kernel_size, hp.num_mels)
+        traffic = ncu_traffic(B, L, T)
+        roofs = []
+        for kname, (tot, cnt) in ktimes.items():
+            if kname in KERNEL_SHARE and cnt:
+                part, eq = KERNEL_SHARE[kname]
+                roofs.append(roofline_entry(kname, tot / cnt, T, dims, peak, a.precision, traffic.get(kname), eq, part))
         if dec_ms:
-            alg = T * bytes_fwd_step(B, L, M)
-            dur = statistics.mean(dec_ms) * 1e-3
-            # DRAM traffic of the two persistent loop kernels per decoder forward, from the committed ncu capture
-            # (profiles/ncu_metrics_loops_r1.txt: 1.04 + 1.59 GB attention loop, 1.02 + 1.38 GB generator loop at this exact shape);
-            # the weights are shared-memory resident, so the traffic is far BELOW the naive algorithmic bytes of SURVEY section 8d
-            traffic = 5.04e9 if (a.precision == 'bf16' and a.config == 'generated_training' and B == 60 and L == 180 and T == 900) else None
-            roof = {'bound': 'hbm', 'achieved': alg / dur / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': alg / dur / 1e9 / peak,
-                    'traffic': traffic, 'kernel': 'decoder forward op (b200tts_decoder_forward): persistent tcgen05/TMA attention-LSTM + attention '
-                    'loop, persistent generator-LSTM loop and the time-batched tcgen05 GEMMs around them, all launches',
-                    'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': dur * 1e3, 'peak_source': peak_src,
-                    'algorithmic_bytes_formula': 'T x BYTES_fwd_step (SURVEY 8d, fp32 naive formulation)'}
+            roofs.append(roofline_entry('decoder forward op (both forward loops + the time-batched GEMMs around them)', statistics.mean(dec_ms),
+                                        T, dims, peak, a.precision, None, 1, None))
+        if decb_ms:
+            roofs.append(roofline_entry('decoder backward op (both reverse loops, post pass, dW / dX GEMMs)', statistics.mean(decb_ms),
+                                        T, dims, peak, a.precision, None, 2, None))
+        roofs.append(roofline_entry('whole training step (encoder, decoder, postnet, loss, backward)', ms / a.steps, T, dims, peak, a.precision,
+                                    None, 3, None, note='3 x T x BYTES_fwd_step: decoder bytes only, the encoder / postnet / loss time counts against them'))
+        loops = [r for r in roofs if r['kernel'] in KERNEL_SHARE]
+        roof = dict(max(loops, key=lambda r: r['avg_launch_ms'])) if loops else (dict(roofs[0]) if roofs else None)
+        if roof:
+            roof['peak_source'] = peak_src
+            roof['why_this_kernel'] = 'largest device time among the kernels of the step (CUDA events around each launch inside the timed steps)'
+            roof['timing'] = {k: {'ms_per_launch': v[0] / max(v[1], 1), 'launches': v[1]} for k, v in ktimes.items()}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic',
@@ -335,10 +460,11 @@ def run_b200(a):
                 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
                         'loss': loss_val},
-                'roofline': roof}
+                'roofline': roof, 'rooflines': roofs}
         if world == 1 and not a.no_cpu_baseline:
-            fps, med, cores, sample = cpu_oracle_frames_per_s(a, 1, 0, sample_frames=16)
-            line['cpu_baseline'] = {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+            line['cpu_baseline'], _ = reference_cpu(a, 1, 0)
+            if not a.no_extra_baselines:
+                line['baselines'] = extra_baselines(a, line['cpu_baseline']['cores'])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

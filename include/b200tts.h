@@ -42,6 +42,13 @@ int b200tts_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 unsigned long long b200tts_launch_count(void);
 
+/* Live kernel timing for bench.py's per-kernel roofline: while enabled, the library brackets its dominant kernels (the four persistent
+ * decoder loops, the attention post pass, the tcgen05 GEMM) with CUDA events on the launching stream.  enable != 0 starts a fresh
+ * collection, 0 stops and clears.  After a device synchronize, kernel_timing_read(index, ...) returns the index-th distinct kernel
+ * name with the summed duration and the number of launches; it returns 1 past the end of the list.                           */
+int b200tts_kernel_timing(int enable);
+int b200tts_kernel_timing_read(int index, char* name, int name_capacity, float* total_ms, int* count);
+
 /* Arithmetic mode of every contraction in the library.  FP32: exact fp32 FFMA kernels (parity gate rtol 1e-3 /
  * atol 1e-4 against the reference).  BF16: operands rounded to bf16, fp32 accumulation on the tensor cores, fp32
  * master weights / states / outputs (BASELINE.json configs[1] "bf16 fwd / fp32 master"; gate: mel L1 < 1e-3).     */

@@ -68,6 +68,8 @@ SIGNATURES = {
     'b200tts_launch_count': (c_ulonglong, []),
     'b200tts_set_precision': (c_int, [c_int]),
     'b200tts_get_precision': (c_int, []),
+    'b200tts_kernel_timing': (c_int, [c_int]),
+    'b200tts_kernel_timing_read': (c_int, [c_int, c_char_p, c_int, POINTER(c_float), POINTER(c_int)]),
     'b200tts_set_scratch': (c_int, [c_void_p, c_size_t]),
     'b200tts_set_tensor_core_gemm': (c_int, [c_int]),
     'b200tts_debug_persist_profile_offset': (c_size_t, [POINTER(DecoderShape)]),
@@ -171,6 +173,25 @@ def set_tensor_core_gemm(enabled):
 
 def get_precision():
     return {v: k for k, v in PRECISIONS.items()}[load().b200tts_get_precision()]
+
+
+def kernel_timing(enable):
+    check(load().b200tts_kernel_timing(int(bool(enable))), 'b200tts_kernel_timing')
+
+
+def kernel_timing_read():
+    """{kernel name: (total ms, launches)} collected since kernel_timing(True); synchronize the device first."""
+    import ctypes
+    lib, out, i = load(), {}, 0
+    while True:
+        name = ctypes.create_string_buffer(128)
+        ms, cnt = c_float(0), c_int(0)
+        st = lib.b200tts_kernel_timing_read(i, name, 128, ctypes.byref(ms), ctypes.byref(cnt))
+        if st == 1:
+            return out
+        check(st, 'b200tts_kernel_timing_read')
+        out[name.value.decode()] = (ms.value, cnt.value)
+        i += 1
 
 
 def launch_count():

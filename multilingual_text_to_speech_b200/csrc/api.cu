@@ -1,6 +1,9 @@
 // extern "C" surface of libb200tts (see include/b200tts.h) + error / launch bookkeeping.
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
+#include <vector>
+#include <string>
 #include "decoder_internal.cuh"
 
 namespace b200tts {
@@ -22,6 +25,34 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
     }
     set_last_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
     return B200TTS_ERR_CUDA;
+}
+
+// ---- named kernel timers -------------------------------------------------------------------------
+namespace {
+struct KSpan { const char* name; cudaEvent_t e0, e1; bool closed; };
+std::atomic<int> g_ktime_on{0};
+std::mutex g_ktime_mu;
+std::vector<KSpan> g_spans;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+void ktimer_start(const char* name, cudaStream_t st) {
+    if (!g_ktime_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_ktime_mu);
+    KSpan s{name, take_event(), take_event(), false};
+    cudaEventRecord(s.e0, st);
+    g_spans.push_back(s);
+}
+void ktimer_stop(const char* name, cudaStream_t st) {
+    if (!g_ktime_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_ktime_mu);
+    for (size_t i = g_spans.size(); i-- > 0;)
+        if (!g_spans[i].closed && g_spans[i].name == name) { cudaEventRecord(g_spans[i].e1, st); g_spans[i].closed = true; return; }
 }
 
 static int require_device() {
@@ -123,6 +154,35 @@ int b200tts_set_precision(int mode) {
     return B200TTS_OK;
 }
 int b200tts_get_precision(void) { return precision_mode(); }
+int b200tts_kernel_timing(int enable) {
+    std::lock_guard<std::mutex> lk(g_ktime_mu);
+    for (auto& s : g_spans) { g_event_pool.push_back(s.e0); g_event_pool.push_back(s.e1); }
+    g_spans.clear();
+    g_ktime_on.store(enable ? 1 : 0);
+    return B200TTS_OK;
+}
+int b200tts_kernel_timing_read(int index, char* name, int name_capacity, float* total_ms, int* count) {
+    // distinct names in first-seen order; the caller synchronises the device first (elapsed times of unfinished spans fail)
+    std::lock_guard<std::mutex> lk(g_ktime_mu);
+    std::vector<const char*> names;
+    for (auto& s : g_spans) {
+        bool seen = false;
+        for (auto n : names) seen = seen || strcmp(n, s.name) == 0;
+        if (!seen) names.push_back(s.name);
+    }
+    if (index < 0 || index >= (int)names.size()) return 1;      // end of list
+    float tot = 0.f; int cnt = 0;
+    for (auto& s : g_spans)
+        if (s.closed && strcmp(s.name, names[index]) == 0) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s.e0, s.e1) != cudaSuccess) { cudaGetLastError(); set_last_error("kernel_timing_read: span of %s not finished (synchronize first)", s.name); return B200TTS_ERR_CUDA; }
+            tot += ms; ++cnt;
+        }
+    if (name && name_capacity > 0) { strncpy(name, names[index], name_capacity - 1); name[name_capacity - 1] = 0; }
+    if (total_ms) *total_ms = tot;
+    if (count) *count = cnt;
+    return B200TTS_OK;
+}
 int b200tts_set_scratch(void* ptr, size_t bytes) {
     if (ptr && (reinterpret_cast<uintptr_t>(ptr) & 1023)) { set_last_error("set_scratch: pointer must be 1024-byte aligned"); return B200TTS_ERR_INVALID; }
     set_tc_scratch(ptr, ptr ? bytes : 0);

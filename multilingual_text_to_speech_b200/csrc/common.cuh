@@ -34,6 +34,16 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line);
         if (_st != B200TTS_OK) return _st;                                          \
     } while (0)
 
+// Named kernel timers (b200tts_kernel_timing): when enabled, CUDA events are recorded on the launching stream around the dominant kernels;
+// bench.py reads per-name totals after a synchronize.  Disabled (the default) they cost one relaxed load.
+void ktimer_start(const char* name, cudaStream_t st);
+void ktimer_stop(const char* name, cudaStream_t st);
+struct KernelTimer {
+    const char* name; cudaStream_t st;
+    KernelTimer(const char* n, cudaStream_t s) : name(n), st(s) { ktimer_start(n, s); }
+    ~KernelTimer() { ktimer_stop(name, st); }
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -10,6 +10,7 @@
 //       writing an fp32 partial [32 x UN] that the next step's P1 sums over the KB K-blocks (deterministic order),
 //   --  grid barrier.
 // Reference semantics: autograd replay of modules/layers.py:18-47 (train.py:83).
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "decoder_internal.cuh"
 
@@ -1100,14 +1101,20 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attrs[2];
-    attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    // profiling aid: ncu cannot capture a launch that is BOTH cooperative and clustered; the kernel carries its own grid barrier, so on an
+    // otherwise idle GPU (all CTAs resident: <= 148, one per SM) the cooperative attribute can be dropped for a capture
+    attrs[0].val.cooperative = getenv("B200TTS_PROFILE_NO_COOP") ? 0 : 1;
     attrs[1].id = cudaLaunchAttributeClusterDimension;          // the attention backward of an utterance runs on a CTA pair
     attrs[1].val.clusterDim.x = 2; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs; cfg.numAttrs = 2;
     int nclusters = 0;
     B200_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg));
     B200_REQUIRE(nclusters * 2 >= grid, "persistent attention backward: only %d CTA pairs can be co-resident, %d needed", nclusters, grid / 2);
-    B200_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
+    {
+        KernelTimer kt("att_bwd_loop_kernel", st);
+        B200_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
+    }
     B200_LAUNCH_CHECK();
     // parallel post pass
     AttPostArgs pp{};
@@ -1118,7 +1125,10 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     B200_CUDA(cudaMemsetAsync(dmemT, 0, (size_t)B * L * A * 4, st));
     B200_CUDA(cudaMemsetAsync(pp.dWcomb_part, 0, (size_t)B * x.MT * A * 32 * 4, st));
     B200_CUDA(cudaMemsetAsync(pp.dv_part, 0, (size_t)B * x.MT * A * 4, st));
-    att_post_kernel<<<B * x.MT, PT, 0, st>>>(pp);
+    {
+        KernelTimer kt("att_post_kernel", st);
+        att_post_kernel<<<B * x.MT, PT, 0, st>>>(pp);
+    }
     B200_LAUNCH_CHECK();
     att_bwd_finish_kernel<<<1, 512, (size_t)A * 32 * 4, st>>>(dw.attn_location, dw.attn_loc_features, dw.attn_energy, pp.dWcomb_part,
                                                              pp.dv_part, w.attn_location, w.attn_loc_features, B * x.MT, A, s.C, s.K);
@@ -1161,7 +1171,10 @@ int persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     B200_REQUIRE(per_sm * sms >= grid, "persistent backward: %d CTAs cannot be co-resident", grid);
     void* params[] = {&a};
-    B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
+    {
+        KernelTimer kt("lstm_bwd_loop_kernel", st);
+        B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
+    }
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
 }

@@ -393,6 +393,7 @@ int tc_persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decode
     B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     B200_REQUIRE(per_sm * sms >= grid, "tcgen05 persistent backward: %d CTAs cannot be co-resident", grid);
     void* params[] = {&tm, &a};
+    KernelTimer kt("lstm_bwd_loop_tc_kernel", st);
     B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PT), params, smem, st));
     B200_LAUNCH_CHECK();
     return B200TTS_OK;

@@ -16,6 +16,7 @@
 // writes it, so the backward pass is unaffected.
 // Reference semantics: modules/tacotron2.py:180-198, modules/layers.py:18-47, modules/attention.py:39-86.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "decoder_internal.cuh"
 
@@ -833,7 +834,10 @@ static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tmH,
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attrs[2];
-    attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    // profiling aid: ncu cannot capture a launch that is BOTH cooperative and clustered; the kernel carries its own grid barrier, so on an
+    // otherwise idle GPU (all CTAs resident: <= 148, one per SM) the cooperative attribute can be dropped for a capture
+    attrs[0].val.cooperative = getenv("B200TTS_PROFILE_NO_COOP") ? 0 : 1;
     cfg.attrs = attrs; cfg.numAttrs = 1;
     if (att) {      // the attention runs on CTA pairs: clusters of 2 (distributed shared memory + cluster barrier)
         B200_REQUIRE(grid % 2 == 0 && grid / 2 >= a.B, "tcgen05 attention loop: %d CTAs cannot form %d pairs", grid, a.B);
@@ -850,6 +854,7 @@ static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tmH,
         B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         B200_REQUIRE(per_sm * sms >= grid, "tcgen05 persistent loop: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, sms);
     }
+    KernelTimer kt(att ? "lstm_loop_tc_kernel<att>" : "lstm_loop_tc_kernel<gen>", st);
     B200_CUDA(cudaLaunchKernelExC(&cfg, fn, params));
     B200_LAUNCH_CHECK();
     return B200TTS_OK;

@@ -525,7 +525,10 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
         configured = true;
     }
     dim3 grid(cdiv(d.N, TBN), cdiv(d.M, TBM), a.ksplit > 1 ? a.ksplit : d.batch);
-    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    {
+        KernelTimer kt("gemm_tc_kernel", st);
+        gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    }
     B200_LAUNCH_CHECK();
     if (a.ksplit > 1) {
         const size_t total = (size_t)d.M * d.N;
@@ -578,7 +581,10 @@ int gemm_tc_conv(const float* weight, const float* in, float* out, int NB, int G
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(L, TBN), cdiv(Mrows, TBM), NB * G);
-    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    {
+        KernelTimer kt("gemm_tc_kernel", st);
+        gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    }
     B200_LAUNCH_CHECK();
     *handled = true;
     return B200TTS_OK;
@@ -617,7 +623,10 @@ int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(R, TBN), cdiv(Cout, TBM), G);
-    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    {
+        KernelTimer kt("gemm_tc_kernel", st);
+        gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
+    }
     B200_LAUNCH_CHECK();
     *handled = true;
     return B200TTS_OK;
