@@ -143,6 +143,22 @@ int b200tts_decoder_forward(const b200tts_decoder_shape* shape, const b200tts_de
                             const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* Decoder state carried between chunks of one decode (all device pointers, fp32; every field required): lets a caller decode in
+ * chunks of T frames and stop early, as the reference's inference loop does (Decoder.inference, tacotron2.py:201-207,216-219). */
+typedef struct {
+    float* att_h; float* att_c; /* [B, D] attention-LSTM state */
+    float* gen_h; float* gen_c; /* [B, D] generator-LSTM state */
+    float* context;             /* [B, M] last attention context */
+    float* cum_weights;         /* [B, L] cumulative attention weights */
+    float* frame;               /* [B, N] last predicted frame (input of the next free-running step) */
+} b200tts_decoder_state;
+
+/* b200tts_decoder_forward on a chunk of T frames: `first` != 0 starts from the zero state (tacotron2.py:164-168), otherwise from
+ * `state`; on return `state` holds the state after the chunk's last step.  Uses the per-step kernels (any precision mode). */
+int b200tts_decoder_forward_chunk(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
+                                  const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* out, b200tts_decoder_state* state,
+                                  int first, void* workspace, size_t workspace_bytes, void* stream);
+
 typedef struct {
     const float* d_spectrogram; /* [B, T, N] or NULL */
     const float* d_stop;        /* [B, T]    or NULL */
@@ -185,6 +201,9 @@ typedef struct {
     int highway;
     int training;
     float eps, momentum, dropout;
+    int stage;               /* 0: whole block.  1: convolution only = Conv1dGenerated.forward / nn.Conv1d (modules/generated.py:34-42;
+                                gamma / beta / keep ignored, out [NB, G*Cout, L]).  2: batch norm (+ activation, dropout) only, applied to
+                                x [NB, G*Cout, L] = BatchNorm1dGenerated.forward (modules/generated.py:71-96; weight ignored, Cin == Cout) */
 } b200tts_convblock_shape;
 
 size_t b200tts_convblock_saved_bytes(const b200tts_convblock_shape* shape);
@@ -200,6 +219,17 @@ int b200tts_convblock_backward(const b200tts_convblock_shape* shape, const float
                                const float* gamma, const float* beta, int affine_gstride, const uint8_t* keep,
                                const void* saved, const float* dout, float* dx, float* dweight, float* dgamma,
                                float* dbeta, void* workspace, void* stream);
+
+/* ---- one LSTM cell step: ZoneoutLSTMCell.forward / DropoutLSTMCell.forward, modules/layers.py:26-34,44-47 ----
+ * gates [B, 4D]: in = x . W_ih^T + b_ih + h . W_hh^T + b_hh (order i, f, g, o), out = the activated gates (saved for the backward);
+ * h_prev / c_prev / h_out / c_out [B, D]; keep masks uint8 [B, D] or NULL (zoneout: both, dropout cell: mask_h only).            */
+int b200tts_lstm_cell_forward(int B, int D, int cell_kind, int training, float rate_h, float rate_c, float* gates, const float* h_prev,
+                              const float* c_prev, const uint8_t* mask_h, const uint8_t* mask_c, float* h_out, float* c_out, void* stream);
+/* d_h [B, D] gradient of h_out; d_c [B, D] in: gradient of c_out, out: gradient of c_prev; d_h_prev [B, D] out: the DIRECT gradient of
+ * h_prev (zoneout carry; zeros for the dropout cell; the part through the gates is d_gates . W_hh); d_gates [B, 4D] out (pre-activation). */
+int b200tts_lstm_cell_backward(int B, int D, int cell_kind, int training, float rate_h, float rate_c, const float* gates, const float* c_prev,
+                               const uint8_t* mask_h, const uint8_t* mask_c, const float* d_h, float* d_c, float* d_h_prev, float* d_gates,
+                               void* stream);
 
 /* ---- parameter generator: Conv1dGenerated / BatchNorm1dGenerated weight synthesis, modules/generated.py:38-39,81-82 ----
  * out[g, :] = (e[g] . Wb^T + bb) . Wk^T + bk;   e [G, gd], Wb [bn, gd], Wk [R, bn]; eb [G, bn] is saved. */
@@ -232,6 +262,25 @@ int b200tts_bilstm_forward(const b200tts_bilstm_shape* shape, const b200tts_bils
 int b200tts_bilstm_backward(const b200tts_bilstm_shape* shape, const b200tts_bilstm_params* params,
                             const int32_t* lengths, const void* saved, const float* dout, float* dx,
                             const b200tts_bilstm_params* d_params, void* workspace, void* stream);
+
+/* ---- loss: TacotronLoss.forward, modules/tacotron2.py:439-485 (guided attention :439-457 in closed form) ----
+ * pre / post / targets [B, N, T]; stop (logits, padded positions already filled as in tacotron2.py:380) / stop_target [B, T]; alignment
+ * [B, T, L]; lengths int32 [B].  losses[4] (device) = { 2*MSE(pre), MSE(post), BCEWithLogits(pos_weight)/(N+2), guided attention }.   */
+typedef struct {
+    int B, N, T, L;
+    int guided;            /* hp.guided_attention_loss and guided_att_steps > 0 */
+    float guided_g;        /* current variance (TacotronLoss._g) */
+    float stop_pos_weight; /* 100 in the reference (tacotron2.py:465) */
+} b200tts_loss_shape;
+size_t b200tts_loss_workspace_bytes(void);
+int b200tts_tacotron_loss_forward(const b200tts_loss_shape* shape, const float* pre, const float* pre_target, const float* post,
+                                  const float* post_target, const float* stop, const float* stop_target, const float* alignment,
+                                  const int32_t* text_lengths, const int32_t* target_lengths, float* losses, void* workspace, void* stream);
+/* grad_losses[4] (device): upstream gradient of each term.  Any of d_pre / d_post / d_stop / d_alignment may be NULL; all are overwritten. */
+int b200tts_tacotron_loss_backward(const b200tts_loss_shape* shape, const float* pre, const float* pre_target, const float* post,
+                                   const float* post_target, const float* stop, const float* stop_target, const int32_t* text_lengths,
+                                   const int32_t* target_lengths, const float* grad_losses, float* d_pre, float* d_post, float* d_stop,
+                                   float* d_alignment, void* stream);
 
 /* ---- dropout-mask generation (counter-based RNG; replaces the Philox draws inside F.dropout) ---- */
 int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream);

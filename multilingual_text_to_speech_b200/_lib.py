@@ -41,13 +41,21 @@ class DecoderOutputs(Structure):
     _fields_ = [(n, c_void_p) for n in ('spectrogram', 'stop', 'alignments')]
 
 
+class DecoderState(Structure):
+    _fields_ = [(n, c_void_p) for n in ('att_h', 'att_c', 'gen_h', 'gen_c', 'context', 'cum_weights', 'frame')]
+
+
 class DecoderOutputGrads(Structure):
     _fields_ = [(n, c_void_p) for n in ('d_spectrogram', 'd_stop', 'd_alignments')]
 
 
 class ConvBlockShape(Structure):
     _fields_ = [(n, c_int) for n in ('NB', 'G', 'Cin', 'Cout', 'L', 'k', 'dilation', 'activation', 'highway', 'training')] + \
-               [('eps', c_float), ('momentum', c_float), ('dropout', c_float)]
+               [('eps', c_float), ('momentum', c_float), ('dropout', c_float), ('stage', c_int)]
+
+
+class LossShape(Structure):
+    _fields_ = [(n, c_int) for n in ('B', 'N', 'T', 'L', 'guided')] + [('guided_g', c_float), ('stop_pos_weight', c_float)]
 
 
 class BiLSTMShape(Structure):
@@ -81,6 +89,8 @@ SIGNATURES = {
     'b200tts_decoder_bwd_workspace_bytes': (c_size_t, [POINTER(DecoderShape)]),
     'b200tts_decoder_forward': (c_int, [POINTER(DecoderShape), POINTER(DecoderParams), POINTER(DecoderInputs),
                                         POINTER(DecoderOutputs), c_void_p, c_size_t, c_void_p]),
+    'b200tts_decoder_forward_chunk': (c_int, [POINTER(DecoderShape), POINTER(DecoderParams), POINTER(DecoderInputs),
+                                              POINTER(DecoderOutputs), POINTER(DecoderState), c_int, c_void_p, c_size_t, c_void_p]),
     'b200tts_decoder_backward': (c_int, [POINTER(DecoderShape), POINTER(DecoderParams), POINTER(DecoderInputs),
                                          POINTER(DecoderOutputs), POINTER(DecoderOutputGrads), c_void_p, c_void_p,
                                          c_size_t, POINTER(DecoderParams), c_void_p, c_void_p]),
@@ -92,6 +102,8 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'b200tts_convblock_backward': (c_int, [POINTER(ConvBlockShape), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'b200tts_lstm_cell_forward': (c_int, [c_int, c_int, c_int, c_int, c_float, c_float] + [c_void_p] * 8),
+    'b200tts_lstm_cell_backward': (c_int, [c_int, c_int, c_int, c_int, c_float, c_float] + [c_void_p] * 9),
     'b200tts_generator_workspace_bytes': (c_size_t, [c_int, c_int]),
     'b200tts_generator_forward': (c_int, [c_int, c_int, c_int, c_longlong] + [c_void_p] * 8),
     'b200tts_generator_backward': (c_int, [c_int, c_int, c_int, c_longlong] + [c_void_p] * 12),
@@ -106,6 +118,9 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     'b200tts_bilstm_backward': (c_int, [POINTER(BiLSTMShape), POINTER(BiLSTMParams), c_void_p, c_void_p, c_void_p, c_void_p,
                                         POINTER(BiLSTMParams), c_void_p, c_void_p]),
+    'b200tts_loss_workspace_bytes': (c_size_t, []),
+    'b200tts_tacotron_loss_forward': (c_int, [POINTER(LossShape)] + [c_void_p] * 12),
+    'b200tts_tacotron_loss_backward': (c_int, [POINTER(LossShape)] + [c_void_p] * 14),
     'b200tts_fill_keep_mask': (c_int, [c_void_p, c_size_t, c_float, c_uint64, c_uint64, c_void_p]),
 }
 

@@ -76,7 +76,8 @@ static int require_device() {
 }
 
 int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
-                         const b200tts_decoder_outputs& out, float* ws, size_t ws_bytes, cudaStream_t st);
+                         const b200tts_decoder_outputs& out, float* ws, size_t ws_bytes, cudaStream_t st,
+                         const b200tts_decoder_state* state = nullptr, int first = 1);
 int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                           const b200tts_decoder_outputs& fwd_out, const b200tts_decoder_output_grads& dout, const float* fws,
                           float* bws, size_t bws_bytes, const b200tts_decoder_params& dw, float* d_memory, cudaStream_t st);
@@ -133,6 +134,13 @@ __global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsi
 }  // namespace b200tts
 
 namespace b200tts {
+size_t loss_workspace_floats();
+int loss_forward_impl(const b200tts_loss_shape& s, const float* pre, const float* pre_t, const float* post, const float* post_t,
+                      const float* stop, const float* stop_t, const float* align, const int* text_len, const int* target_len, float* losses,
+                      float* ws, cudaStream_t st);
+int loss_backward_impl(const b200tts_loss_shape& s, const float* pre, const float* pre_t, const float* post, const float* post_t,
+                       const float* stop, const float* stop_t, const int* text_len, const int* target_len, const float* grad_losses,
+                       float* d_pre, float* d_post, float* d_stop, float* d_align, cudaStream_t st);
 size_t decoder_bwd_profile_offset(const b200tts_decoder_shape& s, int which);
 void set_tc_scratch(void* ptr, size_t bytes);
 size_t adam_clip_scratch_floats();
@@ -227,6 +235,16 @@ int b200tts_decoder_forward(const b200tts_decoder_shape* shape, const b200tts_de
     return decoder_forward_impl(*shape, *params, *in, *out, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int b200tts_decoder_forward_chunk(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
+                                  const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* out, b200tts_decoder_state* state,
+                                  int first, void* workspace, size_t workspace_bytes, void* stream) {
+    B200_REQUIRE(shape && params && in && out && state, "decoder_forward_chunk: null argument");
+    B200_REQUIRE(state->att_h && state->att_c && state->gen_h && state->gen_c && state->context && state->cum_weights && state->frame,
+                 "decoder_forward_chunk: every state buffer is required");
+    B200_TRY(require_device());
+    return decoder_forward_impl(*shape, *params, *in, *out, (float*)workspace, workspace_bytes, (cudaStream_t)stream, state, first);
+}
+
 int b200tts_decoder_backward(const b200tts_decoder_shape* shape, const b200tts_decoder_params* params,
                              const b200tts_decoder_inputs* in, const b200tts_decoder_outputs* fwd_out,
                              const b200tts_decoder_output_grads* dout, const void* fwd_workspace, void* bwd_workspace,
@@ -258,7 +276,8 @@ size_t b200tts_convblock_workspace_bytes(const b200tts_convblock_shape* s) { ret
 int b200tts_convblock_forward(const b200tts_convblock_shape* shape, const float* x, const float* weight, const float* gamma,
                               const float* beta, int affine_gstride, float* running_mean, float* running_var, const uint8_t* keep,
                               float* out, void* saved, void* workspace, void* stream) {
-    B200_REQUIRE(shape && x && weight && gamma && beta && out && saved && workspace, "convblock_forward: null argument");
+    B200_REQUIRE(shape && x && out && saved && workspace, "convblock_forward: null argument");
+    B200_REQUIRE((weight || shape->stage == 2) && ((gamma && beta) || shape->stage == 1), "convblock_forward: null parameter");
     B200_TRY(require_device());
     return convblock_forward_impl(*shape, x, weight, gamma, beta, affine_gstride, running_mean, running_var, keep, out, (float*)saved,
                                   (float*)workspace, (cudaStream_t)stream);
@@ -267,11 +286,39 @@ int b200tts_convblock_forward(const b200tts_convblock_shape* shape, const float*
 int b200tts_convblock_backward(const b200tts_convblock_shape* shape, const float* x, const float* weight, const float* gamma,
                                const float* beta, int affine_gstride, const uint8_t* keep, const void* saved, const float* dout,
                                float* dx, float* dweight, float* dgamma, float* dbeta, void* workspace, void* stream) {
-    B200_REQUIRE(shape && x && weight && gamma && beta && saved && dout && workspace, "convblock_backward: null argument");
+    B200_REQUIRE(shape && x && saved && dout && workspace, "convblock_backward: null argument");
+    B200_REQUIRE((weight || shape->stage == 2) && ((gamma && beta) || shape->stage == 1), "convblock_backward: null parameter");
     B200_REQUIRE(dx || !shape->highway, "convblock_backward: highway blocks need dx");
     B200_TRY(require_device());
     return convblock_backward_impl(*shape, x, weight, gamma, beta, affine_gstride, keep, (const float*)saved, dout, dx, dweight, dgamma,
                                    dbeta, (float*)workspace, (cudaStream_t)stream);
+}
+
+int b200tts_lstm_cell_forward(int B, int D, int cell_kind, int training, float rate_h, float rate_c, float* gates, const float* h_prev,
+                              const float* c_prev, const uint8_t* mask_h, const uint8_t* mask_c, float* h_out, float* c_out, void* stream) {
+    B200_REQUIRE(B > 0 && D > 0 && gates && h_prev && c_prev && h_out && c_out, "lstm_cell_forward: bad argument");
+    B200_REQUIRE(cell_kind == B200TTS_CELL_DROPOUT || cell_kind == B200TTS_CELL_ZONEOUT, "lstm_cell_forward: bad cell kind %d", cell_kind);
+    B200_REQUIRE(rate_h >= 0.f && rate_h < 1.f && rate_c >= 0.f && rate_c < 1.f, "lstm_cell_forward: rates must be in [0, 1)");
+    B200_TRY(require_device());
+    CellFwdArgs a{};
+    a.xproj = gates; a.gates = gates; a.part = nullptr; a.nsplit = 0; a.part_stride = 0;
+    a.c_prev = c_prev; a.h_prev = h_prev; a.ld_hprev = D; a.c_out = c_out; a.h_out = h_out; a.ld_hout = D;
+    a.mask_h = mask_h; a.mask_c = mask_c; a.kind = cell_kind; a.training = training; a.rate_h = rate_h; a.rate_c = rate_c;
+    a.B = B; a.D = D;
+    return launch_cell_fwd(a, (cudaStream_t)stream);
+}
+int b200tts_lstm_cell_backward(int B, int D, int cell_kind, int training, float rate_h, float rate_c, const float* gates, const float* c_prev,
+                               const uint8_t* mask_h, const uint8_t* mask_c, const float* d_h, float* d_c, float* d_h_prev, float* d_gates,
+                               void* stream) {
+    B200_REQUIRE(B > 0 && D > 0 && gates && c_prev && d_h && d_c && d_h_prev && d_gates, "lstm_cell_backward: bad argument");
+    B200_TRY(require_device());
+    B200_CUDA(cudaMemsetAsync(d_h_prev, 0, (size_t)B * D * sizeof(float), (cudaStream_t)stream));
+    CellBwdArgs a{};
+    a.gates = gates; a.c_prev = c_prev; a.dh_static = d_h; a.ld_dhs = D; a.part = nullptr; a.nsplit = 0;
+    a.dc_state = d_c; a.dhz_state = d_h_prev;       // in: zero recurrent term; out: the direct (zoneout) gradient of h_prev
+    a.mask_h = mask_h; a.mask_c = mask_c; a.kind = cell_kind; a.training = training; a.rate_h = rate_h; a.rate_c = rate_c;
+    a.dgates = d_gates; a.B = B; a.D = D; a.last = 0;
+    return launch_cell_bwd(a, (cudaStream_t)stream);
 }
 
 size_t b200tts_generator_workspace_bytes(int G, int bn) { return generator_workspace_floats(G, bn) * sizeof(float); }
@@ -334,6 +381,28 @@ int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t se
     fill_keep_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, key);
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
+}
+
+size_t b200tts_loss_workspace_bytes(void) { return loss_workspace_floats() * sizeof(float); }
+int b200tts_tacotron_loss_forward(const b200tts_loss_shape* shape, const float* pre, const float* pre_target, const float* post,
+                                  const float* post_target, const float* stop, const float* stop_target, const float* alignment,
+                                  const int32_t* text_lengths, const int32_t* target_lengths, float* losses, void* workspace, void* stream) {
+    B200_REQUIRE(shape && pre && pre_target && post && post_target && stop && stop_target && text_lengths && target_lengths && losses && workspace,
+                 "tacotron_loss_forward: null argument");
+    B200_REQUIRE(alignment || !shape->guided, "tacotron_loss_forward: guided attention needs the alignments");
+    B200_TRY(require_device());
+    return loss_forward_impl(*shape, pre, pre_target, post, post_target, stop, stop_target, alignment, text_lengths, target_lengths, losses,
+                             (float*)workspace, (cudaStream_t)stream);
+}
+int b200tts_tacotron_loss_backward(const b200tts_loss_shape* shape, const float* pre, const float* pre_target, const float* post,
+                                   const float* post_target, const float* stop, const float* stop_target, const int32_t* text_lengths,
+                                   const int32_t* target_lengths, const float* grad_losses, float* d_pre, float* d_post, float* d_stop,
+                                   float* d_alignment, void* stream) {
+    B200_REQUIRE(shape && pre && pre_target && post && post_target && stop && stop_target && text_lengths && target_lengths && grad_losses,
+                 "tacotron_loss_backward: null argument");
+    B200_TRY(require_device());
+    return loss_backward_impl(*shape, pre, pre_target, post, post_target, stop, stop_target, text_lengths, target_lengths, grad_losses, d_pre,
+                              d_post, d_stop, d_alignment, (cudaStream_t)stream);
 }
 
 size_t b200tts_adam_clip_scratch_floats(void) { return adam_clip_scratch_floats(); }

@@ -487,8 +487,10 @@ int frame_proj(const FwdCtx& c, int step0, int nsteps) {
 }  // namespace
 
 int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
-                         const b200tts_decoder_outputs& out, float* ws, size_t ws_bytes, cudaStream_t st) {
+                         const b200tts_decoder_outputs& out, float* ws, size_t ws_bytes, cudaStream_t st,
+                         const b200tts_decoder_state* state, int first) {
     B200_TRY(validate_decoder_shape(s));
+    const bool resume = state != nullptr && !first;       // chunked decode: start from the carried state
     FwdCtx c{s, w, in, decoder_layout(s), ws, st};
     const auto& l = c.lay;
     B200_REQUIRE(ws != nullptr && ws_bytes >= l.total * sizeof(float), "decoder_forward: workspace too small (%zu < %zu bytes)",
@@ -520,14 +522,23 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
     B200_TRY(prenet_rows(c, T * B, c.at(l.xtm), c.at(l.p0), c.at(l.p1), in.mask_prenet0, in.mask_prenet1));
     B200_TRY(run_gemm(st, T * B, 4 * D, P, c.at(l.p1), P, w.att_w_ih, P + M, true, c.at(l.ga), 4 * D, c.at(l.bsum_att), 0.f));
     B200_TRY(run_gemm(st, B * s.L, s.A, M, in.memory, M, w.attn_memory, M, true, c.at(l.memT), s.A, nullptr, 0.f));
+    if (resume) {
+        B200_TRY(launch_copy2d(c.at(l.ai), MD, state->context, M, B, M, st));
+        B200_TRY(launch_copy2d(c.at(l.ai) + M, MD, state->att_h, D, B, D, st));
+        B200_TRY(launch_copy2d(c.at(l.ca), D, state->att_c, D, B, D, st));
+        B200_TRY(launch_copy2d(c.at(l.hg), D, state->gen_h, D, B, D, st));
+        B200_TRY(launch_copy2d(c.at(l.cg), D, state->gen_c, D, B, D, st));
+        B200_TRY(launch_copy2d(c.at(l.cum), s.L, state->cum_weights, s.L, B, s.L, st));
+    } else {
     B200_TRY(launch_fill(c.at(l.ai), 0.f, (size_t)B * MD, st));
     B200_TRY(launch_fill(c.at(l.ca), 0.f, BD, st));
     B200_TRY(launch_fill(c.at(l.hg), 0.f, BD, st));
     B200_TRY(launch_fill(c.at(l.cg), 0.f, BD, st));
     B200_TRY(launch_fill(c.at(l.cum), 0.f, (size_t)B * s.L, st));
+    }
 
     // the persistent forward rounds memory / memT to bf16; only the persistent backward recomputes with the same operands
-    const bool persistent = !sequential && precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s) &&
+    const bool persistent = !sequential && state == nullptr && precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s) &&
                             (!s.training || persist_att_bwd_supported(s));
     if (persistent) {
         // bf16 perf mode: one cooperative, weight-stationary kernel per recurrence (decoder_persist.cu)
@@ -588,7 +599,8 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
         for (int i = 0; i < T; ++i) {
             if (!in.teacher[i]) {
                 float* x = c.at(l.xtm) + (size_t)i * B * N;
-                if (i == 0) B200_TRY(launch_fill(x, 0.f, (size_t)B * N, st));
+                if (i == 0 && resume) B200_TRY(launch_copy2d(x, N, state->frame, N, B, N, st));
+                else if (i == 0) B200_TRY(launch_fill(x, 0.f, (size_t)B * N, st));
                 else B200_TRY(launch_copy2d(x, N, c.at(l.fs) + (size_t)(i - 1) * B * (N + 1), N + 1, B, N, st));
                 const uint8_t* m0 = in.mask_step_prenet0 ? in.mask_step_prenet0 + (size_t)i * B * P : nullptr;
                 const uint8_t* m1 = in.mask_step_prenet1 ? in.mask_step_prenet1 + (size_t)i * B * P : nullptr;
@@ -604,6 +616,16 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
     }
     split_frames_kernel<<<grid_for((size_t)B * T * (N + 1)), 256, 0, st>>>(out.spectrogram, out.stop, c.at(l.fs), B, T, N);
     B200_LAUNCH_CHECK();
+    if (state) {        // state after the last step of the chunk
+        const float* ai_T = c.at(l.ai) + (size_t)T * B * MD;
+        B200_TRY(launch_copy2d(state->context, M, ai_T, MD, B, M, st));
+        B200_TRY(launch_copy2d(state->att_h, D, ai_T + M, MD, B, D, st));
+        B200_TRY(launch_copy2d(state->att_c, D, c.at(l.ca) + (size_t)T * BD, D, B, D, st));
+        B200_TRY(launch_copy2d(state->gen_h, D, c.at(l.hg) + (size_t)T * BD, D, B, D, st));
+        B200_TRY(launch_copy2d(state->gen_c, D, c.at(l.cg) + (size_t)T * BD, D, B, D, st));
+        B200_TRY(launch_copy2d(state->cum_weights, s.L, c.at(l.cum) + (size_t)T * B * s.L, s.L, B, s.L, st));
+        B200_TRY(launch_copy2d(state->frame, N, c.at(l.fs) + (size_t)(T - 1) * B * (N + 1), N + 1, B, N, st));
+    }
     return B200TTS_OK;
 }
 

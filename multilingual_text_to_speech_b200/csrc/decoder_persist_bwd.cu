@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <cuda_bf16.h>
 #include "decoder_internal.cuh"
+#include "tc_ptx.cuh"
 
 namespace b200tts {
 
@@ -62,11 +63,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag) {
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag, bool async_fence = false) {
     __shared__ int s_ok;
     __syncthreads();
     if (threadIdx.x == 0) {
         target += nblocks;
+        if (async_fence) tcx::proxy_fence_global();     // global data written above is read by other CTAs through TMA (async proxy)
         // arrival = ONE release-reduction (cumulative over the CTA's writes, which the __syncthreads above made visible to thread 0);
         // the wait polls with relaxed loads and issues a single acquire fence after the last one
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
@@ -252,6 +254,11 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_kernel(const BwdLoopArgs 
 constexpr int KBA = 8;            // K-blocks of the attention-loop product (over hidden units)
 constexpr int NBA = 9;            // N-blocks over the M + D output columns  -> 8 x 9 x 2 = 144 CTAs
 constexpr int GLD = 33;           // row stride of the G tile buffer (floats)
+// tcgen05 variant of the product: CTA (kb, nb) of 8 x 18 keeps W^T[n-block of 80 outputs, K-slice kb] as K-major SWIZZLE_128B tiles (UMMA B
+// operand, N = 80); the whole batch (<= 64 utterances, TMA zero-fills the rest) is the A operand (M = 64), ONE 5-D TMA box per step
+constexpr int NBT = 18;           // n-blocks of the tcgen05 variant  -> 8 x 18 = 144 CTAs (72 pairs)
+constexpr int TUN = 80;           // outputs per n-block (UMMA N)
+constexpr int TMEM_COLS_ATT = 128;
 
 struct AttBwdArgs {
     int B, T, D, M, L, A, KC, NOUT, UK, UN, NBH, MT;      // NOUT = M + D, MT = ceil(L / 16)
@@ -306,17 +313,25 @@ __device__ __forceinline__ void build_pairs(uint32_t* Ph, uint32_t* Pl, const fl
     }
 }
 
-__global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <bool TC>
+__global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_constant__ CUtensorMap tmG, const AttBwdArgs p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw0[];
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw0) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar, accum_bar;
+    __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
-    const int kb = cta % KBA, nb = (cta / KBA) % NBA, bh = cta / (KBA * NBA);
+    const int kb = cta % KBA, nb = TC ? cta / KBA : (cta / KBA) % NBA, bh = TC ? 0 : cta / (KBA * NBA);
     const int B = p.B, D = p.D, UK = p.UK, UN = p.UN, KROWS = 4 * UK, M = p.M, L = p.L, A = p.A;
     const int WLD = UN + 8, ALD = KROWS + 8;
     const int b0 = bh * BT, n0 = nb * UN;
-    __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem_raw);                 // [KROWS][WLD]
-    __nv_bfloat16* As = Ws + (size_t)KROWS * WLD;                                    // [BT][ALD]  (aliased by the attention scratch)
-    unsigned char* extra = reinterpret_cast<unsigned char*>(As + (size_t)BT * ALD);
+    const int NKT = KROWS / 64;                                                      // TC: k-block tiles of the K-slice
+    // mma.sync: Ws [KROWS][WLD] bf16, As [BT][ALD] bf16.  tcgen05: sW [NKT][UN rows][128 B] swizzled, slot [NKT][64 rows][128 B] (one TMA box).
+    // The activation stage `As` doubles as the attention scratch / query-gradient staging in both variants.
+    __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+    unsigned char* sW = smem_raw;
+    __nv_bfloat16* As = TC ? reinterpret_cast<__nv_bfloat16*>(smem_raw + (size_t)NKT * UN * 128) : Ws + (size_t)KROWS * WLD;
+    unsigned char* extra = TC ? reinterpret_cast<unsigned char*>(As) + (size_t)NKT * 8192 : reinterpret_cast<unsigned char*>(As + (size_t)BT * ALD);
     __nv_bfloat16* sWcB = reinterpret_cast<__nv_bfloat16*>(extra);                   // [A][40]
     __nv_bfloat16* sWcB2 = sWcB + (size_t)A * 40;                                    // [32][A+8]
     float* dcum = reinterpret_cast<float*>(sWcB2 + (size_t)32 * (A + 8));            // [L16 + 32] persistent d cum
@@ -329,7 +344,12 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
         const int g = r / UK, uk = r % UK;
         float w = 0.f;
         if (n0 + n < p.NOUT) w = p.W[(size_t)(g * D + kb * UK + uk) * p.ldw + n0 + n];
-        Ws[r * WLD + n] = __float2bfloat16_rn(w);
+        if (TC) {       // W^T[n][k] of k-block tile c = r / 64 (same order as the TMA box: gate-major, then 64-row halves), SWIZZLE_128B
+            const int c = r >> 6, kc = r & 63;
+            *reinterpret_cast<__nv_bfloat16*>(sW + (size_t)c * UN * 128 + n * 128 + ((((kc >> 3) ^ (n & 7))) << 4) + (kc & 7) * 2) = __float2bfloat16_rn(w);
+        } else {
+            Ws[r * WLD + n] = __float2bfloat16_rn(w);
+        }
     }
     for (int idx = tid; idx < A * 40; idx += PT) sWcB[idx] = p.WcB[idx];
     for (int idx = tid; idx < 32 * (A + 8); idx += PT) sWcB2[idx] = p.WcB2[idx];
@@ -340,7 +360,16 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
     const int uo0 = cta * UOWN;
     if (owner)
         for (int idx = tid; idx < A * UOWN; idx += PT) wq8[(idx / UOWN) * (UOWN + 1) + idx % UOWN] = p.Wq[(size_t)(idx / UOWN) * D + uo0 + idx % UOWN];
+    uint32_t tmem_base = 0, prod_it = 0;
+    if (TC) {
+        if (tid == 0) { tcx::mbar_init(&full_bar, 1); tcx::mbar_init(&accum_bar, 1); tcx::mbar_init_fence(); }
+        if (warp == 1) tcx::tmem_alloc<TMEM_COLS_ATT>(&tmem_base_s);
+        tcx::proxy_fence_shared();           // the weight tiles were written through the generic proxy; tcgen05.mma reads them through the async proxy
+        tcx::tc_fence_before();
+    }
     __syncthreads();
+    if (TC) { tcx::tc_fence_after(); tmem_base = tmem_base_s; }
+    const uint32_t idesc = tcx::make_idesc_bf16(64, TUN);
 
     const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
     constexpr int MAXE = 3;               // (b, u) pairs per thread: B * 8 / 256 <= 3 for B <= 64... (B <= 96)
@@ -613,7 +642,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
             cluster_arrive(); cluster_wait();
         }
         BPROF_MARK(1);
-        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) break;
         BPROF_MARK(2);
 
         // =========================== PB: attention-LSTM cell backward ===========================
@@ -735,12 +764,59 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
         }
         pb_prefetch(i - 1);
         BPROF_MARK(3);
-        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, TC)) break;
         BPROF_MARK(4);
         if (i == 0) break;
 
         // =========================== P2: [d ctx | d h](i-1) partial = dgates_i[:, kb] . W[kb, nb] ===========================
-        {
+        if (TC) {
+            // TMA: the bf16 gate gradients of the K-slice, all utterances (rows >= B zero-filled), as NKT swizzled [64 x 64] tiles in ONE box;
+            // tcgen05: D[b, n] (TMEM, 64 lanes x 80 columns) = sum over the tiles; warp 0 issues (elected lane), everybody drains TMEM
+            if (warp == 0) {
+                if (tcx::elect_one()) {
+                    tcx::proxy_fence_shared();       // the slot was last touched through the generic proxy (attention scratch, dq staging)
+                    tcx::proxy_fence_global();
+                    tcx::mbar_expect_tx(&full_bar, (uint32_t)NKT * 8192);
+                    tcx::tma_load_5d(As, &tmG, &full_bar, 0, 0, 0, kb, 0);
+                }
+                __syncwarp();
+                tcx::mbar_wait(&full_bar, prod_it & 1);
+                tcx::tc_fence_after();
+                if (tcx::elect_one()) {
+                    for (int c = 0; c < NKT; ++c) {
+                        const uint64_t adesc = tcx::make_sw128_desc(tcx::smem_u32(reinterpret_cast<unsigned char*>(As) + (size_t)c * 8192));
+                        const uint64_t bdesc = tcx::make_sw128_desc(tcx::smem_u32(sW + (size_t)c * UN * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tcx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c == 0 && k == 0) ? 0u : 1u);
+                    }
+                    tcx::umma_commit(&accum_bar);
+                }
+                __syncwarp();
+            }
+            tcx::mbar_wait(&accum_bar, prod_it & 1);
+            tcx::tc_fence_after();
+            ++prod_it;
+            {   // M = 64 accumulator layout: utterance b sits in TMEM lane (b / 16) * 32 + b % 16; warp = (quadrant, half of the 80 columns)
+                const int q = warp & 3, ch = warp >> 2;
+                uint32_t r[5][8];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) tcx::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 40 + j * 8), r[j]);
+                tcx::tmem_ld_wait();
+                const int b = q * 16 + lane;
+                if (lane < 16 && b < B) {
+                    float* dst = p.part + ((size_t)kb * B + b) * p.NOUT + n0 + ch * 40;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+#pragma unroll
+                        for (int h4 = 0; h4 < 2; ++h4)
+                            if (n0 + ch * 40 + j * 8 + h4 * 4 < p.NOUT)         // NOUT % 4 == 0 (checked on the host)
+                                *reinterpret_cast<float4*>(dst + j * 8 + h4 * 4) =
+                                    make_float4(__uint_as_float(r[j][h4 * 4]), __uint_as_float(r[j][h4 * 4 + 1]), __uint_as_float(r[j][h4 * 4 + 2]),
+                                                __uint_as_float(r[j][h4 * 4 + 3]));
+                }
+                tcx::tc_fence_before();
+            }
+        } else {
             const int segs = UK / 8;
             for (int idx = tid; idx < BT * 4 * segs; idx += PT) {
                 const int r = idx / (4 * segs), rem = idx % (4 * segs), g = rem / segs, sg = rem % segs;
@@ -786,10 +862,15 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const AttBwdArgs p)
             }
         }
         BPROF_MARK(5);
-        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) return;
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) break;
         BPROF_MARK(6);
     }
     BPROF_FLUSH;
+    if (TC) {
+        tcx::tc_fence_before();
+        __syncthreads();
+        if (warp == 1) tcx::tmem_dealloc<TMEM_COLS_ATT>(tmem_base);
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1022,36 +1103,60 @@ AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s) {
     return x;
 }
 
-// where the [8][A] query-gradient partials go inside the attention scratch: 1 = after the G tiles, 0 = aliasing the
-// (dead) head of the scratch, -1 = the scratch does not fit at all
-static int att_bwd_dqp_mode(const b200tts_decoder_shape& s) {
-    const int UK = s.D / KBA, MT = (s.L + 15) / 16, L16 = MT * 16;
-    const size_t region = (size_t)BT * (4 * UK + 8) * 2 / 4;                     // floats available (the A-operand stage)
-    const size_t head = (size_t)((s.M + 3) & ~3) + 2 * L16 + 2 * s.A;            // s_dctx, s_w, s_de, s_qb, s_vv
-    const size_t base = head + 2 * (L16 + 48) + 64 + (size_t)L16 * GLD;
-    if (base + 8 * s.A <= region) return 1;
-    if (base <= region && (size_t)8 * s.A <= head + (L16 + 48)) return 0;       // must end before Pl (d cum staging)
-    return -1;
+// Geometry of the two product variants of the attention reverse loop.
+struct AttBwdGeom {
+    bool tc; int UK, UN, NBH, grid; size_t region, smem;      // region = bytes of the activation stage (= attention scratch capacity)
+};
+static AttBwdGeom att_bwd_geom(const b200tts_decoder_shape& s, bool tc) {
+    AttBwdGeom g{};
+    g.tc = tc;
+    g.UK = s.D / KBA;
+    const int L16 = (s.L + 15) / 16 * 16;
+    const size_t extras = (size_t)s.A * 40 * 2 + (size_t)32 * (s.A + 8) * 2 + (size_t)(L16 + 32) * 4 + (size_t)s.A * 9 * 4;
+    if (tc) {
+        g.UN = TUN; g.NBH = 1; g.grid = KBA * NBT;
+        const int NKT = 4 * g.UK / 64;
+        g.region = (size_t)NKT * 8192;
+        g.smem = 1024 + (size_t)NKT * TUN * 128 + g.region + extras;
+    } else {
+        g.UN = (cdiv(s.M + s.D, NBA) + 15) / 16 * 16; g.NBH = (s.B + BT - 1) / BT; g.grid = KBA * NBA * g.NBH;
+        g.region = (size_t)BT * (4 * g.UK + 8) * 2;
+        g.smem = 1024 + (size_t)4 * g.UK * (g.UN + 8) * 2 + g.region + extras;
+    }
+    return g;
 }
 
-bool persist_att_bwd_supported(const b200tts_decoder_shape& s) {
-    if (!persist_bwd_supported(s)) return false;
-    if (s.A != 128 || s.K > 32 || s.B > 2 * BT || s.B * 8 > 3 * PT || s.D / 8 > KBA * NBA * ((s.B + BT - 1) / BT)) return false;
-    const int UK = s.D / KBA, UN = (cdiv(s.M + s.D, NBA) + 15) / 16 * 16;
-    const int MT = (s.L + 15) / 16, L16 = MT * 16;
-    {   // attention-backward scratch of one CTA of the pair (aliases the activation tile)
-        const int HT0 = (MT + 1) / 2;
-        const size_t fl = (size_t)((s.M + 3) & ~3) + 3 * (size_t)L16 + 2 * s.A + 2 * (size_t)(L16 + 48) + 64 + (size_t)(HT0 + 1) * 16 * GLD +
-                          8 * (size_t)s.A + s.A + 4;
-        if (fl * 4 > (size_t)BT * (4 * UK + 8) * 2) return false;
-        if ((KBA * NBA * ((s.B + BT - 1) / BT)) / 2 < s.B) return false;       // one CTA pair per utterance
+static bool att_bwd_variant_ok(const b200tts_decoder_shape& s, const AttBwdGeom& g) {
+    if (s.A != 128 || s.K > 32 || s.B * 8 > 3 * PT || s.D % KBA != 0) return false;
+    if (s.D / 8 > g.grid) return false;                       // cell-backward ownership: 8 hidden units per CTA
+    if (g.grid / 2 < s.B || g.grid > 148) return false;       // one CTA pair per utterance, all CTAs co-resident
+    if (g.tc) {
+        if (g.UK % 64 != 0 || s.B > 64 || s.M + s.D > NBT * TUN || (s.M + s.D) % 4 != 0) return false;
+    } else {
+        if (!persist_bwd_supported(s) || s.B > 2 * BT) return false;
     }
-    // the cell-backward phase stages the query gradients [B][A] fp32 + [64][8] products in the (then idle) activation tile
-    if ((size_t)s.B * s.A * 4 + 64 * 8 * 4 > (size_t)BT * (4 * UK + 8) * 2) return false;
-    const size_t fixed = ((size_t)4 * UK * (UN + 8) + (size_t)BT * (4 * UK + 8)) * 2 + (size_t)s.A * 40 * 2 + (size_t)32 * (s.A + 8) * 2 +
-                         (size_t)(L16 + 32) * 4 + (size_t)s.A * 9 * 4;
-    return fixed <= 227 * 1024 && att_bwd_dqp_mode(s) >= 0;
+    const int MT = (s.L + 15) / 16, L16 = MT * 16, HT0 = (MT + 1) / 2;
+    // attention-backward scratch of one CTA of the pair (aliases the activation stage)
+    const size_t fl = (size_t)((s.M + 3) & ~3) + 3 * (size_t)L16 + 2 * s.A + 2 * (size_t)(L16 + 48) + 64 + (size_t)(HT0 + 1) * 16 * GLD +
+                      8 * (size_t)s.A + s.A + 4;
+    if (fl * 4 > g.region) return false;
+    // the cell-backward phase stages the query gradients [B][A] fp32 + [64][8] products in the (then idle) activation stage
+    if ((size_t)s.B * s.A * 4 + 64 * 8 * 4 > g.region) return false;
+    return g.smem <= 227 * 1024;
 }
+
+static bool att_bwd_pick(const b200tts_decoder_shape& s, AttBwdGeom* out) {
+    for (int tc = 1; tc >= 0; --tc) {
+        if (tc && getenv("B200TTS_ATT_BWD_MMA_SYNC")) continue;      // A/B switch: force the mma.sync product
+        const AttBwdGeom g = att_bwd_geom(s, tc != 0);
+        if (att_bwd_variant_ok(s, g)) { if (out) *out = g; return true; }
+    }
+    return false;
+}
+
+bool persist_att_bwd_supported(const b200tts_decoder_shape& s) { return att_bwd_pick(s, nullptr); }
+
+int tc_make_mapN_bf16(void* map, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides, const unsigned* box);
 
 int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                          const DecoderLayout& fl, const float* fws, const PersistLayout& pl, const unsigned char* pws,
@@ -1061,8 +1166,10 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     const AttBwdExtra x = att_bwd_extra(s);
     const int B = s.B, D = s.D, M = s.M, T = s.T, L = s.L, A = s.A;
     AttBwdArgs a{};
-    a.B = B; a.T = T; a.D = D; a.M = M; a.L = L; a.A = A; a.KC = s.K; a.NOUT = M + D; a.UK = D / KBA;
-    a.UN = (cdiv(M + D, NBA) + 15) / 16 * 16; a.NBH = (B + BT - 1) / BT; a.MT = x.MT;
+    AttBwdGeom geo{};
+    B200_REQUIRE(att_bwd_pick(s, &geo), "persistent attention backward: shape not supported");
+    a.B = B; a.T = T; a.D = D; a.M = M; a.L = L; a.A = A; a.KC = s.K; a.NOUT = M + D; a.UK = geo.UK;
+    a.UN = geo.UN; a.NBH = geo.NBH; a.MT = x.MT;
     a.W = fws + fl.wcat_att; a.ldw = M + D;
     a.gates = fws + fl.ga; a.cstate = fws + fl.ca; a.dh_static = dh_static; a.dctx_static = dctx_static;
     a.mask_h = in.mask_att_h; a.mask_c = in.mask_att_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
@@ -1078,7 +1185,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     a.WcB = wcb; a.WcB2 = wcb2; a.memTf = memTf;
     a.memb = reinterpret_cast<const __nv_bfloat16*>(pws + pl.memb); a.ldm = pl.ldm;
     a.memFb = reinterpret_cast<const uint4*>(pws + pl.memFb); a.M16 = pl.M16;
-    a.dqp_after_g = att_bwd_dqp_mode(s);
+    a.dqp_after_g = 1;
     a.lengths = in.text_lengths; a.dctx_tot = dctx_tot; a.dq = dq; a.de = reinterpret_cast<float*>(extra + x.de);
     a.barrier = reinterpret_cast<unsigned*>(extra + x.barrier); a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);
     a.prof = reinterpret_cast<long long*>(extra + x.barrier + 256);
@@ -1086,18 +1193,26 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     B200_CUDA(cudaMemsetAsync(a.barrier, 0, 256, st));
     att_bwd_prep_kernel<<<148 * 4, 256, 0, st>>>(wcb, wcb2, memTf, wcombT, fws + fl.memT, B, L, A, s.K, x.MT);
     B200_LAUNCH_CHECK();
-    const int L16 = x.MT * 16;
-    const size_t smem = ((size_t)4 * a.UK * (a.UN + 8) + (size_t)BT * (4 * a.UK + 8)) * 2 + (size_t)A * 40 * 2 + (size_t)32 * (A + 8) * 2 +
-                        (size_t)(L16 + 32) * 4 + (size_t)A * 9 * 4;
-    void* fn = (void*)att_bwd_loop_kernel;
+    const size_t smem = geo.smem;
+    void* fn = geo.tc ? (void*)att_bwd_loop_kernel<true> : (void*)att_bwd_loop_kernel<false>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = KBA * NBA * a.NBH;
+    const int grid = geo.grid;
     int per_sm = 0, dev = 0, sms = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PT, smem));
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     B200_REQUIRE(per_sm * sms >= grid && grid % 2 == 0 && grid / 2 >= B, "persistent attention backward: %d CTAs cannot be co-resident / paired", grid);
-    void* params[] = {&a};
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (geo.tc) {
+        // bf16 gate gradients dgb [B, 4D] as {64 k, B rows, UK/64 halves, KBA k-slices, 4 gates}: element (b, g, kb, h, c) at
+        // b * 4D + g * D + kb * UK + h * 64 + c; one box = {64, 64 rows, UK/64, 1, 4} = the whole K-slice of a CTA
+        const unsigned long long dims[5] = {64ull, (unsigned long long)B, (unsigned long long)(geo.UK / 64), (unsigned long long)KBA, 4ull};
+        const unsigned long long strides[4] = {(unsigned long long)4 * D * 2, 128ull, (unsigned long long)geo.UK * 2, (unsigned long long)D * 2};
+        const unsigned box[5] = {64u, 64u, (unsigned)(geo.UK / 64), 1u, 4u};
+        B200_TRY(tc_make_mapN_bf16(&tm, a.dgb, 5, dims, strides, box));
+    }
+    void* params[] = {&tm, &a};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attrs[2];

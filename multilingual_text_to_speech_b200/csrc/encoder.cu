@@ -366,6 +366,9 @@ int validate_block(const b200tts_convblock_shape& s) {
     B200_REQUIRE(!s.highway || s.Cout == 2 * s.Cin, "convblock: highway needs Cout == 2*Cin (got %d, %d)", s.Cout, s.Cin);
     B200_REQUIRE(s.activation >= 0 && s.activation <= 2, "convblock: unknown activation %d", s.activation);
     B200_REQUIRE(s.dropout >= 0.f && s.dropout < 1.f, "convblock: dropout must be in [0,1)");
+    B200_REQUIRE(s.stage >= 0 && s.stage <= 2, "convblock: unknown stage %d", s.stage);
+    B200_REQUIRE(s.stage == 0 || !s.highway, "convblock: the highway gate needs the whole block (stage 0)");
+    B200_REQUIRE(s.stage != 2 || (s.Cin == s.Cout && s.k == 1), "convblock: stage 2 (batch norm only) needs Cin == Cout and k == 1");
     return B200TTS_OK;
 }
 
@@ -386,11 +389,12 @@ int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, con
                            float* out, float* saved, float* ws, cudaStream_t st) {
     B200_TRY(validate_block(s));
     const BlockDims d = block_dims(s);
-    float* conv = saved;
+    float* conv = s.stage == 1 ? out : saved;     // convolution only: the product IS the output
     float* mean = saved + align_up_sz(d.conv_elems, 64);
     float* invstd = mean + align_up_sz(d.Ct, 64);
-    bool implicit = false;
-    if (precision_mode() != 0 && s.k > 1)       // bf16 perf mode: implicit convolution on the tcgen05 GEMM (TMA row shifts per tap, no im2col)
+    bool implicit = s.stage == 2;                 // batch norm only: there is no product, x plays the role of the convolution output
+    if (s.stage == 2) conv = const_cast<float*>(x);
+    if (!implicit && precision_mode() != 0 && s.k > 1)       // bf16 perf mode: implicit convolution on the tcgen05 GEMM (TMA row shifts per tap, no im2col)
         B200_TRY(gemm_tc_conv(weight, x, conv, s.NB, s.G, s.Cout, s.Cin, s.L, s.k, s.dilation, d.pad, 0, 0.f, st, &implicit));
     if (!implicit) {
         const float* col = x;
@@ -406,6 +410,7 @@ int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, con
         g.M = s.Cout; g.N = s.L; g.K = s.Cin * s.k; g.batch = s.NB * s.G;
         B200_TRY(gemm_run(g, st));
     }
+    if (s.stage == 1) return B200TTS_OK;
     if (s.training) {
         bn_stats_kernel<<<(int)d.Ct, 256, 0, st>>>(conv, mean, invstd, running_mean, running_var, s.NB, (int)d.Ct, s.L, s.eps, s.momentum);
     } else {
@@ -425,18 +430,25 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
                             float* dx, float* dweight, float* dgamma, float* dbeta, float* ws, cudaStream_t st) {
     B200_TRY(validate_block(s));
     const BlockDims d = block_dims(s);
-    const float* conv = saved;
+    const float* conv = s.stage == 2 ? x : saved;
     const float* mean = saved + align_up_sz(d.conv_elems, 64);
     const float* invstd = mean + align_up_sz(d.Ct, 64);
     float* col = ws;
     float* dcol = col + align_up_sz(d.col_elems, 64);
     float* dz = dcol + align_up_sz(d.col_elems, 64);
+    if (s.stage == 2) {      // batch norm only: the gradient w.r.t. the normalised input IS dx
+        B200_REQUIRE(dx, "convblock_backward: stage 2 needs dx");
+        dz = dx;
+    }
     float* s1 = dz + align_up_sz(d.conv_elems, 64);
     float* s2 = s1 + align_up_sz(d.Ct, 64);
     float* scratch = s2 + align_up_sz(d.Ct, 64);
 
     BlockArgs a{conv, mean, invstd, gamma, beta, affine_gstride, (s.training && s.dropout > 0.f) ? keep : nullptr,
                 1.f / (1.f - s.dropout), x, s.NB, s.G, s.Cout, s.L, s.activation, s.highway};
+    if (s.stage == 1) {      // convolution only: dout is the gradient of the product
+        B200_CUDA(cudaMemcpyAsync(dz, dout, d.conv_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
     block_bwd_prep_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, dout, dz, dx);
     B200_LAUNCH_CHECK();
     bn_bwd_reduce_kernel<<<(int)d.Ct, 256, 0, st>>>(dz, conv, mean, invstd, s1, s2, dgamma, dbeta, affine_gstride, s.NB, s.G, s.Cout, s.L);
@@ -444,6 +456,8 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
     bn_bwd_apply_kernel<<<grid_for(d.conv_elems), 256, 0, st>>>(dz, conv, mean, invstd, gamma, affine_gstride, s1, s2, s.NB, s.G, s.Cout,
                                                                 s.L, s.training);
     B200_LAUNCH_CHECK();
+    }
+    if (s.stage == 2) return B200TTS_OK;
     const float* colr = x;
     bool have_col = (s.k == 1);
     auto ensure_col = [&]() -> int {         // im2col only for the paths that still need the materialised matrix

@@ -432,6 +432,22 @@ int tc_make_map3_bf16(void* map, const void* base, int d0, int d1, int d2, size_
     return B200TTS_OK;
 }
 
+// rank-N (<= 5) bf16 tensor map, SWIZZLE_128B; dims / box: `rank` entries (innermost first), strides: rank - 1 byte strides
+int tc_make_mapN_bf16(void* map, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides, const unsigned* box) {
+    EncodeTiledFn fn = encode_fn();
+    B200_REQUIRE(fn != nullptr, "tc_make_mapN: cuTensorMapEncodeTiled is unavailable");
+    B200_REQUIRE(rank >= 1 && rank <= 5, "tc_make_mapN: rank %d", rank);
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
+    const CUresult r = fn(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "tc_make_mapN: cuTensorMapEncodeTiled failed with %d (rank %d)", (int)r, rank);
+    return B200TTS_OK;
+}
+
 void set_tc_scratch(void* ptr, size_t bytes) { g_scratch.ptr = static_cast<unsigned char*>(ptr); g_scratch.bytes = bytes; g_ncache = 0; g_cache_off = 0; }
 void tc_pack_cache_begin() { g_cache_on = true; g_ncache = 0; g_cache_off = 0; }
 void tc_pack_cache_end() { g_cache_on = false; g_ncache = 0; g_cache_off = 0; }

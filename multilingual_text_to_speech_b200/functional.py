@@ -212,6 +212,50 @@ class DecoderFunction(torch.autograd.Function):
         return (None, d_memory, None, None, *grads)
 
 
+class DecoderState:
+    """Device buffers of the decoder state carried between the chunks of one free-running decode (b200tts_decoder_state)."""
+
+    def __init__(self, B, D, M, L, N, device):
+        z = lambda *shape: torch.zeros(*shape, device=device, dtype=torch.float32)   # noqa: E731
+        self.att_h, self.att_c, self.gen_h, self.gen_c = z(B, D), z(B, D), z(B, D), z(B, D)
+        self.context, self.cum_weights, self.frame = z(B, M), z(B, L), z(B, N)
+        self.first = True
+
+    def struct(self):
+        return _lib.DecoderState(*[ptr(t) for t in (self.att_h, self.att_c, self.gen_h, self.gen_c, self.context, self.cum_weights, self.frame)])
+
+
+def decoder_forward_chunk(cfg, memory, text_lengths, params, state, frames):
+    """`frames` free-running decoder steps continuing from `state` (updated in place); no autograd (inference)."""
+    _require_cuda(memory, text_lengths, *params)
+    with torch.no_grad():
+        memory = _f32c(memory)
+        params = [_f32c(p) for p in params]
+        text_lengths = text_lengths.to(torch.int32).contiguous()
+        byname = dict(zip(DECODER_PARAM_FIELDS, params))
+        B, L, M = memory.shape
+        D, P, A = byname['att_w_hh'].shape[1], byname['prenet_w1'].shape[0], byname['attn_query'].shape[0]
+        C, K = byname['attn_loc_features'].shape[0], byname['attn_loc_features'].shape[-1]
+        N = byname['frame_w'].shape[0]
+        T = int(frames)
+        target = torch.zeros(B, N, T, device=memory.device, dtype=torch.float32)
+        shape, pstruct, inputs, teacher_np = _decoder_structs(cfg, (B, L, T, M, D, P, A, C, K, N), params, memory, text_lengths, target)
+        lib = _lib.load()
+        nbytes = lib.b200tts_decoder_workspace_bytes(ctypes.byref(shape))
+        if nbytes == 0:
+            raise _lib.B200TTSError('decoder shape rejected: ' + lib.b200tts_last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=memory.device)
+        spec = torch.empty(B, T, N, device=memory.device, dtype=torch.float32)
+        stop = torch.empty(B, T, device=memory.device, dtype=torch.float32)
+        align = torch.empty(B, T, L, device=memory.device, dtype=torch.float32)
+        outs = DecoderOutputs(ptr(spec), ptr(stop), ptr(align))
+        st = state.struct()
+        check(lib.b200tts_decoder_forward_chunk(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs), ctypes.byref(outs),
+                                                ctypes.byref(st), int(state.first), ptr(ws), nbytes, _stream()), 'b200tts_decoder_forward_chunk')
+        state.first = False
+    return spec, stop, align
+
+
 def decoder_forward(cfg, memory, target, text_lengths, params):
     """params: list of the 22 decoder parameter tensors in DECODER_PARAM_FIELDS order."""
     return DecoderFunction.apply(cfg, memory, target, text_lengths, *params)
@@ -236,16 +280,21 @@ class ConvBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, keep, meta):
-        (G, k, dilation, activation, highway, training, eps, momentum, dropout, gstride) = meta
+        (G, k, dilation, activation, highway, training, eps, momentum, dropout, gstride, stage) = meta
         _require_cuda(x, weight, gamma, beta)
-        x, weight = _f32c(x), _f32c(weight)
+        x = _f32c(x)
         NB, GC, L = x.shape
         Cin = GC // G
-        Cout = weight.shape[0] // G
-        assert weight.shape[1] == Cin and weight.shape[2] == k, (weight.shape, Cin, k)
-        assert gamma.stride(-1) == 1 and beta.stride(-1) == 1
+        if stage == 2:          # batch norm only
+            Cout = Cin
+        else:
+            weight = _f32c(weight)
+            Cout = weight.shape[0] // G
+            assert weight.shape[1] == Cin and weight.shape[2] == k, (weight.shape, Cin, k)
+        if stage != 1:
+            assert gamma.stride(-1) == 1 and beta.stride(-1) == 1
         shape = _lib.ConvBlockShape(NB, G, Cin, Cout, L, k, dilation, ACTIVATIONS[activation], int(highway), int(training),
-                                    eps, momentum, dropout)
+                                    eps, momentum, dropout, stage)
         lib = _lib.load()
         saved = _bytes(lib.b200tts_convblock_saved_bytes(ctypes.byref(shape)), x.device)
         ws = _bytes(lib.b200tts_convblock_workspace_bytes(ctypes.byref(shape)), x.device)
@@ -268,9 +317,13 @@ class ConvBlockFunction(torch.autograd.Function):
         ws = _bytes(lib.b200tts_convblock_workspace_bytes(ctypes.byref(shape)), x.device)
         dout = _f32c(dout)
         dx = torch.empty_like(x)
-        dweight = torch.zeros_like(weight)
+        dweight = torch.zeros_like(weight) if weight is not None else None
         # gamma / beta may be strided views of one generated-affine tensor: produce gradients in the same geometry
         G, Cout, gs = shape.G, shape.Cout, ctx.gstride
+        if shape.stage == 1:    # convolution only: no affine parameters
+            check(lib.b200tts_convblock_backward(ctypes.byref(shape), ptr(x), ptr(weight), None, None, gs, None, ptr(ctx.saved_buf), ptr(dout),
+                                                 ptr(dx), ptr(dweight), None, None, ptr(ws), _stream()), 'b200tts_convblock_backward')
+            return dx, dweight, None, None, None, None, None, None
         dgb = torch.zeros(2 * G * Cout, device=x.device, dtype=torch.float32)
         if gs == Cout:      # plain batch norm: separate dense gamma / beta
             dgamma, dbeta = dgb[:G * Cout], dgb[G * Cout:]
@@ -288,9 +341,50 @@ class ConvBlockFunction(torch.autograd.Function):
 
 
 def conv_block(x, weight, gamma, beta, running_mean, running_var, keep, groups, kernel, dilation, activation, highway,
-               training, eps, momentum, dropout, gstride):
-    meta = (groups, kernel, dilation, activation, highway, training, eps, momentum, dropout, gstride)
+               training, eps, momentum, dropout, gstride, stage=0):
+    """stage 0: the whole block; 1: grouped convolution only (gamma / beta None); 2: batch norm (+ activation / dropout) only (weight None)."""
+    meta = (groups, kernel, dilation, activation, highway, training, eps, momentum, dropout, gstride, stage)
     return ConvBlockFunction.apply(x, weight, gamma, beta, running_mean, running_var, keep, meta)
+
+
+# ------------------------------------------------------------------------------------------------
+# one LSTM cell step (module-level API of ZoneoutLSTMCell / DropoutLSTMCell)
+# ------------------------------------------------------------------------------------------------
+class LSTMCellFunction(torch.autograd.Function):
+    """(h, c) = cell(gates_pre, h_prev, c_prev) with the regulariser of the cell kind (reference modules/layers.py:26-34, 44-47);
+    gates_pre = x . W_ih^T + b_ih + h . W_hh^T + b_hh comes from the library GEMM."""
+
+    @staticmethod
+    def forward(ctx, gates_pre, h_prev, c_prev, mask_h, mask_c, meta):
+        kind, training, rate_h, rate_c = meta
+        _require_cuda(gates_pre, h_prev, c_prev)
+        gates = _f32c(gates_pre).clone()
+        h_prev, c_prev = _f32c(h_prev), _f32c(c_prev)
+        B, D = h_prev.shape
+        h, c = torch.empty_like(h_prev), torch.empty_like(c_prev)
+        check(_lib.load().b200tts_lstm_cell_forward(B, D, kind, int(training), rate_h, rate_c, ptr(gates), ptr(h_prev), ptr(c_prev), ptr(mask_h),
+                                                    ptr(mask_c), ptr(h), ptr(c), _stream()), 'b200tts_lstm_cell_forward')
+        ctx.meta, ctx.masks = meta, (mask_h, mask_c)
+        ctx.save_for_backward(gates, c_prev)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        gates, c_prev = ctx.saved_tensors
+        kind, training, rate_h, rate_c = ctx.meta
+        B, D = c_prev.shape
+        dh = _f32c(dh) if dh is not None else torch.zeros_like(c_prev)
+        dc_io = _f32c(dc).clone() if dc is not None else torch.zeros_like(c_prev)
+        dh_prev, dgates = torch.empty_like(c_prev), torch.empty_like(gates)
+        check(_lib.load().b200tts_lstm_cell_backward(B, D, kind, int(training), rate_h, rate_c, ptr(gates), ptr(c_prev), ptr(ctx.masks[0]),
+                                                     ptr(ctx.masks[1]), ptr(dh), ptr(dc_io), ptr(dh_prev), ptr(dgates), _stream()),
+              'b200tts_lstm_cell_backward')
+        return dgates, dh_prev, dc_io, None, None, None
+
+
+def lstm_cell(cell_input, h, c, w_ih, w_hh, b_ih, b_hh, kind, training, rate_h, rate_c, mask_h=None, mask_c=None):
+    gates = linear(cell_input, w_ih, b_ih) + linear(h, w_hh, b_hh)
+    return LSTMCellFunction.apply(gates, h, c, mask_h, mask_c, (int(kind), bool(training), float(rate_h), float(rate_c)))
 
 
 class GeneratorFunction(torch.autograd.Function):
@@ -423,3 +517,55 @@ class LinearFunction(torch.autograd.Function):
 
 def linear(x, weight, bias=None):
     return LinearFunction.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused loss
+# ------------------------------------------------------------------------------------------------
+class TacotronLossFunction(torch.autograd.Function):
+    """[2*MSE(pre), MSE(post), stop BCE / (N + 2), guided attention] as ONE library op each way (reference modules/tacotron2.py:439-485);
+    the guided-attention weights are evaluated in closed form inside the kernels (no [B, T, L] weight tensor, no Python loop)."""
+
+    @staticmethod
+    def forward(ctx, pre, post, stop, align, pre_target, post_target, stop_target, text_lengths, target_lengths, meta):
+        guided, g, pos_weight = meta
+        _require_cuda(pre, post, stop, pre_target, post_target, stop_target)
+        pre, post, stop, pre_target, post_target, stop_target = [_f32c(t) for t in (pre, post, stop, pre_target, post_target, stop_target)]
+        align = _f32c(align) if align is not None else None
+        B, N, T = pre.shape
+        L = align.shape[2] if align is not None else 1
+        dev = pre.device
+        tl = text_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        ml = target_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        shape = _lib.LossShape(B, N, T, L, int(bool(guided) and align is not None), float(g), float(pos_weight))
+        lib = _lib.load()
+        ws = _bytes(lib.b200tts_loss_workspace_bytes(), dev)
+        losses = torch.empty(4, device=dev, dtype=torch.float32)
+        check(lib.b200tts_tacotron_loss_forward(ctypes.byref(shape), ptr(pre), ptr(pre_target), ptr(post), ptr(post_target), ptr(stop),
+                                                ptr(stop_target), ptr(align), ptr(tl), ptr(ml), ptr(losses), ptr(ws), _stream()),
+              'b200tts_tacotron_loss_forward')
+        ctx.shape = shape
+        ctx.has_align = align is not None
+        ctx.align_shape = None if align is None else tuple(align.shape)
+        ctx.save_for_backward(pre, post, stop, pre_target, post_target, stop_target, tl, ml)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        pre, post, stop, pre_target, post_target, stop_target, tl, ml = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        g = _f32c(g)
+        d_pre = torch.empty_like(pre) if need[0] else None
+        d_post = torch.empty_like(post) if need[1] else None
+        d_stop = torch.empty_like(stop) if need[2] else None
+        d_align = torch.empty(ctx.align_shape, device=pre.device, dtype=torch.float32) if (need[3] and ctx.has_align) else None
+        check(_lib.load().b200tts_tacotron_loss_backward(ctypes.byref(ctx.shape), ptr(pre), ptr(pre_target), ptr(post), ptr(post_target),
+                                                         ptr(stop), ptr(stop_target), ptr(tl), ptr(ml), ptr(g), ptr(d_pre), ptr(d_post),
+                                                         ptr(d_stop), ptr(d_align), _stream()), 'b200tts_tacotron_loss_backward')
+        return d_pre, d_post, d_stop, d_align, None, None, None, None, None, None
+
+
+def tacotron_loss(pre, post, stop, align, pre_target, post_target, stop_target, text_lengths, target_lengths, guided, g, pos_weight=100.0):
+    """-> tensor [4]: mel_pre, mel_pos, stop_token, guided_att (0 when `guided` is false)."""
+    return TacotronLossFunction.apply(pre, post, stop, align, pre_target, post_target, stop_target, text_lengths, target_lengths,
+                                      (guided, g, pos_weight))

@@ -56,24 +56,25 @@ class MultiEncoder(torch.nn.Module):
         self._encoders = ModuleList([Encoder(*encoder_args) for _ in range(num_langs)])
 
     def forward(self, x, x_lenghts, x_langs):
-        xs = None
-        x_langs_normed = x_langs / x_langs.sum(2, keepdim=True)[0]
-        for l in range(self._num_langs):
-            w = x_langs_normed[:, :, l].reshape(x.shape[0], -1, 1)
-            if not w.bool().any():
-                continue
-            ex = self._encoders[l](x, x_lenghts)
-            xs = w * ex if xs is None else xs + w * ex
-        return xs
+        """x_langs [B, L, G]: per-character language weights.  The reference divides by `x_langs.sum(2, keepdim=True)[0]`
+        (encoder.py:88): the weight sums of utterance 0, broadcast over the batch."""
+        share = x_langs / x_langs.sum(dim=2, keepdim=True)[0].unsqueeze(0)          # [B, L, G]
+        mixed = None
+        for lang, encoder in enumerate(self._encoders):
+            w = share[..., lang:lang + 1]
+            if not bool((w != 0).any()):
+                continue                                  # languages that are not requested are not encoded at all
+            part = w * encoder(x, x_lenghts)
+            mixed = part if mixed is None else mixed + part
+        return mixed
 
 
-def _mix_languages(x, x_langs, groups):
-    """Inference-time per-character language blending (encoder.py:213-219); the normaliser comes from position 0."""
-    xr = torch.zeros(1, x.shape[1], x.shape[2], device=x.device)
-    x_langs_normed = x_langs / x_langs.sum(2, keepdim=True)[0]
-    for l in range(groups):
-        xr[0] += x_langs_normed[0, :, l].reshape(-1, 1) * x[l]
-    return xr
+def _mix_languages(per_language, x_langs):
+    """Code-switching / accent blending at inference (encoder.py:213-219): `per_language` [G, L, E] holds the one input encoded by
+    every language's generated weights, `x_langs` [1, L, G] the per-character language weights; each character takes the convex
+    combination given by its own normalised weights."""
+    share = x_langs[0] / x_langs[0].sum(dim=1, keepdim=True)                        # [L, G]
+    return torch.einsum('lg,gle->le', share, per_language).unsqueeze(0)
 
 
 class ConvolutionalEncoder(torch.nn.Module):
@@ -106,7 +107,7 @@ class ConvolutionalEncoder(torch.nn.Module):
         x = x.transpose(1, 2).reshape(bs // self._groups, self._groups * self._input_dim, -1).contiguous()
         x = self._layers(x)
         x = x.reshape(bs, self._output_dim, -1).transpose(1, 2)
-        return _mix_languages(x, x_langs, self._groups) if mixing else x
+        return _mix_languages(x, x_langs) if mixing else x
 
 
 class GeneratedConvolutionalEncoder(torch.nn.Module):
@@ -144,4 +145,4 @@ class GeneratedConvolutionalEncoder(torch.nn.Module):
         x = x.transpose(1, 2).reshape(bs // self._groups, self._groups * self._input_dim, -1).contiguous()
         _, x = self._layers((e, x))
         x = x.reshape(bs, self._output_dim, -1).transpose(1, 2)
-        return _mix_languages(x, x_langs, self._groups) if mixing else x
+        return _mix_languages(x, x_langs) if mixing else x

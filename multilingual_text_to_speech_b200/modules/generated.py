@@ -32,8 +32,21 @@ class Conv1dGenerated(torch.nn.Module):
         return flat.view(self._out_channels, self._in_channels // self._groups, self._kernel_size)
 
     def forward(self, generator_embedding, x):
-        raise NotImplementedError('Conv1dGenerated is fused into ConvBlockGenerated (conv + batch norm in one op); '
-                                  'call ConvBlockGenerated or .generate()')
+        """Standalone generated grouped convolution (generated.py:34-42): kernel synthesis + the conv-only stage of the block op.
+        (Inside ConvBlockGenerated the convolution, batch norm and activation are ONE op.)"""
+        kernel = self.generate(generator_embedding)
+        out = F.conv_block(x, kernel, None, None, None, None, None, self._groups, self._kernel_size, self._dilation, 'identity', False,
+                           self.training, 0.0, 0.0, 0.0, 0, stage=1)
+        # the reference convolves WITHOUT padding (its caller pads, layers.py:112-115,126); the library op is 'same'-padded, and the
+        # un-padded ("valid") result is exactly its centre
+        pad = (self._kernel_size - 1) * self._dilation // 2
+        if pad:
+            out = out[:, :, pad:out.shape[2] - pad]
+        if self._bias is not None:
+            bias = F.GeneratorFunction.apply(generator_embedding, self._bottleneck.weight, self._bottleneck.bias, self._bias.weight,
+                                             self._bias.bias)
+            out = out + bias.reshape(1, -1, 1)
+        return out
 
 
 class BatchNorm1dGenerated(torch.nn.Module):
@@ -57,4 +70,11 @@ class BatchNorm1dGenerated(torch.nn.Module):
                                          self._affine.weight, self._affine.bias)
 
     def forward(self, generator_embedding, x):
-        raise NotImplementedError('BatchNorm1dGenerated is fused into ConvBlockGenerated; call that or .generate()')
+        """Standalone generated batch norm (generated.py:71-96): affine synthesis + the batch-norm-only stage of the block op."""
+        affine = self.generate(generator_embedding)
+        C = self._num_features
+        out = F.conv_block(x, None, affine[:, :C], affine[:, C:], self.running_mean, self.running_var, None, self._groups, 1, 1, 'identity',
+                           False, self.training, self._eps, self._momentum, 0.0, 2 * C, stage=2)
+        if self.training:
+            self.num_batches_tracked += 1
+        return out

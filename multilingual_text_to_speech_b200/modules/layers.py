@@ -12,8 +12,8 @@ def get_activation(name):
 
 
 class ZoneoutLSTMCell(torch.nn.LSTMCell):
-    """LSTM cell with zoneout (layers.py:18-34).  Holds the parameters; the recurrence itself runs inside the
-    fused decoder op, which reads `zoneout_h` / `zoneout_c` from here."""
+    """LSTM cell with zoneout (layers.py:18-34).  Inside `Decoder` the recurrence runs in the fused decoder op, which reads the
+    parameters and `zoneout_h` / `zoneout_c` from here; the standalone `forward` is one library cell step (with autograd)."""
 
     def __init__(self, input_size, hidden_size, zoneout_rate_hidden, zoneout_rate_cell, bias=True):
         super().__init__(input_size, hidden_size, bias)
@@ -21,18 +21,27 @@ class ZoneoutLSTMCell(torch.nn.LSTMCell):
         self.zoneout_h = zoneout_rate_hidden
 
     def forward(self, cell_input, h, c):
-        raise NotImplementedError('the cell is fused into Decoder (b200tts_decoder_forward); call the decoder')
+        mh = mc = None
+        if self.training:
+            mh = MaskSource.keep_mask('cell_h', h.shape, self.zoneout_h, h.device)
+            mc = MaskSource.keep_mask('cell_c', c.shape, self.zoneout_c, c.device)
+        from .. import _lib
+        return F.lstm_cell(cell_input, h, c, self.weight_ih, self.weight_hh, self.bias_ih, self.bias_hh, _lib.CELL_ZONEOUT, self.training,
+                           self.zoneout_h, self.zoneout_c, mh, mc)
 
 
 class DropoutLSTMCell(torch.nn.LSTMCell):
-    """LSTM cell with dropout on the hidden state (layers.py:37-47); parameters only, see ZoneoutLSTMCell."""
+    """LSTM cell with dropout on the hidden state (layers.py:37-47); fused inside `Decoder`, standalone `forward` = one library step."""
 
     def __init__(self, input_size, hidden_size, dropout_rate, bias=True):
         super().__init__(input_size, hidden_size, bias)
         self._dropout = Dropout(dropout_rate)
 
     def forward(self, cell_input, h, c):
-        raise NotImplementedError('the cell is fused into Decoder (b200tts_decoder_forward); call the decoder')
+        mh = MaskSource.keep_mask('cell_h', h.shape, self._dropout.p, h.device) if self.training else None
+        from .. import _lib
+        return F.lstm_cell(cell_input, h, c, self.weight_ih, self.weight_hh, self.bias_ih, self.bias_hh, _lib.CELL_DROPOUT, self.training,
+                           self._dropout.p, 0.0, mh, None)
 
 
 class ConvBlock(torch.nn.Module):

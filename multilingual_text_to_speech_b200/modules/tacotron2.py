@@ -144,17 +144,85 @@ class Decoder(torch.nn.Module):
                 return i + 1
         return len(stop_logits)
 
-    def _decode(self, encoded_input, mask, target, teacher_forcing_ratio, speaker, language):
-        inference = target is None
-        if inference:
-            # free-running decode over max_frames (every step feeds its own previous frame through the prenet inside the fused op),
-            # trimmed afterwards exactly where the reference's loop stops: frames up to the cut do not depend on later ones
-            target = torch.zeros(encoded_input.shape[0], self._output_dim, self._max_frames, device=encoded_input.device)
-            teacher_forcing_ratio = 0.0
+    # frames decoded per library call in inference: the stop rule (one device -> host read of the chunk's stop logits) runs between chunks
+    inference_chunk = 128
+
+    class _StopRule:
+        """Streaming form of the reference's inference exit (tacotron2.py:201-207): returns the number of frames to keep once the stop
+        token (sigmoid >= 0.5, i.e. logit >= 0) has fired for the (stop_frames + 1)-th time."""
+
+        def __init__(self, stop_frames):
+            self.stop_frames, self.remaining, self.seen, self.cut = stop_frames, -1, 0, None
+
+        def feed(self, logits):
+            for fired in (logits >= 0).tolist():
+                self.seen += 1
+                if self.cut is not None or not fired:
+                    continue
+                if self.remaining == -1:
+                    self.remaining = self.stop_frames
+                    continue
+                self.remaining -= 1
+                if self.remaining == 0:
+                    self.cut = self.seen
+            return self.cut
+
+    def _memory(self, encoded_input, speaker, language):
         if hp.multi_speaker and self._speaker_embedding is not None:
             encoded_input = self._add_conditional_embedding(encoded_input, self._speaker_embedding, speaker)
         if hp.multi_language and self._language_embedding is not None:
             encoded_input = self._add_conditional_embedding(encoded_input, self._language_embedding, language)
+        return encoded_input
+
+    def _decode_inference(self, encoded_input, mask, speaker, language):
+        """Free-running decode in chunks with carried state and early exit (tacotron2.py:148-209 with target=None): every chunk is one
+        library call; between chunks the stop rule reads the chunk's stop logits.  B == 1 reproduces the reference; B > 1 (which the
+        reference cannot run: it uses the stop token as a Python bool) stops once every utterance has finished."""
+        memory = self._memory(encoded_input, speaker, language)
+        B, L, M = memory.shape
+        device = memory.device
+        P, D, N = self._prenet._layers[0].weight.shape[0], self._decoder_dim, self._output_dim
+        kind, rate_h, rate_c = self._cell_config()
+        lengths = mask.sum(dim=1).to(torch.int32)
+        state = F.DecoderState(B, D, M, L, N, device)
+        rules = [self._StopRule(hp.stop_frames) for _ in range(B)]
+        specs, stops, aligns = [], [], []
+        done = 0
+        params = self._param_list()
+        while done < self._max_frames:
+            Tc = min(self.inference_chunk, self._max_frames - done)
+            masks = {}
+            for name in ('step_prenet0', 'step_prenet1'):
+                tape = MaskSource.raw(name)
+                if MaskSource.tape is not None:
+                    if tape is not None:
+                        masks[name] = tape[done:done + Tc].to(device=device, dtype=torch.uint8).contiguous()
+                else:
+                    m = MaskSource.keep_mask(name, (Tc, B, P), self._prenet._dropout_rate, device)
+                    if m is not None:
+                        masks[name] = m
+            if self.training:
+                for name in ('att_h', 'gen_h') + (('att_c', 'gen_c') if kind == _lib.CELL_ZONEOUT else ()):
+                    m = MaskSource.keep_mask(name, (Tc, B, D), rate_c if name.endswith('_c') else rate_h, device)
+                    if m is not None:
+                        masks[name] = m
+            cfg = F.DecoderConfig(kind, self.training, rate_h, rate_c, self._prenet._dropout_rate, masks, np.zeros(Tc, dtype=np.uint8))
+            spec, stop, align = F.decoder_forward_chunk(cfg, memory, lengths, params, state, Tc)
+            specs.append(spec); stops.append(stop); aligns.append(align)
+            done += Tc
+            host_stop = stop.float().cpu()
+            cuts = [rule.feed(host_stop[b]) for b, rule in enumerate(rules)]
+            if all(c is not None for c in cuts):
+                break
+        spectrogram, stop, alignment = torch.cat(specs, 1), torch.cat(stops, 1), torch.cat(aligns, 1)
+        cuts = [r.cut if r.cut is not None else done for r in rules]
+        cut = max(cuts)
+        return spectrogram[:, :cut], stop[:, :cut], alignment[:, :cut]
+
+    def _decode(self, encoded_input, mask, target, teacher_forcing_ratio, speaker, language):
+        if target is None:
+            return self._decode_inference(encoded_input, mask, speaker, language)
+        encoded_input = self._memory(encoded_input, speaker, language)
         B, T = encoded_input.shape[0], target.shape[2]
         device = encoded_input.device
         # one coin per step, shared by the batch (tacotron2.py:171); drawn on the host: it steers the launch sequence
@@ -164,17 +232,11 @@ class Decoder(torch.nn.Module):
         else:
             teacher = (np.random.default_rng(MaskSource.seed + MaskSource.counter).random(T) > (1 - teacher_forcing_ratio)).astype(np.uint8)
             MaskSource.counter += 1
-        if inference:
-            teacher = np.zeros(T, dtype=np.uint8)
         teacher = None if teacher.all() else teacher
         kind, rate_h, rate_c = self._cell_config()
         cfg = F.DecoderConfig(kind, self.training, rate_h, rate_c, self._prenet._dropout_rate, self._masks(B, T, device, teacher), teacher)
         lengths = mask.sum(dim=1).to(torch.int32)
-        spectrogram, stop, alignment = F.decoder_forward(cfg, encoded_input, target, lengths, self._param_list())
-        if inference and B == 1:
-            cut = self._stop_cut(stop[0].detach().float().cpu(), hp.stop_frames)
-            spectrogram, stop, alignment = spectrogram[:, :cut], stop[:, :cut], alignment[:, :cut]
-        return spectrogram, stop, alignment
+        return F.decoder_forward(cfg, encoded_input, target, lengths, self._param_list())
 
     def forward(self, encoded_input, encoded_lenghts, target, teacher_forcing_ratio, speaker, language):
         ml = encoded_input.size(1)
@@ -292,8 +354,9 @@ class Tacotron(torch.nn.Module):
 
 class TacotronLoss(torch.nn.Module):
     """Loss terms of the reference (tacotron2.py:411-485): 2*MSE(pre) + MSE(post) + weighted stop BCE / (mels + 2)
-    [+ adversarial classifier CE] [+ guided attention].  The guided-attention weights are evaluated in closed
-    form on the device instead of the reference's per-utterance Python loop with meshgrid."""
+    [+ adversarial classifier CE] [+ guided attention].  The four Tacotron terms are ONE fused library op forward and one backward
+    (csrc/loss.cu); the guided-attention weights are evaluated in closed form inside the kernels instead of the reference's
+    per-utterance Python loop with meshgrid, and no [B, T, L] weight tensor is materialised."""
 
     def __init__(self, guided_att_steps, guided_att_variance, guided_att_gamma):
         super().__init__()
@@ -312,31 +375,15 @@ class TacotronLoss(torch.nn.Module):
         self._g *= self._gamma
         self._g_steps = max(0, self._g_steps - 1)
 
-    def _guided_attention(self, alignments, input_lengths, target_lengths):
-        if self._g_steps == 0:
-            return 0
-        B, T, L = alignments.shape
-        dev = alignments.device
-        f = torch.arange(T, dtype=torch.float, device=dev)[None, :, None]
-        l = torch.arange(L, dtype=torch.float, device=dev)[None, None, :]
-        tl = target_lengths.to(dev).float()[:, None, None]
-        il = input_lengths.to(dev).float()[:, None, None]
-        weights = 1 - torch.exp(-(l / il - f / tl) ** 2 / (2 * self._g ** 2))
-        weights = weights * ((f < tl) & (l < il))
-        loss = torch.sum(weights * alignments, dim=(1, 2))
-        return torch.mean(loss / target_lengths.to(dev).float())
-
     def forward(self, source_length, target_length, pre_prediction, pre_target, post_prediction, post_target, stop, target_stop,
                 alignment, speaker, speaker_prediction, encoder_outputs, classifier):
-        stop_balance = torch.tensor([100], device=stop.device, dtype=torch.float32)
-        losses = {
-            'mel_pre': 2 * TF.mse_loss(pre_prediction, pre_target),
-            'mel_pos': TF.mse_loss(post_prediction, post_target),
-            'stop_token': TF.binary_cross_entropy_with_logits(stop, target_stop, pos_weight=stop_balance) / (hp.num_mels + 2),
-        }
+        guided = bool(hp.guided_attention_loss) and self._g_steps > 0
+        terms = F.tacotron_loss(pre_prediction, post_prediction, stop, alignment if guided else None, pre_target, post_target,
+                                target_stop, source_length, target_length, guided, self._g, 100.0)
+        losses = {'mel_pre': terms[0], 'mel_pos': terms[1], 'stop_token': terms[2]}
         if hp.reversal_classifier:
             losses['lang_class'] = ReversalClassifier.loss(source_length.to(stop.device), speaker, speaker_prediction)
             losses['lang_class'] = losses['lang_class'] * (hp.reversal_classifier_w / (hp.num_mels + 2))
         if hp.guided_attention_loss:
-            losses['guided_att'] = self._guided_attention(alignment, source_length, target_length)
+            losses['guided_att'] = terms[3] if guided else 0
         return sum(losses.values()), losses

@@ -1,11 +1,14 @@
-"""Tacotron.inference (synthesize.py entry point, reference tacotron2.py:387-408): free-running decode inside the fused op, trimmed
-at the stop token like the reference's loop.  Checked against the same model's eval-mode forward with a zero teacher-forcing ratio
-(whose free-running path is pinned to the reference by the `lj_eval_free` golden case)."""
+"""Tacotron.inference (synthesize.py entry point) against golden vectors of the UNMODIFIED reference's own `inference()`
+(modules/tacotron2.py:387-408, :201-207; tests/golden/make_golden_inference.py): chunked free-running decode with carried state and
+early exit, the always-on prenet dropout replayed from the recorded masks, and the per-character language-mixing branch of the
+generated encoder (modules/encoder.py:213-219)."""
+import json
+import os
+import numpy as np
 import pytest
 import torch
 
-import model_cases
-from helpers import Golden
+from helpers import GOLDEN_DIR, assert_close
 
 pytestmark = pytest.mark.gpu
 
@@ -17,26 +20,45 @@ def _built():
     assert torch.cuda.is_available()
 
 
-def test_inference_matches_free_running_forward():
-    from multilingual_text_to_speech_b200.rng import MaskSource
+def _load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}
+    tape = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('tape.')}
+    inp = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('in.')}
+    return meta, sd, tape, inp, torch.from_numpy(z['out.post'])
+
+
+@pytest.mark.parametrize('name', ['inf_lj', 'inf_generated_mix'])
+@pytest.mark.parametrize('chunk', [7, 128])
+def test_inference_matches_reference(name, chunk):
+    from multilingual_text_to_speech_b200 import functional as F
     from multilingual_text_to_speech_b200.params.params import Params as hp
-    from multilingual_text_to_speech_b200.modules.tacotron2 import Decoder
-    g = Golden('lj_eval_free')
+    from multilingual_text_to_speech_b200.modules.tacotron2 import Tacotron, Decoder
+    from multilingual_text_to_speech_b200.rng import MaskSource
+    meta, sd, tape, inp, ref = _load(name)
+    hp.reset()
+    hp.load_state_dict(meta['hp'])
+    model = Tacotron()
+    model.load_state_dict(sd, strict=True)
     dev = torch.device('cuda:0')
-    model = model_cases.build_model(g, dev).eval()
-    T = 24
-    model._decoder._max_frames = T
-    text = g.inputs['text'][0].to(dev)
-    L = int(text.shape[0])
-    MaskSource.manual_seed(77)
-    post_inf = model.inference(text.clone())
-    # the same decode through forward(): eval mode, teacher forcing ratio 0 -> every frame free-running; same mask stream
-    MaskSource.manual_seed(77)
-    with torch.no_grad():
-        post, pre, stop, align, _, _ = model(text[None], torch.tensor([L], device=dev), torch.zeros(1, hp.num_mels, T, device=dev),
-                                             torch.tensor([T], device=dev), None, None, 0.0)
-    cut = Decoder._stop_cut(stop[0].float().cpu(), hp.stop_frames)
-    assert post_inf.shape == (hp.num_mels, cut), (post_inf.shape, cut)
-    if cut == T:       # nothing trimmed: the post-net saw the same frames
-        assert torch.allclose(post_inf, post[0], rtol=1e-4, atol=1e-5)
-    assert torch.isfinite(post_inf).all()
+    model = model.to(dev).eval()
+    calls = []
+    orig = F.decoder_forward_chunk
+    F.decoder_forward_chunk = lambda *a, **k: (calls.append(a[-1]), orig(*a, **k))[1]
+    old_chunk = Decoder.inference_chunk
+    Decoder.inference_chunk = chunk
+    MaskSource.use_tape(tape)
+    try:
+        language = inp['language'].to(dev) if 'language' in inp else None
+        out = model.inference(inp['text'].to(dev), speaker=None, language=language)
+    finally:
+        MaskSource.use_tape(None)
+        Decoder.inference_chunk = old_chunk
+        F.decoder_forward_chunk = orig
+    T = meta['T']
+    assert tuple(out.shape) == tuple(ref.shape) == (hp.num_mels, T), (out.shape, ref.shape)
+    assert_close(out, ref, 1e-3, 1e-4, f'{name}: inference spectrogram')
+    # early exit: no more chunks were decoded than the stop rule needed (the reference stops after frame T of max_output_length)
+    assert T < hp.max_output_length
+    assert sum(calls) == min(-(-T // chunk) * chunk, hp.max_output_length), (calls, T)
