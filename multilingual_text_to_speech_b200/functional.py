@@ -256,9 +256,27 @@ def decoder_forward_chunk(cfg, memory, text_lengths, params, state, frames):
     return spec, stop, align
 
 
+# the persistent loop kernels of the bf16 mode hold the whole batch in one MMA tile (<= 64 utterances)
+MAX_PERSIST_BATCH = 64
+
+
 def decoder_forward(cfg, memory, target, text_lengths, params):
-    """params: list of the 22 decoder parameter tensors in DECODER_PARAM_FIELDS order."""
-    return DecoderFunction.apply(cfg, memory, target, text_lengths, *params)
+    """params: list of the 22 decoder parameter tensors in DECODER_PARAM_FIELDS order.
+
+    Utterances are independent inside the decoder (only the weights are shared), so a batch larger than the persistent kernels' tile
+    (B > 64: BASELINE configs[3..4] run 65 / 80 per GPU) is decoded as ceil(B / 64) equal slices through the same fused op instead of
+    dropping to the per-step kernel chains; parameter gradients of the slices add up in autograd."""
+    B = memory.shape[0]
+    if B <= MAX_PERSIST_BATCH or _lib.get_precision() != 'bf16':
+        return DecoderFunction.apply(cfg, memory, target, text_lengths, *params)
+    nslice = -(-B // MAX_PERSIST_BATCH)
+    bounds = [round(k * B / nslice) for k in range(nslice + 1)]
+    outs = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        masks = {k: v[:, lo:hi].contiguous() for k, v in cfg.masks.items()}
+        sub = DecoderConfig(cfg.cell_kind, cfg.training, cfg.rate_h, cfg.rate_c, cfg.prenet_rate, masks, cfg.teacher)
+        outs.append(DecoderFunction.apply(sub, memory[lo:hi], target[lo:hi], text_lengths[lo:hi], *params))
+    return tuple(torch.cat([o[j] for o in outs], dim=0) for j in range(3))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -4,6 +4,10 @@ The reference clips the global gradient norm (`clip_grad_norm_(model.parameters(
 `torch.optim.Adam(lr, weight_decay)` (coupled L2 decay, not AdamW) over ~400 parameter tensors with a `StepLR` schedule.  Here every
 parameter is a view of ONE flat fp32 buffer (`FlatParams`), its gradient a view of the all-reduced flat gradient bucket
 (`distributed.GradBucket`), and one library call (`b200tts_adam_clip_step`: norm, clip, Adam, three launches) updates the model.
+
+Difference to torch.optim.Adam worth knowing: a parameter that received NO gradient in a step has a zero (not a None) gradient here,
+so it is still weight-decayed and its moments decay -- torch skips such parameters.  Every parameter of the Tacotron model receives a
+gradient in every training step, so the two coincide on the hot path (tests/test_gpu_optim.py checks the real model).
 """
 import ctypes
 
@@ -11,23 +15,22 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr
+from .distributed import flat_layout
 
 
 class FlatParams:
-    """Re-homes the trainable parameters of `model` as views of one flat buffer (same order as `GradBucket`)."""
+    """Re-homes the trainable parameters of `model` as views of one flat buffer (same order and same 16-byte aligned layout as
+    `GradBucket`; the padding elements stay zero in the parameter, gradient and moment buffers)."""
 
     def __init__(self, model):
         self.params = [p for p in model.parameters() if p.requires_grad]
         ref = self.params[0]
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(total, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            view = self.flat[off:off + n].view_as(p)
+        self.offsets, total = flat_layout(self.params)
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-            off += n
 
 
 class FusedAdam:
@@ -35,7 +38,9 @@ class FusedAdam:
 
     def __init__(self, flat_params, grad_bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None,
                  lr_decay_every=None, lr_decay=1.0):
-        assert flat_params.flat.numel() == grad_bucket.flat.numel(), 'parameter and gradient buffers differ in size'
+        assert flat_params.flat.numel() == grad_bucket.flat.numel() and flat_params.offsets == grad_bucket.offsets, \
+            'parameter and gradient buffers differ in layout'
+        self.bucket = grad_bucket
         self.p, self.g = flat_params.flat, grad_bucket.flat
         self.m, self.v = torch.zeros_like(self.p), torch.zeros_like(self.p)
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
@@ -55,6 +60,7 @@ class FusedAdam:
         if not self.p.is_cuda:
             raise _lib.B200TTSError('FusedAdam needs CUDA buffers (there is no CPU fallback)')
         lib = _lib.load()
+        self.bucket.bind()          # a gradient that escaped the bucket (zero_grad(set_to_none=True)) is folded back in, never dropped
         if self._scratch is None:
             self._scratch = torch.zeros(lib.b200tts_adam_clip_scratch_floats(), dtype=torch.float32, device=self.p.device)
         lr = self.current_lr()

@@ -24,6 +24,11 @@ PARAM_KEYS = [
 ]
 
 
+# bf16 perf-mode gradient gates (relative L2 error vs the operand-quantised oracle), see run_case_bf16
+GRAD_REL_BOUND = 4e-2
+GRAD_REL_BOUND_ATT = 8e-2
+
+
 class Case:
     """hp (namespace), sd (fp32 CPU state dict, reference names), memory [B,L,M], lengths, target [B,N,T], tape."""
     pass
@@ -191,8 +196,12 @@ def run_case_bf16(c, check_grads=True, verbose=False):
                 rel = float((got - ref).norm() / (ref.norm() + 1e-12))
                 cos = float((got * ref).sum() / (got.norm() * ref.norm() + 1e-30))
                 report['d_' + name] = rel
-                # sharpened synthetic attention makes a few (utterance, position) pairs chaotic under bf16; the direction must hold
-                assert cos > 0.9, (c.name, name, rel, cos)
+                # relative L2 error against the gradient of the operand-quantised oracle (same bf16 operands, wide accumulation):
+                # what remains is the kernels' own arithmetic (fp32 accumulation order, tanh.approx / ex2 gate math, bf16 rounding of the
+                # gate GRADIENTS in the recurrent products).  Bounds: measured values (<= 2e-2 everywhere, attention parameters up to
+                # ~4e-2 on the sharpened synthetic attention) with ~2x margin; a wrong block or a 30 % error fails.
+                bound = GRAD_REL_BOUND_ATT if name.startswith('attn_') or name in ('memory',) else GRAD_REL_BOUND
+                assert rel < bound and cos > 0.995, (c.name, name, rel, cos, bound)
     finally:
         _lib.set_precision('fp32')
     if verbose:

@@ -198,6 +198,7 @@ def run_gpu(mode, fx=None, with_grads=True, verbose=True):
         rs = ref['stop']
         real = rs < 999.0
         rep['stop_sign_mismatch'] = int(((stop.detach().cpu() > 0) != (rs > 0))[real & (rs.abs() > 1e-5)].sum())
+        rep['stop_sign_mismatch_margin>2e-3'] = int(((stop.detach().cpu() > 0) != (rs > 0))[real & (rs.abs() > 2e-3)].sum())
         if with_grads:
             crit = TacotronLoss(hp.guided_attention_steps, fx.meta['guided_g'], hp.guided_attention_gain)
             loss, parts = crit(i['text_length'], i['target_length'], pre, i['target'], post, i['target'], stop, i['stop_target'],

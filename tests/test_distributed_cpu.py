@@ -45,5 +45,9 @@ def test_flat_bucket_allreduce_matches_global_batch_gradient():
     model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     x = torch.cat([res[0][1], res[1][1]]); y = torch.cat([res[0][2], res[1][2]])
     torch.nn.functional.mse_loss(model(x), y).backward()
-    ref = torch.cat([p.grad.flatten() for p in model.parameters()])
+    from multilingual_text_to_speech_b200.distributed import flat_layout
+    offsets, total = flat_layout(list(model.parameters()))          # tensors start on 16-byte boundaries; the padding stays zero
+    ref = torch.zeros(total)
+    for p, off in zip(model.parameters(), offsets):
+        ref[off:off + p.numel()] = p.grad.flatten()
     assert torch.allclose(res[0][0], ref, rtol=1e-5, atol=1e-7)

@@ -139,6 +139,9 @@ def test_gemm_bf16_mode(M, N, K, ta, tb, splitk):
     dict(B=40, L=64, T=24, kind='zoneout', seed=1),
     dict(B=5, L=33, T=21, M=292, kind='dropout', seed=2),
     dict(B=60, L=180, T=16, kind='zoneout', seed=6),
+    dict(B=12, L=300, T=12, kind='zoneout', seed=7),            # BASELINE configs[4]: texts up to 300 on the persistent kernels
+    dict(B=80, L=50, T=10, kind='dropout', seed=8),             # B > 64 (configs[3..4] run 65 / 80 per GPU): decoded as two slices
+    dict(B=65, L=44, T=9, M=292, kind='zoneout', seed=9),
 ])
 def test_decoder_bf16_perf_mode(kw):
     """Persistent weight-stationary bf16 kernels (decoder_persist.cu) + bf16 tensor-core GEMMs."""

@@ -40,3 +40,68 @@ def test_fused_adam_matches_torch(max_norm):
         for p, q in zip(model.parameters(), ref.parameters()):
             assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), (it, float((p - q).abs().max()))
     assert model[0].weight.data_ptr() >= flat.flat.data_ptr()          # parameters live inside the flat buffer
+
+
+def test_flat_layout_is_aligned_and_survives_set_to_none():
+    from multilingual_text_to_speech_b200.distributed import GradBucket, flat_layout
+    dev = torch.device('cuda:0')
+    model = torch.nn.Sequential(torch.nn.Linear(3, 1), torch.nn.Linear(1, 7)).to(dev)      # 1-element bias in the middle of the buffer
+    bucket = GradBucket(model, 1)
+    offs, total = flat_layout(bucket.params)
+    assert all(o % 4 == 0 for o in offs) and total % 4 == 0
+    assert all(p.grad.data_ptr() % 16 == 0 for p in bucket.params)
+    x = torch.randn(5, 3, device=dev)
+    model(x).sum().backward()
+    want = [p.grad.clone() for p in bucket.params]
+    model.zero_grad(set_to_none=True)                      # detaches every .grad from the bucket
+    bucket.zero()                                          # re-binds
+    model(x).sum().backward()
+    for p, w in zip(bucket.params, want):
+        lo = bucket.flat.data_ptr()
+        assert lo <= p.grad.data_ptr() < lo + bucket.flat.numel() * 4
+        assert torch.equal(p.grad, w)
+    # a gradient produced while detached is folded back in, not lost
+    model.zero_grad(set_to_none=True)
+    model(x).sum().backward()
+    bucket.allreduce()
+    for p, w in zip(bucket.params, want):
+        assert torch.allclose(p.grad, 2 * w)
+
+
+def test_fused_adam_on_the_real_model():
+    """FlatParams + GradBucket + FusedAdam on a (small-dimension) Tacotron against clip_grad_norm_ + torch.optim.Adam, 3 steps."""
+    import model_cases
+    from helpers import Golden
+    from multilingual_text_to_speech_b200.optim import FlatParams, FusedAdam
+    from multilingual_text_to_speech_b200.distributed import GradBucket
+    from multilingual_text_to_speech_b200.modules.tacotron2 import TacotronLoss
+    from multilingual_text_to_speech_b200.rng import MaskSource
+    from multilingual_text_to_speech_b200.params.params import Params as hp
+    g = Golden('generated_training')
+    dev = torch.device('cuda:0')
+    model, ref = model_cases.build_model(g, dev), model_cases.build_model(g, dev)
+    flat, bucket = FlatParams(model), GradBucket(model, 1)
+    opt = FusedAdam(flat, bucket, lr=1e-3, weight_decay=1e-6, max_grad_norm=0.25)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-6)
+    i = {k: v.to(dev) for k, v in g.inputs.items()}
+
+    def loss_of(m):
+        crit = TacotronLoss(hp.guided_attention_steps, g.meta['guided_g'], hp.guided_attention_gain)
+        MaskSource.use_tape(g.tape)
+        try:
+            post, pre, stop, align, spk, enc = m(i['text'], i['text_length'], i['target'], i['target_length'], i.get('speakers'), i.get('languages'), 1.0)
+        finally:
+            MaskSource.use_tape(None)
+        return crit(i['text_length'], i['target_length'], pre, i['target'], post, i['target'], stop, i['stop_target'], align, i.get('speakers'),
+                    spk, enc, None)[0]
+
+    for it in range(3):
+        bucket.zero()
+        loss_of(model).backward()
+        ropt.zero_grad()
+        loss_of(ref).backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.25)
+        opt.step(); ropt.step()
+        worst = max(float((p - q).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
+        assert worst < 2e-5, (it, worst)
+    assert all(p.data_ptr() % 16 == 0 for p in model.parameters())

@@ -69,3 +69,22 @@ def test_inference_stop_rule_matches_reference_loop():
             assert Decoder._stop_cut(x, sf) == reference_loop(x, sf)
     assert Decoder._stop_cut(torch.full((10,), -3.0), 5) == 10                      # never fires: all frames
     assert Decoder._stop_cut(torch.tensor([-1.0, 2.0, 2.0, -1.0, 2.0, 2.0]), 3) == 6   # fires at 1 (arms), 2, 4, 5 -> cut after frame 5
+
+
+def test_streaming_stop_rule_equals_the_loop_rule():
+    """Decoder._StopRule fed chunk by chunk (the chunked inference) cuts exactly where the one-shot rule does."""
+    import torch
+    from multilingual_text_to_speech_b200.modules.tacotron2 import Decoder
+    g = torch.Generator().manual_seed(5)
+    for trial in range(200):
+        n = int(torch.randint(1, 90, (1,), generator=g))
+        x = torch.randn(n, generator=g) * 2 + (torch.arange(n) - n / 2) * 0.1
+        for sf in (1, 5):
+            want = Decoder._stop_cut(x, sf)
+            chunk = int(torch.randint(1, 17, (1,), generator=g))
+            rule, cut = Decoder._StopRule(sf), None
+            for i in range(0, n, chunk):
+                cut = rule.feed(x[i:i + chunk])
+                if cut is not None:
+                    break
+            assert (cut if cut is not None else n) == want, (trial, sf, chunk, cut, want)
