@@ -100,7 +100,7 @@ __device__ __forceinline__ void st_peer_f32(const float* local_smem, uint32_t pe
 }
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-#define BPROF_DECL long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
+#define BPROF_DECL long long prof_acc[BPROF_N] = {}; long long prof_t = clock64();
 #define BPROF_MARK(slot)                                                                                         \
     do {                                                                                                         \
         if (p.prof && threadIdx.x == 0) { const long long now = clock64(); prof_acc[slot] += now - prof_t; prof_t = now; } \
@@ -108,10 +108,11 @@ __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefe
 #define BPROF_FLUSH                                                                                              \
     do {                                                                                                         \
         if (p.prof && threadIdx.x == 0)                                                                          \
-            for (int k9 = 0; k9 < 8; ++k9) p.prof[(size_t)blockIdx.x * 8 + k9] = prof_acc[k9];                   \
+            for (int k9 = 0; k9 < BPROF_N; ++k9) p.prof[(size_t)blockIdx.x * BPROF_N + k9] = prof_acc[k9];       \
     } while (0)
 
 // Generator-LSTM reverse loop (no attention): NOUT = D.
+#define BPROF_N 8
 __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_kernel(const BwdLoopArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -313,6 +314,8 @@ __device__ __forceinline__ void build_pairs(uint32_t* Ph, uint32_t* Pl, const fl
     }
 }
 
+#undef BPROF_N
+#define BPROF_N 16
 template <bool TC>
 __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_constant__ CUtensorMap tmG, const AttBwdArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
@@ -451,6 +454,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             for (int a = tid; a < A; a += PT) { s_qb[a] = p.q[((size_t)i * B + b) * A + a] + p.bias[a]; s_vv[a] = p.v[a]; }
             build_pairs(s_Ph, s_Pl, p.cum + ((size_t)i * B + b) * L, L, half, L16 + 48, tid, PT);
             __syncthreads();
+            BPROF_MARK(8);                                  // PA.a: operands of the step staged
             // dw[l] = dalign + dcum + <dctx, memory[l]> on the tensor cores: A = fragment-major memory (one 16-byte load per lane per
             // MMA), B = (hi(dctx), lo(dctx)) in columns 0 / 1; warp owns position tiles {warp, warp + 8}
             {
@@ -508,6 +512,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 }
             }
             __syncthreads();
+            BPROF_MARK(9);                                  // PA.b: dw = <dctx, memory> MMAs
             // softmax backward: dot = sum_l w[l] dw[l] over ALL positions = own partial + the peer's (exchanged through DSMEM)
             float pdot = 0.f;
             for (int l = t_lo * 16 + tid; l < t_hi * 16 && l < len; l += PT) pdot = fmaf(s_w[l], s_de[l], pdot);
@@ -597,6 +602,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             }
             // dq[a] = sum_l ds[l, a]: reduce over the 8 row lanes, then over warps
             __syncthreads();                               // every warp is done with s_de / s_qb / s_vv / Ph / Pl
+            BPROF_MARK(10);                                 // PA.d: energies backward MMAs (after slot 0 = softmax backward + pair barrier)
 #pragma unroll
             for (int nt = 0; nt < 16; ++nt)
 #pragma unroll
@@ -625,6 +631,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             }
             cluster_arrive();
             cluster_wait();
+            BPROF_MARK(11);                                 // PA.e: dq reduction, G halo exchange, pair barrier
             if (hf == 0 && tid < A) p.dq[((size_t)i * B + b) * A + tid] = pdq + s_dqx[tid];
             // d cum_{i-1}[j] = d cum_i[j] + sum_k G[j + half - k, k] for the own positions (their G rows: own tiles + the halo tile)
             for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) {
@@ -677,6 +684,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                     *reinterpret_cast<float4*>(s_dq + b * A + ((c4 * 4 + 8 * (b & 7)) & (A - 1))) = v;
                 }
                 __syncthreads();
+                BPROF_MARK(13);                             // PB.a: recurrent partials + query gradients loaded
                 const int g = lane >> 2, tq = lane & 3, mt = warp & 3, kh = warp >> 2;      // warp = (16-utterance tile, half of the A range)
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 const int ksteps = A / 32;                                // k-steps of 16 per half
@@ -714,6 +722,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 __syncthreads();
                 if (kh == 1) { d0[0] += acc[0]; d0[1] += acc[1]; d1[0] += acc[2]; d1[1] += acc[3]; }
                 __syncthreads();
+                BPROF_MARK(14);                             // PB.b: dq . Wq on the tensor cores
             }
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
@@ -1098,7 +1107,7 @@ AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s) {
     x.de = take((size_t)s.T * s.B * s.L * 4);
     x.dwpart = take((size_t)s.B * x.MT * s.A * 32 * 4);
     x.dvpart = take((size_t)s.B * x.MT * s.A * 4);
-    x.barrier = take(256 + 148 * 8 * 8);
+    x.barrier = take(256 + 148 * 16 * 8);
     x.total = off;
     return x;
 }

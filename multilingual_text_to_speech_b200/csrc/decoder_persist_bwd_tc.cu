@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_tc_kernel(const __grid_co
     const int B = p.B, D = p.D, NNB = p.NNB;
     const int b0 = bh * BT, n0 = nb * ROWS;
     const int u0 = (gsel * NNB + nb) * UNITS;                 // hidden units whose cell backward this CTA owns
-    const unsigned nblocks = gridDim.x;
+    // batch halves are independent (cell backward and product of a CTA serve the same 32 utterances): one barrier counter per half
+    const unsigned nblocks = (unsigned)(NG * p.NNB);
+    unsigned* const bar_counter = p.barrier + 16 * bh;
     const bool compute = warp < NCW, is_producer = warp == NCW, is_mma = warp == NCW + 1;
 
     unsigned char* sW = smem_raw;                              // [NNB][64 rows (n)][128 B] swizzled: W^T[n0 + r, gate gsel, k]
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_tc_kernel(const __grid_co
             }
         }
         PROF_MARK(0);
-        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) break;
+        if (!grid_barrier(bar_counter, target, nblocks, p.abort_flag, &s_ok)) break;
         PROF_MARK(1);
         if (i == 0) break;
 
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_tc_kernel(const __grid_co
         }
         ++it;
         PROF_MARK(3);
-        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) break;
+        if (!grid_barrier(bar_counter, target, nblocks, p.abort_flag, &s_ok)) break;
         PROF_MARK(4);
     }
     if (p.prof && tid == 0)

@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     const int rb = cta % p.RB, bh = cta / p.RB;
     const int u0 = rb * UNITS, b0 = bh * BT;
     const int Kp = p.Kp, D = p.D, B = p.B;
-    const unsigned nblocks = gridDim.x;
+    // the two batch halves never exchange data (a CTA's LSTM rows and the attention pairs it hosts serve the same 32 utterances):
+    // each half synchronises on its own barrier counter, 64 arrivals instead of 128
+    const unsigned nblocks = (unsigned)p.RB;
+    unsigned* const bar_counter = p.barrier + 16 * (cta / p.RB);
     const bool compute = warp < NCW;
     const bool is_producer = (warp == NCW);        // whole warps run the role loops; one elected lane issues the TMA / MMA instructions
     const bool is_mma = (warp == NCW + 1);
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             }
         }
         PROF_MARK(1);
-        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
+        if (!grid_barrier(bar_counter, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
         PROF_MARK(2);
 
         // =================== h part of step i+1: TMA + tcgen05 run while the attention of step i is computed ===================
@@ -757,7 +760,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             }
             if (compute && i + 1 < p.T) prefetch(i + 1, false);      // L2 hits (prefetched a step ago); they land behind the barrier wait
             PROF_MARK(6);
-            if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
+            if (!grid_barrier(bar_counter, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
             PROF_MARK(7);
         }
     }

@@ -196,7 +196,11 @@ class Decoder(torch.nn.Module):
                 tape = MaskSource.raw(name)
                 if MaskSource.tape is not None:
                     if tape is not None:
-                        masks[name] = tape[done:done + Tc].to(device=device, dtype=torch.uint8).contiguous()
+                        # a recorded tape ends where the reference's loop stopped; frames decoded past it are discarded by the stop rule
+                        part = tape[done:done + Tc].to(device=device, dtype=torch.uint8)
+                        if part.shape[0] < Tc:
+                            part = torch.cat([part, torch.ones(Tc - part.shape[0], B, P, dtype=torch.uint8, device=device)])
+                        masks[name] = part.contiguous()
                 else:
                     m = MaskSource.keep_mask(name, (Tc, B, P), self._prenet._dropout_rate, device)
                     if m is not None:

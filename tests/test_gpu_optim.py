@@ -105,3 +105,15 @@ def test_fused_adam_on_the_real_model():
         worst = max(float((p - q).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
         assert worst < 2e-5, (it, worst)
     assert all(p.data_ptr() % 16 == 0 for p in model.parameters())
+
+
+def test_pinned_prefetcher_delivers_batches_in_order():
+    from multilingual_text_to_speech_b200.utils.data import PinnedPrefetcher
+    batches = [(torch.full((4, 7), k, dtype=torch.long), None, torch.randn(4, 3, 9) + k) for k in range(6)]
+    seen = []
+    for dev in PinnedPrefetcher(batches, 'cuda:0', depth=2):
+        assert dev[0].is_cuda and dev[1] is None and dev[2].is_cuda
+        seen.append((int(dev[0][0, 0]), dev[2].cpu()))
+    assert [k for k, _ in seen] == list(range(6))
+    for (k, got), ref in zip(seen, batches):
+        assert torch.equal(got, ref[2])

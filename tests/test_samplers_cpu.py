@@ -98,3 +98,26 @@ def test_small_samplers():
     r = RandomImbalancedSampler(_DS(items))
     draws = list(r)
     assert len(draws) == 100 and 25 < sum(items[i]['language'] for i in draws) < 75       # both languages about equally likely
+
+
+def test_collate_matches_the_reference_layout_and_fixes_the_sort_branch():
+    """TextToSpeechCollate (dataset/dataset.py:262-322): padding, stop targets from the last `stop_frames` real frames on, and the
+    sort branch (broken in the reference) permuting every field consistently."""
+    import numpy as np
+    from multilingual_text_to_speech_b200.utils.data import TextToSpeechCollate
+    rng = np.random.default_rng(0)
+    items = []
+    for k, (n, f) in enumerate([(5, 30), (9, 44), (3, 12), (9, 40)]):
+        items.append((k % 3, k % 2, list(rng.integers(1, 50, n)), rng.standard_normal((8, f)).astype(np.float32), None))
+    plain = TextToSpeechCollate(False, 8, 5, True, True)(items)
+    text, tl, mel, lin, ml, stop, spk, lang = plain
+    assert text.shape == (4, 9) and mel.shape == (4, 8, 44) and lin is None and stop.shape == (4, 44)
+    assert tl.tolist() == [5, 9, 3, 9] and ml.tolist() == [30, 44, 12, 40] and spk.tolist() == [0, 1, 2, 0] and lang.tolist() == [0, 1, 0, 1]
+    assert text[0, 5:].eq(0).all() and (mel[2, :, 12:] == 0).all() and np.allclose(mel[2, :, :12].numpy(), items[2][3])
+    assert stop[0, :25].eq(0).all() and stop[0, 25:].eq(1).all()            # ones from frame 30 - 5 on, including the padding
+    srt = TextToSpeechCollate(True, 8, 5, True, True)(items)
+    assert srt[1].tolist() == [9, 9, 5, 3] and srt[4].tolist() == [44, 40, 30, 12]      # stable: item 1 before item 3
+    assert srt[6].tolist() == [1, 0, 0, 2] and srt[7].tolist() == [1, 1, 0, 0]
+    assert np.allclose(srt[2][3, :, :12].numpy(), items[2][3]) and srt[0][2, :5].tolist() == [int(v) for v in items[0][2]]
+    fixed = TextToSpeechCollate(False, 8, 5, False, False, pad_text_to=16, pad_frames_to=64)(items)
+    assert fixed[0].shape == (4, 16) and fixed[2].shape == (4, 8, 64) and fixed[6] is None and fixed[7] is None
