@@ -187,6 +187,20 @@ int b200tts_attention_step(int B, int L, int M, int D, int A, int C, int K, cons
                            float* workspace, void* stream);
 
 
+/* Backward of one attention step (autograd of attention.py:39-45,67-86 for the module-level API; the training path runs the fused
+ * decoder backward instead).  q [B, A] = query . Wq^T as the forward computed it (the head of its workspace); cum_prev [B, L] the
+ * cumulative weights the step CONSUMED; weights [B, L] its output.  d_cum [B, L]: in = gradient of the UPDATED cumulative weights,
+ * out = gradient of cum_prev.  d_q [B, A] out (the caller forms d query = d_q . Wq, d Wq += d_q^T . query, d bias += sum_b d_q);
+ * d_memory_transform [B, L, A], d_w_location [A, C], d_w_loc_features [C, K], d_w_energy [A] are ACCUMULATED (+=).
+ * workspace floats: b200tts_attention_step_backward_workspace_elems(B, M, A, C, K).                                              */
+size_t b200tts_attention_step_backward_workspace_elems(int B, int M, int A, int C, int K);
+int b200tts_attention_step_backward(int B, int L, int M, int A, int C, int K, const float* q, const float* memory,
+                                    const float* memory_transform, const int32_t* text_lengths, const float* w_location,
+                                    const float* w_loc_features, const float* bias, const float* w_energy, const float* cum_prev,
+                                    const float* weights, const float* d_context, const float* d_weights, float* d_cum, float* d_q,
+                                    float* d_memory_transform, float* d_w_location, float* d_w_loc_features, float* d_w_energy,
+                                    float* workspace, void* stream);
+
 /* ---- convolution block: ConvBlock / HighwayConvBlock / ConvBlockGenerated / HighwayConvBlockGenerated ----
  * modules/layers.py:50-178.  x [NB, G*Cin, L] -> pad((k-1)*dil/2) -> grouped Conv1d(no bias) -> BatchNorm1d
  * (batch statistics over (NB, L) incl. padded positions when training) -> activation -> Dropout ->

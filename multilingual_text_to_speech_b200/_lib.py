@@ -96,6 +96,8 @@ SIGNATURES = {
                                          c_size_t, POINTER(DecoderParams), c_void_p, c_void_p]),
     'b200tts_attention_step_workspace_elems': (c_size_t, [c_int, c_int, c_int]),
     'b200tts_attention_step': (c_int, [c_int] * 7 + [c_void_p] * 13),
+    'b200tts_attention_step_backward_workspace_elems': (c_size_t, [c_int] * 5),
+    'b200tts_attention_step_backward': (c_int, [c_int] * 6 + [c_void_p] * 20),
     'b200tts_convblock_saved_bytes': (c_size_t, [POINTER(ConvBlockShape)]),
     'b200tts_convblock_workspace_bytes': (c_size_t, [POINTER(ConvBlockShape)]),
     'b200tts_convblock_forward': (c_int, [POINTER(ConvBlockShape), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

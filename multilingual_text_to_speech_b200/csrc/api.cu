@@ -82,6 +82,11 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
                           const b200tts_decoder_outputs& fwd_out, const b200tts_decoder_output_grads& dout, const float* fws,
                           float* bws, size_t bws_bytes, const b200tts_decoder_params& dw, float* d_memory, cudaStream_t st);
 size_t decoder_bwd_workspace_floats(const b200tts_decoder_shape& s);
+size_t attention_step_backward_workspace_elems(int B, int M, int A, int C, int K);
+int attention_step_backward_impl(int B, int L, int M, int A, int C, int K, const float* q, const float* memory, const float* memT,
+                                 const int* lengths, const float* Wloc, const float* Wc, const float* bias, const float* v,
+                                 const float* cum_prev, const float* weights, const float* d_ctx, const float* d_weights, float* d_cum,
+                                 float* d_q, float* d_memT, float* d_Wloc, float* d_Wc, float* d_v, float* ws, cudaStream_t st);
 int attention_step_impl(int B, int L, int M, int D, int A, int C, int K, const float* query, const float* memory,
                         const float* memT, const int* lengths, const float* Wq, const float* Wloc, const float* Wc,
                         const float* bias, const float* v, float* cum, float* ctx, float* weights, float* workspace,
@@ -268,6 +273,24 @@ int b200tts_attention_step(int B, int L, int M, int D, int A, int C, int K, cons
                  "attention_step: null argument");
     return attention_step_impl(B, L, M, D, A, C, K, query, memory, memory_transform, text_lengths, w_query, w_location,
                                w_loc_features, bias, w_energy, cum_weights, context, weights, workspace, (cudaStream_t)stream);
+}
+
+size_t b200tts_attention_step_backward_workspace_elems(int B, int M, int A, int C, int K) {
+    return attention_step_backward_workspace_elems(B, M, A, C, K);
+}
+int b200tts_attention_step_backward(int B, int L, int M, int A, int C, int K, const float* q, const float* memory,
+                                    const float* memory_transform, const int32_t* text_lengths, const float* w_location,
+                                    const float* w_loc_features, const float* bias, const float* w_energy, const float* cum_prev,
+                                    const float* weights, const float* d_context, const float* d_weights, float* d_cum, float* d_q,
+                                    float* d_memory_transform, float* d_w_location, float* d_w_loc_features, float* d_w_energy,
+                                    float* workspace, void* stream) {
+    B200_TRY(require_device());
+    B200_REQUIRE(q && memory && memory_transform && text_lengths && w_location && w_loc_features && bias && w_energy && cum_prev && weights &&
+                 d_context && d_cum && d_q && d_memory_transform && d_w_location && d_w_loc_features && d_w_energy && workspace,
+                 "attention_step_backward: null argument");
+    return attention_step_backward_impl(B, L, M, A, C, K, q, memory, memory_transform, text_lengths, w_location, w_loc_features, bias,
+                                        w_energy, cum_prev, weights, d_context, d_weights, d_cum, d_q, d_memory_transform, d_w_location,
+                                        d_w_loc_features, d_w_energy, workspace, (cudaStream_t)stream);
 }
 
 size_t b200tts_convblock_saved_bytes(const b200tts_convblock_shape* s) { return s ? convblock_saved_floats(*s) * sizeof(float) : 0; }

@@ -592,6 +592,39 @@ size_t decoder_bwd_profile_offset(const b200tts_decoder_shape& s, int which) {
     return l.pextra2 * sizeof(float) + att_bwd_extra(s).barrier + 256;
 }
 
+// standalone backward of one attention step (module-level API): per-utterance accumulators in the workspace, reduced over the batch here
+size_t attention_step_backward_workspace_elems(int B, int M, int A, int C, int K) {
+    return (size_t)B * ((size_t)A * C + (size_t)C * K + A + M);
+}
+int attention_step_backward_impl(int B, int L, int M, int A, int C, int K, const float* q, const float* memory, const float* memT,
+                                 const int* lengths, const float* Wloc, const float* Wc, const float* bias, const float* v,
+                                 const float* cum_prev, const float* weights, const float* d_ctx, const float* d_weights, float* d_cum,
+                                 float* d_q, float* d_memT, float* d_Wloc, float* d_Wc, float* d_v, float* ws, cudaStream_t st) {
+    B200_REQUIRE(A <= 128 && A % 4 == 0 && C % 4 == 0 && (A / 4) * (C / 4) <= ATT_THREADS && M <= 512 && (K % 2) == 1,
+                 "attention_step_backward: unsupported dims A=%d C=%d M=%d K=%d", A, C, M, K);
+    float* dWloc_acc = ws;
+    float* dWc_acc = dWloc_acc + (size_t)B * A * C;
+    float* dv_acc = dWc_acc + (size_t)B * C * K;
+    float* dctx_tot = dv_acc + (size_t)B * A;
+    B200_TRY(launch_fill(ws, 0.f, (size_t)B * ((size_t)A * C + (size_t)C * K + A), st));
+    AttnBwdArgs aa{};
+    aa.q = q; aa.memT = memT; aa.memory = memory; aa.lengths = lengths;
+    aa.Wc = Wc; aa.Wloc = Wloc; aa.bias = bias; aa.v = v; aa.cum_prev = cum_prev;
+    aa.w = weights; aa.w_bstride = L; aa.dalign = d_weights; aa.dalign_bstride = L;
+    aa.dctx_static = d_ctx; aa.part = nullptr; aa.nsplit = 0; aa.part_stride = 0; aa.ld_part = 0;
+    aa.dcum = d_cum; aa.dctx_tot = dctx_tot; aa.dq = d_q; aa.dmemT = d_memT;
+    aa.dWloc_acc = dWloc_acc; aa.dWc_acc = dWc_acc; aa.dv_acc = dv_acc;
+    aa.B = B; aa.L = L; aa.M = M; aa.A = A; aa.C = C; aa.K = K; aa.last = 0;
+    B200_TRY(launch_attn_bwd(aa, st));
+    batchsum_add_kernel<<<grid_for((size_t)A * C), 256, 0, st>>>(d_Wloc, dWloc_acc, B, (size_t)A * C);
+    B200_LAUNCH_CHECK();
+    batchsum_add_kernel<<<grid_for((size_t)C * K), 256, 0, st>>>(d_Wc, dWc_acc, B, (size_t)C * K);
+    B200_LAUNCH_CHECK();
+    batchsum_add_kernel<<<1, 256, 0, st>>>(d_v, dv_acc, B, (size_t)A);
+    B200_LAUNCH_CHECK();
+    return B200TTS_OK;
+}
+
 int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                           const b200tts_decoder_outputs& fwd_out, const b200tts_decoder_output_grads& dout, const float* fws,
                           float* bws, size_t bws_bytes, const b200tts_decoder_params& dw, float* d_memory, cudaStream_t st) {

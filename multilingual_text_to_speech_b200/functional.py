@@ -109,6 +109,54 @@ def attention_step(query, memory, memory_transform, text_lengths, w_query, w_loc
     return ctx, weights
 
 
+class AttentionStepFunction(torch.autograd.Function):
+    """One LocationSensitiveAttention step WITH autograd (reference modules/attention.py:39-45, 67-86): returns
+    (context, weights, updated cumulative weights); the backward is the library's single-step attention backward."""
+
+    @staticmethod
+    def forward(ctx, query, memory, memT, cum_prev, text_lengths, w_query, w_location, w_loc_features, bias, w_energy):
+        _require_cuda(query, memory, memT, cum_prev)
+        query, memory, memT = _f32c(query), _f32c(memory), _f32c(memT)
+        ws_args = [_f32c(t) for t in (w_query, w_location, w_loc_features, bias, w_energy)]
+        lengths = text_lengths.to(torch.int32).contiguous()
+        B, L, M = memory.shape
+        D, A = query.shape[1], ws_args[0].shape[0]
+        C, _, K = ws_args[2].shape
+        lib = _lib.load()
+        ws = torch.empty(lib.b200tts_attention_step_workspace_elems(B, L, A), device=query.device, dtype=torch.float32)
+        context = torch.empty(B, M, device=query.device, dtype=torch.float32)
+        weights = torch.empty(B, L, device=query.device, dtype=torch.float32)
+        cum_next = _f32c(cum_prev).clone()
+        check(lib.b200tts_attention_step(B, L, M, D, A, C, K, ptr(query), ptr(memory), ptr(memT), ptr(lengths), *[ptr(t) for t in ws_args],
+                                         ptr(cum_next), ptr(context), ptr(weights), ptr(ws), _stream()), 'b200tts_attention_step')
+        q = ws[:B * A].view(B, A).clone()              # the forward left q = query . Wq^T at the head of its workspace
+        ctx.dims = (B, L, M, D, A, C, K)
+        ctx.save_for_backward(query, memory, memT, _f32c(cum_prev), lengths, q, weights, *ws_args)
+        return context, weights, cum_next
+
+    @staticmethod
+    def backward(ctx, d_context, d_weights, d_cum_next):
+        query, memory, memT, cum_prev, lengths, q, weights, w_query, w_location, w_loc_features, bias, w_energy = ctx.saved_tensors
+        B, L, M, D, A, C, K = ctx.dims
+        dev = query.device
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)   # noqa: E731
+        d_context = _f32c(d_context) if d_context is not None else z(B, M)
+        d_weights = _f32c(d_weights) if d_weights is not None else None
+        d_cum = _f32c(d_cum_next).clone() if d_cum_next is not None else z(B, L)
+        d_q, d_memT, d_wloc, d_wc, d_v = z(B, A), z(B, L, A), torch.zeros_like(w_location), torch.zeros_like(w_loc_features), torch.zeros_like(w_energy)
+        lib = _lib.load()
+        ws = torch.empty(lib.b200tts_attention_step_backward_workspace_elems(B, M, A, C, K), device=dev, dtype=torch.float32)
+        check(lib.b200tts_attention_step_backward(B, L, M, A, C, K, ptr(q), ptr(memory), ptr(memT), ptr(lengths), ptr(w_location),
+                                                  ptr(w_loc_features), ptr(bias), ptr(w_energy), ptr(cum_prev), ptr(weights), ptr(d_context),
+                                                  ptr(d_weights), ptr(d_cum), ptr(d_q), ptr(d_memT), ptr(d_wloc), ptr(d_wc), ptr(d_v), ptr(ws),
+                                                  _stream()), 'b200tts_attention_step_backward')
+        d_query = gemm(d_q, w_query, False, False)                       # [B, A] . [A, D]
+        d_wq = gemm(d_q, query, True, False)                             # [A, B] . [B, D]
+        d_bias = d_q.sum(0, keepdim=True).view_as(bias)
+        d_memory = weights.unsqueeze(2) * d_context.unsqueeze(1)         # context = weights . memory
+        return d_query, d_memory, d_memT, d_cum, None, d_wq, d_wloc, d_wc, d_bias, d_v
+
+
 # ------------------------------------------------------------------------------------------------
 # fused decoder
 # ------------------------------------------------------------------------------------------------

@@ -38,12 +38,12 @@ class LocationSensitiveAttention(AttentionBase):
         self._smoothing = smoothing
 
     def forward(self, query, memory, mask, prev_decoder_output):
-        """(context, weights) for one decoder step; module state (_prev_weights) is advanced in place.  Inference-style
-        API: no autograd through this entry point (training uses the fused decoder op)."""
+        """(context, weights) for one decoder step (attention.py:39-45); the module state (`_prev_weights`, `_prev_context`) advances as
+        in the reference and carries autograd history: gradients flow to the query, the memory, the memory projection and every
+        attention parameter through the library's single-step backward.  (Training inside `Decoder` uses the fused op instead.)"""
         lengths = mask.sum(dim=1).to(torch.int32)
-        with torch.no_grad():
-            ctx, w = F.attention_step(query, memory, self._memory_transform, lengths, self._query.weight,
-                                      self._location.weight, self._loc_features.weight, self._bias, self._energy.weight,
-                                      self._prev_weights)
+        ctx, w, cum = F.AttentionStepFunction.apply(query, memory, self._memory_transform, self._prev_weights, lengths, self._query.weight,
+                                                    self._location.weight, self._loc_features.weight, self._bias, self._energy.weight)
+        self._prev_weights = cum
         self._prev_context = ctx
         return ctx, w

@@ -121,3 +121,45 @@ def test_generated_conv_and_batchnorm_match_reference(train):
         assert_close(ob.running_mean, rb.running_mean, 1e-3, 1e-6, 'running_mean')
         assert_close(ob.running_var, rb.running_var, 1e-3, 1e-6, 'running_var')
         assert int(ob.num_batches_tracked) == int(rb.num_batches_tracked) == 1
+
+
+@needs_ref
+def test_attention_module_forward_and_autograd_match_reference():
+    """LocationSensitiveAttention.reset + three forward steps (attention.py:23-28, 39-45, 67-86) with gradients through the carried
+    cumulative weights, against the reference module."""
+    R.load()
+    from modules.attention import LocationSensitiveAttention as RA
+    from multilingual_text_to_speech_b200.modules.attention import LocationSensitiveAttention
+    torch.manual_seed(7)
+    B, L, M, D, A, C, K = 5, 37, 288, 1024, 128, 32, 31
+    ref = RA(K, C, False, A, D, M)
+    own = LocationSensitiveAttention(K, C, False, A, D, M)
+    with torch.no_grad():
+        for prm in ref.parameters():
+            prm.mul_(3.0)
+    _copy_params(own, ref)
+    own = own.cuda()
+    lens = torch.tensor([37, 30, 37, 12, 25])
+    mask = torch.arange(L)[None, :] < lens[:, None]
+    memory = torch.randn(B, L, M)
+    queries = [torch.randn(B, D) for _ in range(3)]
+    mr = memory.clone().requires_grad_(True); qr = [q.clone().requires_grad_(True) for q in queries]
+    mo = memory.cuda().requires_grad_(True); qo = [q.cuda().requires_grad_(True) for q in queries]
+    ref.reset(mr, B, L, memory.device)
+    own.reset(mo, B, L, mo.device)
+    gen = torch.Generator().manual_seed(1)
+    loss_r, loss_o = 0.0, 0.0
+    for step in range(3):
+        c1, w1 = ref(qr[step], mr, mask, None)
+        c2, w2 = own(qo[step], mo, mask.cuda(), None)
+        assert_close(w2, w1, 1e-3, 1e-6, f'weights step {step}')
+        assert_close(c2, c1, 1e-3, 1e-5, f'context step {step}')
+        gc, gw = torch.randn(B, M, generator=gen), torch.randn(B, L, generator=gen)
+        loss_r = loss_r + (c1 * gc).sum() + (w1 * gw).sum()
+        loss_o = loss_o + (c2 * gc.cuda()).sum() + (w2 * gw.cuda()).sum()
+    loss_r.backward(); loss_o.backward()
+    assert_close(mo.grad, mr.grad, 3e-3, 1e-4 * float(mr.grad.abs().max()), 'd memory')
+    for step in range(3):
+        assert_close(qo[step].grad, qr[step].grad, 3e-3, 1e-4 * float(qr[step].grad.abs().max()), f'd query {step}')
+    for (n, p), (_, q) in zip(own.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, 3e-3, 2e-4 * float(q.grad.abs().max()), 'd' + n)
