@@ -100,7 +100,7 @@ __device__ __forceinline__ void st_peer_f32(const float* local_smem, uint32_t pe
 }
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-#define BPROF_DECL long long prof_acc[BPROF_N] = {}; long long prof_t = clock64();
+#define BPROF_DECL long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
 #define BPROF_MARK(slot)                                                                                         \
     do {                                                                                                         \
         if (p.prof && threadIdx.x == 0) { const long long now = clock64(); prof_acc[slot] += now - prof_t; prof_t = now; } \
@@ -108,11 +108,10 @@ __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefe
 #define BPROF_FLUSH                                                                                              \
     do {                                                                                                         \
         if (p.prof && threadIdx.x == 0)                                                                          \
-            for (int k9 = 0; k9 < BPROF_N; ++k9) p.prof[(size_t)blockIdx.x * BPROF_N + k9] = prof_acc[k9];       \
+            for (int k9 = 0; k9 < 8; ++k9) p.prof[(size_t)blockIdx.x * 8 + k9] = prof_acc[k9];                   \
     } while (0)
 
 // Generator-LSTM reverse loop (no attention): NOUT = D.
-#define BPROF_N 8
 __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_kernel(const BwdLoopArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -281,8 +280,6 @@ struct AttBwdArgs {
     const uint4* memFb; int M16;                          // [B][MT][M16][32] A fragments (rows = positions, k = memory dims), bf16
     const int* lengths;
     int dqp_after_g;                                      // 1: dq partials live after the G tile buffer, 0: alias the scratch head
-    int memF_resident;                                    // 1: this CTA's half of the memory fragments (memFb) stays in shared memory for all T steps
-    int memT_off;                                         // > 0: byte offset inside the activation stage where each step's memTf half is prefetched (cp.async)
     float* dctx_tot;                                      // [T, B, M] out
     float* dq;                                            // [T, B, A] out
     float* de;                                            // [T, B, L] out (softmax-backward energies, consumed by the post pass)
@@ -316,8 +313,6 @@ __device__ __forceinline__ void build_pairs(uint32_t* Ph, uint32_t* Pl, const fl
     }
 }
 
-#undef BPROF_N
-#define BPROF_N 16
 template <bool TC>
 __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_constant__ CUtensorMap tmG, const AttBwdArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
@@ -341,7 +336,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
     __nv_bfloat16* sWcB2 = sWcB + (size_t)A * 40;                                    // [32][A+8]
     float* dcum = reinterpret_cast<float*>(sWcB2 + (size_t)32 * (A + 8));            // [L16 + 32] persistent d cum
     float* wq8 = dcum + (p.MT * 16 + 32);                                            // [A][8 + 1] query weights of this CTA's 8 units
-    uint4* sMemF = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(wq8 + (size_t)A * 9) + 15) & ~(uintptr_t)15);   // resident memFb half
     const unsigned nblocks = gridDim.x;
     const int L16 = p.MT * 16;
 
@@ -403,17 +397,9 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
     float* s_dqx = s_dqp + 8 * A;                         // [A]  the peer's partial (written through distributed shared memory)
     float* s_dotx = s_dqx + A;                            // [4]  the peer's partial softmax dot
     float* s_stage = s_dotx + 4;                          // [L16] d cum staging
-    uint32_t* s_bfrag = reinterpret_cast<uint32_t*>(s_stage + L16);   // [M16][8][2] B fragments (hi / lo bf16 of d ctx) of the dw product
     BPROF_DECL
 
     const int pc = cta >> 1;
-    if (p.memF_resident && pc < B) {      // one-time: fragment-major memory of the own position tiles (the dw product reads it every step)
-        const uint4* src = p.memFb + (((size_t)pc * p.MT + t_lo) * p.M16) * 32;
-        const int n16 = (t_hi - t_lo) * p.M16 * 32;
-        for (int idx = tid; idx < n16; idx += PT) sMemF[idx] = __ldg(src + idx);
-        __syncthreads();
-    }
-    uint4* const sMemT = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(As) + p.memT_off);     // per-step memTf half (when memT_off > 0)
     // cell-backward operands of this thread's (b, u) pairs (owner CTAs): fetched a whole reverse step ahead, at the end of the previous
     // cell phase, so that their DRAM latency never sits on the critical path
     float gi_[MAXE], gf_[MAXE], gg_[MAXE], go_[MAXE], cp_[MAXE], dhs_[MAXE];
@@ -439,30 +425,8 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
     if (pc < B) { const int l0 = p.lengths[pc]; pa_len = l0 < 0 ? 0 : (l0 > L ? L : l0); }
     for (int i = p.T - 1; i >= 0; --i) {
         const bool last = (i == p.T - 1);
-        // recurrent partial sums of this thread's (b, u) pairs (owner CTAs; written by the product of the previous reverse step): the loads
-        // are ISSUED here, together with the operand loads of the attention phase below, and only summed after those were issued too --
-        // one global round trip for everything the step starts with, a whole attention phase before the cell backward needs the sums
-        float rec_[MAXE];
-        float r8[MAXE][KBA];
-#pragma unroll
-        for (int e = 0; e < MAXE; ++e) {
-            const int idx = tid + e * PT;
-            const bool on = owner && idx < B * UOWN && !last;
-            const int b = on ? idx / UOWN : 0, u = uo0 + idx % UOWN;
-#pragma unroll
-            for (int k2 = 0; k2 < KBA; ++k2) r8[e][k2] = on ? __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u) : 0.f;
-        }
         // =========================== PA: attention backward of utterance `pc` on the CTA pair (2 pc, 2 pc + 1) ===========================
         if (pc < B) {
-            if (p.memT_off > 0) {      // this step's memory-projection fragments of the own tiles: asynchronous copy, consumed by the energy backward
-                const int nchunk = (t_hi - t_lo) * 256;               // 16-byte chunks: [tile][lane][8]
-                const __nv_bfloat16* src = p.memTf + ((size_t)pc * p.MT + t_lo) * 32 * 64;
-                for (int qd = tid; qd < nchunk; qd += PT) {
-                    const int ln = (qd >> 3) & 31, c4 = qd & 7;
-                    cp_async16(sMemT + (qd & ~7) + (c4 ^ (ln & 7)), src + (size_t)qd * 8);     // chunk index swizzled against bank conflicts
-                }
-                asm volatile("cp.async.commit_group;\n" ::);
-            }
             const int b = pc, half = (p.KC - 1) / 2;
             if (i > 0) {       // DRAM -> L2 one step ahead: the rows of step i-1 this phase starts with (alignment, query, cumulative weights, d ctx)
                 const size_t r1 = (size_t)(i - 1) * B + b;
@@ -476,58 +440,17 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             }
             const int len = pa_len;                        // loaded once, before the loop
             const int mtiles = (len + 15) / 16;
-            {
-                // d ctx of the step = static part + the KBA partial slabs of the product: both rounds (M > 256) issued before any is consumed
-                constexpr int MR = 2;                      // rounds of PT memory dims (M <= 512)
-                float gs[MR], gp[MR][KBA];
-#pragma unroll
-                for (int r = 0; r < MR; ++r) {
-                    const int m = tid + r * PT;
-                    const bool on = m < M;
-                    gs[r] = on ? p.dctx_static[((size_t)i * B + b) * M + m] : 0.f;
-#pragma unroll
-                    for (int k2 = 0; k2 < KBA; ++k2) gp[r][k2] = (on && !last) ? __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + m) : 0.f;
-                }
-                const float wl = (tid < L) ? p.align[(size_t)b * p.align_bstride + (size_t)i * L + tid] : 0.f;          // L16 <= 256 checked below
-                const float qv = (tid < A) ? p.q[((size_t)i * B + b) * A + tid] : 0.f;
-#pragma unroll
-                for (int r = 0; r < MR; ++r) {
-                    const int m = tid + r * PT;
-                    if (m < M) {
-                        float g = gs[r];
-#pragma unroll
-                        for (int k2 = 0; k2 < KBA; ++k2) g += gp[r][k2];
-                        s_dctx[m] = g;
-                        if (hf == 0) p.dctx_tot[((size_t)i * B + b) * M + m] = g;
-                    }
-                }
-                if (L16 <= PT) { if (tid < L16) s_w[tid] = wl; }
-                else for (int l = tid; l < L16; l += PT) s_w[l] = l < L ? p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] : 0.f;
-                if (tid < A) { s_qb[tid] = qv + p.bias[tid]; s_vv[tid] = p.v[tid]; }
+            for (int m = tid; m < M; m += PT) {
+                float g = p.dctx_static[((size_t)i * B + b) * M + m];
+                if (!last)
+                    for (int k2 = 0; k2 < KBA; ++k2) g += __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + m);
+                s_dctx[m] = g;
+                if (hf == 0) p.dctx_tot[((size_t)i * B + b) * M + m] = g;
             }
+            for (int l = tid; l < L16; l += PT) s_w[l] = l < L ? p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] : 0.f;
+            for (int a = tid; a < A; a += PT) { s_qb[a] = p.q[((size_t)i * B + b) * A + a] + p.bias[a]; s_vv[a] = p.v[a]; }
             build_pairs(s_Ph, s_Pl, p.cum + ((size_t)i * B + b) * L, L, half, L16 + 48, tid, PT);
-#pragma unroll
-            for (int e = 0; e < MAXE; ++e) {               // the recurrent sums requested at the top of the step (their loads are long in flight)
-                float rs = 0.f;
-#pragma unroll
-                for (int k2 = 0; k2 < KBA; ++k2) rs += r8[e][k2];
-                rec_[e] = rs;
-            }
             __syncthreads();
-            // B fragments of the dw product (identical for every position tile and warp): built ONCE per step.  Entry (k-tile, g, tq):
-            // column g = 0 carries hi(d ctx), g = 1 carries lo(d ctx); lanes with g >= 2 feed zeros
-            if (tid < p.M16 * 8) {
-                const int kt = tid >> 3, gg2 = (tid >> 2) & 1, tq2 = tid & 3;
-                const int m0 = kt * 16 + 2 * tq2;
-                const float w0 = m0 < M ? s_dctx[m0] : 0.f, w1 = m0 + 1 < M ? s_dctx[m0 + 1] : 0.f;
-                const float w2 = m0 + 8 < M ? s_dctx[m0 + 8] : 0.f, w3 = m0 + 9 < M ? s_dctx[m0 + 9] : 0.f;
-                const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
-                const float h2 = __bfloat162float(__float2bfloat16_rn(w2)), h3 = __bfloat162float(__float2bfloat16_rn(w3));
-                s_bfrag[tid * 2] = gg2 == 0 ? pack2(h0, h1) : pack2(w0 - h0, w1 - h1);
-                s_bfrag[tid * 2 + 1] = gg2 == 0 ? pack2(h2, h3) : pack2(w2 - h2, w3 - h3);
-            }
-            __syncthreads();
-            BPROF_MARK(8);                                  // PA.a: operands of the step staged
             // dw[l] = dalign + dcum + <dctx, memory[l]> on the tensor cores: A = fragment-major memory (one 16-byte load per lane per
             // MMA), B = (hi(dctx), lo(dctx)) in columns 0 / 1; warp owns position tiles {warp, warp + 8}
             {
@@ -537,21 +460,23 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                     float dacc[4] = {0.f, 0.f, 0.f, 0.f}, dacc2[4] = {0.f, 0.f, 0.f, 0.f};
                     if (lt * 16 < len) {
                         const uint4* fr = p.memFb + (((size_t)b * p.MT + lt) * p.M16) * 32 + lane;
-                        const uint4* frs = sMemF + ((size_t)(lt - t_lo) * p.M16) * 32 + lane;
                         for (int kt0 = 0; kt0 < p.M16; kt0 += KT) {
                             uint4 av[KT];
 #pragma unroll
                             for (int j = 0; j < KT; ++j)
-                                if (kt0 + j < p.M16) av[j] = p.memF_resident ? frs[(size_t)(kt0 + j) * 32] : __ldg(fr + (size_t)(kt0 + j) * 32);
-                            // B fragments from the per-step table: lanes g = 0 hold hi(dctx), g = 1 hold lo(dctx), the other columns zero
+                                if (kt0 + j < p.M16) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
+                            // B fragments: lanes g = 0 hold hi(dctx), g = 1 hold lo(dctx), other columns zero (branch-free)
                             uint32_t bfr[KT][2];
 #pragma unroll
                             for (int j = 0; j < KT; ++j) {
-                                bfr[j][0] = 0u; bfr[j][1] = 0u;
-                                if (g < 2 && kt0 + j < p.M16) {
-                                    const uint2 v2 = *reinterpret_cast<const uint2*>(s_bfrag + (((kt0 + j) * 8 + g * 4 + tq) << 1));
-                                    bfr[j][0] = v2.x; bfr[j][1] = v2.y;
-                                }
+                                const int m0 = (kt0 + j) * 16 + 2 * tq;
+                                const float w0 = m0 < M ? s_dctx[m0] : 0.f, w1 = m0 + 1 < M ? s_dctx[m0 + 1] : 0.f;
+                                const float w2 = m0 + 8 < M ? s_dctx[m0 + 8] : 0.f, w3 = m0 + 9 < M ? s_dctx[m0 + 9] : 0.f;
+                                const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
+                                const float h2 = __bfloat162float(__float2bfloat16_rn(w2)), h3 = __bfloat162float(__float2bfloat16_rn(w3));
+                                const float s0 = g == 0 ? h0 : (g == 1 ? w0 - h0 : 0.f), s1 = g == 0 ? h1 : (g == 1 ? w1 - h1 : 0.f);
+                                const float s2 = g == 0 ? h2 : (g == 1 ? w2 - h2 : 0.f), s3 = g == 0 ? h3 : (g == 1 ? w3 - h3 : 0.f);
+                                bfr[j][0] = pack2(s0, s1); bfr[j][1] = pack2(s2, s3);
                             }
 #pragma unroll
                             for (int j = 0; j < KT; j += 2) {        // two independent accumulation chains
@@ -583,7 +508,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 }
             }
             __syncthreads();
-            BPROF_MARK(9);                                  // PA.b: dw = <dctx, memory> MMAs
             // softmax backward: dot = sum_l w[l] dw[l] over ALL positions = own partial + the peer's (exchanged through DSMEM)
             float pdot = 0.f;
             for (int l = t_lo * 16 + tid; l < t_hi * 16 && l < len; l += PT) pdot = fmaf(s_w[l], s_de[l], pdot);
@@ -597,7 +521,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 s_de[l] = d;
                 if (l < L) p.de[((size_t)i * B + b) * L + l] = d;
             }
-            if (p.memT_off > 0) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncthreads();
             BPROF_MARK(0);
             // energies backward on the tensor cores; warp owns position tiles {warp, warp + 8}
@@ -630,12 +553,11 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 }
                 // ds = de[l] * v[a] * (1 - tanh^2(S + q + bias + memT)); fragment-major memory projection: 64 bf16 per lane
                 const uint4* mf = reinterpret_cast<const uint4*>(p.memTf + (((size_t)b * p.MT + mt) * 32 + lane) * 64);
-                const uint4* mfs = sMemT + ((size_t)(mt - t_lo) * 32 + lane) * 8;
                 const float de0 = s_de[l0 + g], de1 = s_de[l0 + g + 8];
                 uint32_t dsA[16][2];
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const uint4 raw = p.memT_off > 0 ? mfs[c4 ^ (lane & 7)] : mf[c4];      // n-tiles 2*c4, 2*c4+1; 4 values each
+                    const uint4 raw = mf[c4];                      // n-tiles 2*c4, 2*c4+1; 4 values each
                     const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
@@ -675,7 +597,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             }
             // dq[a] = sum_l ds[l, a]: reduce over the 8 row lanes, then over warps
             __syncthreads();                               // every warp is done with s_de / s_qb / s_vv / Ph / Pl
-            BPROF_MARK(10);                                 // PA.d: energies backward MMAs (after slot 0 = softmax backward + pair barrier)
 #pragma unroll
             for (int nt = 0; nt < 16; ++nt)
 #pragma unroll
@@ -704,7 +625,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             }
             cluster_arrive();
             cluster_wait();
-            BPROF_MARK(11);                                 // PA.e: dq reduction, G halo exchange, pair barrier
             if (hf == 0 && tid < A) p.dq[((size_t)i * B + b) * A + tid] = pdq + s_dqx[tid];
             // d cum_{i-1}[j] = d cum_i[j] + sum_k G[j + half - k, k] for the own positions (their G rows: own tiles + the halo tile)
             for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) {
@@ -718,13 +638,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             __syncthreads();
             for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) dcum[j] = s_stage[j];
         } else {
-#pragma unroll
-            for (int e = 0; e < MAXE; ++e) {
-                float rs = 0.f;
-#pragma unroll
-                for (int k2 = 0; k2 < KBA; ++k2) rs += r8[e][k2];
-                rec_[e] = rs;
-            }
             cluster_arrive(); cluster_wait();               // idle pairs: every thread of the cluster takes part in the two pair barriers
             cluster_arrive(); cluster_wait();
         }
@@ -734,6 +647,23 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
 
         // =========================== PB: attention-LSTM cell backward ===========================
         if (owner) {
+            // recurrent partial sums of this thread's (b, u) pairs (written by the product of the previous reverse step)
+            float rec_[MAXE];
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) {
+                const int idx = tid + e * PT;
+                rec_[e] = 0.f;
+                if (idx < B * UOWN && !last) {
+                    const int b = idx / UOWN, u = uo0 + idx % UOWN;
+                    float r8[KBA];
+#pragma unroll
+                    for (int k2 = 0; k2 < KBA; ++k2) r8[k2] = __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
+                    float rs = 0.f;
+#pragma unroll
+                    for (int k2 = 0; k2 < KBA; ++k2) rs += r8[k2];
+                    rec_[e] = rs;
+                }
+            }
             // d h (query part) = dq[b, :] . Wq[:, u] on the tensor cores: A = dq rows staged in shared memory (bf16 hi + lo),
             // B = this CTA's 8 columns of Wq (bf16 hi + lo, register resident); hi.hi + lo.hi + hi.lo = fp32-equivalent
             // (As is idle between PA and P2: [B][A] query gradients, row b rotated by 8 (b & 7) floats against bank conflicts, then [64][8] products)
@@ -741,25 +671,12 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             float* s_dhq = s_dq + (size_t)B * A;
             {
                 const int nf4 = A / 4;
-                constexpr int DQR = 4;                     // float4 loads per thread and batch: all in flight before the first store
-                for (int base = 0; base < B * nf4; base += DQR * PT) {
-                    float4 vq[DQR];
-#pragma unroll
-                    for (int j = 0; j < DQR; ++j) {
-                        const int idx = base + tid + j * PT;
-                        if (idx < B * nf4) vq[j] = __ldcg(reinterpret_cast<const float4*>(p.dq + (size_t)i * B * A) + idx);
-                    }
-#pragma unroll
-                    for (int j = 0; j < DQR; ++j) {
-                        const int idx = base + tid + j * PT;
-                        if (idx < B * nf4) {
-                            const int b = idx / nf4, c4 = idx % nf4;
-                            *reinterpret_cast<float4*>(s_dq + b * A + ((c4 * 4 + 8 * (b & 7)) & (A - 1))) = vq[j];
-                        }
-                    }
+                for (int idx = tid; idx < B * nf4; idx += PT) {
+                    const int b = idx / nf4, c4 = idx % nf4;
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(p.dq + ((size_t)i * B + b) * A) + c4);
+                    *reinterpret_cast<float4*>(s_dq + b * A + ((c4 * 4 + 8 * (b & 7)) & (A - 1))) = v;
                 }
                 __syncthreads();
-                BPROF_MARK(13);                             // PB.a: recurrent partials + query gradients loaded
                 const int g = lane >> 2, tq = lane & 3, mt = warp & 3, kh = warp >> 2;      // warp = (16-utterance tile, half of the A range)
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 const int ksteps = A / 32;                                // k-steps of 16 per half
@@ -797,7 +714,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 __syncthreads();
                 if (kh == 1) { d0[0] += acc[0]; d0[1] += acc[1]; d1[0] += acc[2]; d1[1] += acc[3]; }
                 __syncthreads();
-                BPROF_MARK(14);                             // PB.b: dq . Wq on the tensor cores
             }
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
@@ -1182,7 +1098,7 @@ AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s) {
     x.de = take((size_t)s.T * s.B * s.L * 4);
     x.dwpart = take((size_t)s.B * x.MT * s.A * 32 * 4);
     x.dvpart = take((size_t)s.B * x.MT * s.A * 4);
-    x.barrier = take(256 + 148 * 16 * 8);
+    x.barrier = take(256 + 148 * 8 * 8);
     x.total = off;
     return x;
 }
@@ -1222,7 +1138,7 @@ static bool att_bwd_variant_ok(const b200tts_decoder_shape& s, const AttBwdGeom&
     const int MT = (s.L + 15) / 16, L16 = MT * 16, HT0 = (MT + 1) / 2;
     // attention-backward scratch of one CTA of the pair (aliases the activation stage)
     const size_t fl = (size_t)((s.M + 3) & ~3) + 3 * (size_t)L16 + 2 * s.A + 2 * (size_t)(L16 + 48) + 64 + (size_t)(HT0 + 1) * 16 * GLD +
-                      8 * (size_t)s.A + s.A + 4 + (size_t)L16 + 16 * (size_t)((s.M + 15) / 16);
+                      8 * (size_t)s.A + s.A + 4;
     if (fl * 4 > g.region) return false;
     // the cell-backward phase stages the query gradients [B][A] fp32 + [64][8] products in the (then idle) activation stage
     if ((size_t)s.B * s.A * 4 + 64 * 8 * 4 > g.region) return false;
@@ -1270,19 +1186,6 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     a.memb = reinterpret_cast<const __nv_bfloat16*>(pws + pl.memb); a.ldm = pl.ldm;
     a.memFb = reinterpret_cast<const uint4*>(pws + pl.memFb); a.M16 = pl.M16;
     a.dqp_after_g = 1;
-    {
-        // the own half of the memory fragments stays resident when the shared memory allows (L = 180: 55 KB); the memTf half of every step
-        // is prefetched into the free tail of the activation stage when it fits behind the attention scratch
-        const int MT = x.MT, L16 = MT * 16, HT0 = (MT + 1) / 2;
-        const size_t scratch = ((size_t)((M + 3) & ~3) + 3 * (size_t)L16 + 2 * A + 2 * (size_t)(L16 + 48) + 64 + (size_t)(HT0 + 1) * 16 * GLD +
-                                8 * (size_t)A + A + 4 + (size_t)L16 + 16 * (size_t)pl.M16) * 4;
-        const size_t memf = (size_t)HT0 * pl.M16 * 512, memt = (size_t)HT0 * 4096;
-        a.memF_resident = (geo.tc && geo.smem + 16 + memf + 1024 <= 227 * 1024) ? 1 : 0;
-        if (a.memF_resident) geo.smem += 16 + memf;
-        const size_t off = (scratch + 127) / 128 * 128;
-        a.memT_off = (geo.tc && off + memt <= geo.region) ? (int)off : 0;
-        if (getenv("B200TTS_ATT_BWD_NO_RESIDENT")) { if (a.memF_resident) geo.smem -= 16 + memf; a.memF_resident = 0; a.memT_off = 0; }
-    }
     a.lengths = in.text_lengths; a.dctx_tot = dctx_tot; a.dq = dq; a.de = reinterpret_cast<float*>(extra + x.de);
     a.barrier = reinterpret_cast<unsigned*>(extra + x.barrier); a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);
     a.prof = reinterpret_cast<long long*>(extra + x.barrier + 256);

@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_tc_kernel(const __grid_co
     const int b0 = bh * BT, n0 = nb * ROWS;
     const int u0 = (gsel * NNB + nb) * UNITS;                 // hidden units whose cell backward this CTA owns
     // batch halves are independent (cell backward and product of a CTA serve the same 32 utterances): one barrier counter per half
-    const unsigned nblocks = (unsigned)(NG * p.NNB);
-    unsigned* const bar_counter = p.barrier + 16 * bh;
+    // (per-batch-half barrier counters were measured SLOWER than one grid-wide counter: +0.9 ms on the attention loop; the cost of a
+    // barrier is its latency chain -- store acks, atomic round trip, poll -- not the number of arrivals: tools/microbench/barrier_latency.cu)
+    const unsigned nblocks = gridDim.x;
+    unsigned* const bar_counter = p.barrier;
     const bool compute = warp < NCW, is_producer = warp == NCW, is_mma = warp == NCW + 1;
 
     unsigned char* sW = smem_raw;                              // [NNB][64 rows (n)][128 B] swizzled: W^T[n0 + r, gate gsel, k]

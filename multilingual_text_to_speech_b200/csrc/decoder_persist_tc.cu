@@ -243,8 +243,10 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     const int Kp = p.Kp, D = p.D, B = p.B;
     // the two batch halves never exchange data (a CTA's LSTM rows and the attention pairs it hosts serve the same 32 utterances):
     // each half synchronises on its own barrier counter, 64 arrivals instead of 128
-    const unsigned nblocks = (unsigned)p.RB;
-    unsigned* const bar_counter = p.barrier + 16 * (cta / p.RB);
+    // (per-batch-half barrier counters were measured SLOWER than one grid-wide counter: +0.9 ms on the attention loop; the cost of a
+    // barrier is its latency chain -- store acks, atomic round trip, poll -- not the number of arrivals: tools/microbench/barrier_latency.cu)
+    const unsigned nblocks = gridDim.x;
+    unsigned* const bar_counter = p.barrier;
     const bool compute = warp < NCW;
     const bool is_producer = (warp == NCW);        // whole warps run the role loops; one elected lane issues the TMA / MMA instructions
     const bool is_mma = (warp == NCW + 1);

@@ -56,11 +56,10 @@ def main():
             if not a.fwd_only:
                 shp = F.PROFILE['last_shape']
                 bnames = [['cell', 'barrier1', 'tma+tcgen05', 'tmem+store', 'barrier2', '-', '-', '-'],
-                          ['PA.c softmax-bwd+pair', 'PA.f dcum update', 'barrier1', 'PB.c cell math+stores', 'barrier2', 'P2 tma+mma+tmem', 'barrier3', '-',
-                           'PA.a stage operands', 'PA.b dw MMAs', 'PA.d energy-bwd MMAs', 'PA.e dq/G exchange', '-', 'PB.a loads', 'PB.b dq.Wq MMAs', '-']]
+                          ['attn:dw/softmax', 'attn:mma+dcum', 'barrier1', 'cell', 'barrier2', 'product', 'barrier3', '-']]
                 for which, loop in enumerate(('gen-bwd', 'att-bwd')):
                     boff = _lib.load().b200tts_debug_persist_bwd_profile_offset(ctypes.byref(shp), which)
-                    ns = 16 if which == 1 else 8
+                    ns = 8
                     rb = F.PROFILE['last_bws'][boff:boff + 148 * ns * 8].view(torch.int64).view(148, ns).cpu().double()
                     act = rb[rb.sum(1) > 0]
                     if len(act):
