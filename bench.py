@@ -41,6 +41,7 @@ def parse():
                     help='frames per utterance of the CPU reference sample (reference arm / cpu_baseline): the first N of --frames')
     ap.add_argument('--no-extra-baselines', action='store_true',
                     help='skip the cfg-1 CPU timing and the eager-PyTorch-on-B200 timing of the unmodified reference (N=1 only)')
+    ap.add_argument('--no-graph', action='store_true', help='issue every step from Python instead of replaying the captured CUDA graph')
     ap.add_argument('--breakdown', default='', help='write a per-kernel device-time table of one extra (untimed) step to this file')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help="bf16: tensor-core operands, fp32 master/state (BASELINE configs[1]); fp32: exact parity mode")
@@ -345,13 +346,34 @@ def run_b200(a):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     F.PROFILE.clear()
 
-    def step(batch):
+    def eager_step(batch):
         bucket.zero()
         post, pre, stop, align, spk, enc = model(batch['text'], batch['text_length'], batch['target'], batch['target_length'],
                                                  batch.get('speakers'), batch.get('languages'), hp.teacher_forcing)
         loss, _ = crit(batch['text_length'], batch['target_length'], pre, batch['target'], post, batch['target'], stop,
                        batch['stop_target'], align, batch.get('speakers'), spk, enc, None)
         loss.backward()
+        bucket.allreduce()
+        return loss
+
+    # the public way to run a step of fixed shape: forward + loss + backward captured ONCE into a CUDA graph and replayed
+    # (multilingual_text_to_speech_b200.graph.GraphedTrainStep); the gradient all-reduce follows the replay
+    graphed, launches_per_step, launch_mode = None, None, 'eager (one Python-issued launch sequence per step)'
+    if not a.no_graph:
+        try:
+            from multilingual_text_to_speech_b200.graph import GraphedTrainStep
+            n_before = _lib.launch_count()
+            graphed = GraphedTrainStep(model, crit, bucket, resident, teacher_forcing=hp.teacher_forcing, warmup=max(a.warmup, 3))
+            launches_per_step = (_lib.launch_count() - n_before) // (max(a.warmup, 3) + 1)
+            launch_mode = 'CUDA graph replay of the captured step (GraphedTrainStep), gradient all-reduce after the replay'
+        except Exception as exc:      # noqa: BLE001 -- capture is an optimisation; the eager path is the same kernels
+            graphed, launch_mode = None, f'eager (graph capture failed: {exc!r})'[:300]
+            torch.cuda.synchronize()
+
+    def step(batch):
+        if graphed is None:
+            return eager_step(batch)
+        loss = graphed(batch)
         bucket.allreduce()
         return loss
 
@@ -364,7 +386,10 @@ def run_b200(a):
         e0.record()
         loss_val = None
         for _ in range(n):
-            batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if from_host else resident
+            if from_host and graphed is not None:
+                batch = host                       # GraphedTrainStep copies the pinned host tensors into its static device buffers
+            else:
+                batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if from_host else resident
             loss = step(batch)
             if from_host:
                 loss_val = float(loss.detach())   # device -> host read of the step's result
@@ -384,19 +409,27 @@ def run_b200(a):
     for _ in range(max(a.warmup, 3)):
         step(resident)
     F.PROFILE.clear()
-    F.PROFILE['enabled'] = True
-    _lib.kernel_timing(True)              # CUDA events on the launching stream around the dominant kernels, inside the timed steps
     n0 = _lib.launch_count()
     ncu_range = bool(os.environ.get('B200TTS_NCU_RANGE'))   # `ncu --profile-from-start off`: capture exactly the timed steps
+    if graphed is None:
+        F.PROFILE['enabled'] = True
+        _lib.kernel_timing(True)          # CUDA events on the launching stream around the dominant kernels, inside the timed steps
     if ncu_range:
         torch.cuda.profiler.start()
     ms, _ = timed(a.steps, from_host=False)
     if ncu_range:
         torch.cuda.profiler.stop()
-    launches = _lib.launch_count() - n0
+    launches = (_lib.launch_count() - n0) if graphed is None else launches_per_step * a.steps
+    if graphed is not None:
+        # events cannot be timed inside a replayed graph: the per-kernel durations come from the SAME kernels issued eagerly, a.steps
+        # steps on the same inputs right after the timed replays (the kernels are launch-order independent; only the gaps differ)
+        F.PROFILE['enabled'] = True
+        _lib.kernel_timing(True)
+        for _ in range(a.steps):
+            eager_step(resident)
     F.PROFILE['enabled'] = False
     torch.cuda.synchronize()
-    ktimes = _lib.kernel_timing_read()    # {kernel: (total ms, launches)} over the a.steps timed steps
+    ktimes = _lib.kernel_timing_read()    # {kernel: (total ms, launches)} over a.steps steps
     _lib.kernel_timing(False)
     dec_ms = [s.elapsed_time(e) for s, e in F.PROFILE.get('decoder_fwd', [])]
     decb_ms = [s.elapsed_time(e) for s, e in F.PROFILE.get('decoder_bwd', [])]
@@ -405,7 +438,7 @@ def run_b200(a):
     if a.breakdown and rank == 0:       # CUPTI kernel times of ONE extra step (not part of any reported number)
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step(resident)
+            eager_step(resident)
             torch.cuda.synchronize()
         import collections
         import tempfile
@@ -456,7 +489,7 @@ def run_b200(a):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': config_dict(a, world, B, L, T),
+                'config': dict(config_dict(a, world, B, L, T), launch=launch_mode),
                 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
                         'loss': loss_val},

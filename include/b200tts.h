@@ -298,6 +298,9 @@ int b200tts_tacotron_loss_backward(const b200tts_loss_shape* shape, const float*
 
 /* ---- dropout-mask generation (counter-based RNG; replaces the Philox draws inside F.dropout) ---- */
 int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream);
+/* Optional DEVICE-side epoch mixed into every mask key (NULL = off): a training step captured in a CUDA graph bakes the host seeds into
+ * its kernel nodes, so the graph increments *epoch (a device uint64 the caller owns) once per replay and every replay draws new masks. */
+int b200tts_set_mask_epoch(const uint64_t* device_epoch);
 
 /* ---- optimizer step on flat buffers: clip_grad_norm_ + torch.optim.Adam with coupled L2 decay (train.py:84-85, 260-271) ----
  * p, g, m, v: n fp32 elements each (the flat parameter buffer, the flat all-reduced gradient, Adam moments); g is overwritten with

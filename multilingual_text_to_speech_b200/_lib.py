@@ -123,6 +123,7 @@ SIGNATURES = {
     'b200tts_loss_workspace_bytes': (c_size_t, []),
     'b200tts_tacotron_loss_forward': (c_int, [POINTER(LossShape)] + [c_void_p] * 12),
     'b200tts_tacotron_loss_backward': (c_int, [POINTER(LossShape)] + [c_void_p] * 14),
+    'b200tts_set_mask_epoch': (c_int, [c_void_p]),
     'b200tts_fill_keep_mask': (c_int, [c_void_p, c_size_t, c_float, c_uint64, c_uint64, c_void_p]),
 }
 

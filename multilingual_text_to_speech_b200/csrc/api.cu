@@ -123,7 +123,9 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
-__global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsigned threshold, unsigned long long key) {
+__global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsigned threshold, unsigned long long key,
+                                      const unsigned long long* __restrict__ epoch) {
+    if (epoch) key ^= mix64(*epoch * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull);
     const size_t groups = (n + 3) / 4;
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
         const unsigned long long r = mix64(key + g * 0x9E3779B97F4A7C15ull);
@@ -392,6 +394,11 @@ int b200tts_bilstm_backward(const b200tts_bilstm_shape* shape, const b200tts_bil
     return bilstm_backward_impl(*shape, *params, lengths, (const float*)saved, dout, dx, *d_params, (float*)workspace, (cudaStream_t)stream);
 }
 
+static const unsigned long long* g_mask_epoch = nullptr;
+int b200tts_set_mask_epoch(const uint64_t* device_epoch) {
+    g_mask_epoch = reinterpret_cast<const unsigned long long*>(device_epoch);
+    return B200TTS_OK;
+}
 int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t seed, uint64_t stream_id, void* stream) {
     B200_TRY(require_device());
     B200_REQUIRE(mask || n == 0, "fill_keep_mask: null mask");
@@ -401,7 +408,7 @@ int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t se
     const unsigned long long key = mix64(seed ^ 0xD6E8FEB86659FD93ull) ^ (stream_id * 0xA24BAED4963EE407ull);
     size_t groups = (n + 3) / 4;
     int blocks = (int)((groups + 255) / 256 > 148 * 16 ? 148 * 16 : (groups + 255) / 256);
-    fill_keep_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, key);
+    fill_keep_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, key, g_mask_epoch);
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
 }

@@ -35,8 +35,9 @@ class ReversalClassifier(torch.nn.Module):
     @staticmethod
     def loss(input_lengths, speakers, prediction, embeddings=None):
         """Masked cross entropy over valid input positions (classifier.py:60-69)."""
-        ml = int(torch.max(input_lengths))
-        mask = torch.arange(ml, device=input_lengths.device)[None, :] < input_lengths[:, None]
-        target = speakers[:, None].expand(-1, ml).clone()
-        target[~mask] = -100
-        return torch.nn.functional.cross_entropy(prediction[:, :ml].transpose(1, 2), target, ignore_index=-100)
+        # the reference sizes the mask by max(input_lengths), which must equal the padded length of `prediction` for its cross entropy
+        # to be shape-valid; using that padded length directly avoids a device -> host read (the step stays CUDA-graph capturable)
+        ml = prediction.shape[1]
+        mask = torch.arange(ml, device=prediction.device)[None, :] < input_lengths.to(prediction.device)[:, None]
+        target = torch.where(mask, speakers[:, None].expand(-1, ml), torch.full_like(mask, -100, dtype=speakers.dtype))
+        return torch.nn.functional.cross_entropy(prediction.transpose(1, 2), target, ignore_index=-100)

@@ -117,3 +117,59 @@ def test_pinned_prefetcher_delivers_batches_in_order():
     assert [k for k, _ in seen] == list(range(6))
     for (k, got), ref in zip(seen, batches):
         assert torch.equal(got, ref[2])
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (one CUDA graph per step) computes what the eager step computes: same loss and gradients on a mask tape, and
+    fresh dropout masks on every replay without one (device-side mask epoch)."""
+    import model_cases
+    from helpers import Golden
+    from multilingual_text_to_speech_b200.distributed import GradBucket
+    from multilingual_text_to_speech_b200.graph import GraphedTrainStep
+    from multilingual_text_to_speech_b200.modules.tacotron2 import TacotronLoss
+    from multilingual_text_to_speech_b200.rng import MaskSource
+    from multilingual_text_to_speech_b200.params.params import Params as hp
+    g = Golden('generated_training')
+    dev = torch.device('cuda:0')
+    model = model_cases.build_model(g, dev)
+    bucket = GradBucket(model, 1)
+    crit = TacotronLoss(hp.guided_attention_steps, g.meta['guided_g'], hp.guided_attention_gain)
+    batch = {k: v.to(dev) for k, v in g.inputs.items()}
+    batch.setdefault('speakers', None); batch.setdefault('languages', None)
+    # masks resident on the device (a host -> device copy from pageable memory cannot be captured); the teacher coins stay on the host
+    MaskSource.use_tape({k: (v if k == 'teacher' else v.to(dev)) for k, v in g.tape.items()})
+    step = None
+    try:
+        # (no autograd graph built on another stream may be alive at capture time: its AccumulateGrad nodes would run on that stream)
+        step = GraphedTrainStep(model, crit, bucket, batch, teacher_forcing=1.0, warmup=2)
+        got = []
+        for _ in range(2):
+            loss_g = step(batch)
+            torch.cuda.synchronize()
+            got.append((float(loss_g), bucket.flat.clone()))
+        step.close(); step = None
+        bucket.zero()
+        post, pre, stop, align, spk, enc = model(batch['text'], batch['text_length'], batch['target'], batch['target_length'], batch['speakers'],
+                                                 batch['languages'], 1.0)
+        loss, _ = crit(batch['text_length'], batch['target_length'], pre, batch['target'], post, batch['target'], stop, batch['stop_target'],
+                       align, batch['speakers'], spk, enc, None)
+        loss.backward()
+        want_loss, want_grad = float(loss), bucket.flat.clone()
+        del loss, post, pre, stop, align, spk, enc
+        for got_loss, got_grad in got:
+            assert abs(got_loss - want_loss) < 1e-6 * max(1.0, abs(want_loss))
+            assert torch.allclose(got_grad, want_grad, rtol=1e-5, atol=1e-8)
+    finally:
+        MaskSource.use_tape(None)
+        if step is not None:
+            step.close()
+    # without a tape: every replay draws new masks (the loss changes from replay to replay)
+    MaskSource.manual_seed(5)
+    step = GraphedTrainStep(model, crit, bucket, batch, teacher_forcing=1.0, warmup=2)
+    try:
+        losses = []
+        for _ in range(3):
+            losses.append(float(step(batch)))
+        assert len(set(losses)) == 3, losses
+    finally:
+        step.close()
