@@ -126,13 +126,26 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
 __global__ void fill_keep_mask_kernel(uint8_t* __restrict__ mask, size_t n, unsigned threshold, unsigned long long key,
                                       const unsigned long long* __restrict__ epoch) {
     if (epoch) key ^= mix64(*epoch * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull);
-    const size_t groups = (n + 3) / 4;
-    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
-        const unsigned long long r = mix64(key + g * 0x9E3779B97F4A7C15ull);
+    // group g of 4 decisions comes from one 64-bit draw (16 bits each); a thread iteration produces 4 groups = one 16-byte store.
+    // (same stream of decisions as a one-group-per-thread kernel: decision i depends on (key, i / 4, i % 4) only)
+    const size_t groups = (n + 3) / 4, quads = (groups + 3) / 4;
+    const bool aligned = (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < quads; q += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const size_t i = g * 4 + j;
-            if (i < n) mask[i] = (((unsigned)(r >> (16 * j)) & 0xFFFFu) >= threshold) ? 1 : 0;
+        for (int gg = 0; gg < 4; ++gg) {
+            const unsigned long long r = mix64(key + (q * 4 + gg) * 0x9E3779B97F4A7C15ull);
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v |= ((((unsigned)(r >> (16 * j)) & 0xFFFFu) >= threshold) ? 1u : 0u) << (8 * j);
+            w[gg] = v;
+        }
+        const size_t i0 = q * 16;
+        if (aligned && i0 + 16 <= n) {
+            *reinterpret_cast<uint4*>(mask + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int e = 0; e < 16; ++e)
+                if (i0 + e < n) mask[i0 + e] = (uint8_t)((w[e >> 2] >> (8 * (e & 3))) & 0xFFu);
         }
     }
 }
@@ -406,8 +419,9 @@ int b200tts_fill_keep_mask(uint8_t* mask, size_t n, float drop_rate, uint64_t se
     if (n == 0) return B200TTS_OK;
     const unsigned threshold = (unsigned)(drop_rate * 65536.0f + 0.5f);
     const unsigned long long key = mix64(seed ^ 0xD6E8FEB86659FD93ull) ^ (stream_id * 0xA24BAED4963EE407ull);
-    size_t groups = (n + 3) / 4;
-    int blocks = (int)((groups + 255) / 256 > 148 * 16 ? 148 * 16 : (groups + 255) / 256);
+    size_t quads = (n + 15) / 16;
+    int blocks = (int)((quads + 255) / 256 > 148 * 16 ? 148 * 16 : (quads + 255) / 256);
+    if (blocks < 1) blocks = 1;
     fill_keep_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, key, g_mask_epoch);
     B200_LAUNCH_CHECK();
     return B200TTS_OK;

@@ -1043,21 +1043,33 @@ __global__ void att_bwd_prep_kernel(__nv_bfloat16* __restrict__ WcB, __nv_bfloat
     }
 }
 
-// dWloc[a, c] += sum_k dWcomb[a, k] * Wc[c, k];  dWc[c, k] += sum_a Wloc[a, c] * dWcomb[a, k];  dv += sum parts
+// stage 1: dW[a, k] = sum over the nparts partial blocks (one thread per element, grid over the A * 32 + A outputs; fixed order)
+__global__ void att_bwd_reduce_parts_kernel(float* __restrict__ dWsum, float* __restrict__ dvsum, const float* __restrict__ dWcomb_part,
+                                            const float* __restrict__ dv_part, int nparts, int A) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < A * 32) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int p2 = 0;
+        for (; p2 + 3 < nparts; p2 += 4) {
+            s0 += dWcomb_part[(size_t)p2 * A * 32 + idx]; s1 += dWcomb_part[(size_t)(p2 + 1) * A * 32 + idx];
+            s2 += dWcomb_part[(size_t)(p2 + 2) * A * 32 + idx]; s3 += dWcomb_part[(size_t)(p2 + 3) * A * 32 + idx];
+        }
+        for (; p2 < nparts; ++p2) s0 += dWcomb_part[(size_t)p2 * A * 32 + idx];
+        dWsum[idx] = (s0 + s1) + (s2 + s3);
+    } else if (idx < A * 32 + A) {
+        const int a = idx - A * 32;
+        float sv = 0.f;
+        for (int p2 = 0; p2 < nparts; ++p2) sv += dv_part[(size_t)p2 * A + a];
+        dvsum[a] = sv;
+    }
+}
+// stage 2: dWloc[a, c] += sum_k dWcomb[a, k] * Wc[c, k];  dWc[c, k] += sum_a Wloc[a, c] * dWcomb[a, k];  dv += dvsum
 __global__ void att_bwd_finish_kernel(float* __restrict__ dWloc, float* __restrict__ dWc, float* __restrict__ dv,
-                                      const float* __restrict__ dWcomb_part, const float* __restrict__ dv_part,
-                                      const float* __restrict__ Wloc, const float* __restrict__ Wc, int nparts, int A, int C, int KC) {
+                                      const float* __restrict__ dWsum, const float* __restrict__ dvsum,
+                                      const float* __restrict__ Wloc, const float* __restrict__ Wc, int A, int C, int KC) {
     extern __shared__ float dW[];        // [A][32] reduced dWcomb
-    for (int idx = threadIdx.x; idx < A * 32; idx += blockDim.x) {
-        float s = 0.f;
-        for (int p2 = 0; p2 < nparts; ++p2) s += dWcomb_part[(size_t)p2 * A * 32 + idx];
-        dW[idx] = s;
-    }
-    for (int a = threadIdx.x; a < A; a += blockDim.x) {
-        float s = 0.f;
-        for (int p2 = 0; p2 < nparts; ++p2) s += dv_part[(size_t)p2 * A + a];
-        dv[a] += s;
-    }
+    for (int idx = threadIdx.x; idx < A * 32; idx += blockDim.x) dW[idx] = dWsum[idx];
+    for (int a = threadIdx.x; a < A; a += blockDim.x) dv[a] += dvsum[a];
     __syncthreads();
     for (int idx = threadIdx.x; idx < A * C; idx += blockDim.x) {
         const int a = idx / C, c = idx % C;
@@ -1245,8 +1257,13 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
         att_post_kernel<<<B * x.MT, PT, 0, st>>>(pp);
     }
     B200_LAUNCH_CHECK();
-    att_bwd_finish_kernel<<<1, 512, (size_t)A * 32 * 4, st>>>(dw.attn_location, dw.attn_loc_features, dw.attn_energy, pp.dWcomb_part,
-                                                             pp.dv_part, w.attn_location, w.attn_loc_features, B * x.MT, A, s.C, s.K);
+    // the de buffer is dead after the post pass: its head holds the reduced partials
+    float* dWsum = a.de;
+    float* dvsum = dWsum + (size_t)A * 32;
+    att_bwd_reduce_parts_kernel<<<cdiv(A * 32 + A, 128), 128, 0, st>>>(dWsum, dvsum, pp.dWcomb_part, pp.dv_part, B * x.MT, A);
+    B200_LAUNCH_CHECK();
+    att_bwd_finish_kernel<<<1, 512, (size_t)A * 32 * 4, st>>>(dw.attn_location, dw.attn_loc_features, dw.attn_energy, dWsum, dvsum,
+                                                             w.attn_location, w.attn_loc_features, A, s.C, s.K);
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
 }

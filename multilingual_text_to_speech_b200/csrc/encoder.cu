@@ -145,6 +145,124 @@ __global__ void block_fwd_kernel(const BlockArgs p, float* __restrict__ out) {
     }
 }
 
+// The same for 4 consecutive positions per thread (L % 4 == 0, 16-byte aligned tensors): one index split per 4 elements, 128-bit
+// loads / stores, 32-bit keep-mask words.  Element arithmetic is identical to the scalar kernel.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 keep4(const uint8_t* keep, size_t i, float scale) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(keep + i);
+    return make_float4((float)(w & 0xffu) * scale, (float)((w >> 8) & 0xffu) * scale, (float)((w >> 16) & 0xffu) * scale, (float)(w >> 24) * scale);
+}
+__global__ void __launch_bounds__(256) block_fwd_vec4_kernel(const BlockArgs p, float* __restrict__ out) {
+    const int Cf = p.highway ? p.Cout / 2 : p.Cout, L4 = p.L >> 2;
+    const unsigned total = (unsigned)p.NB * p.G * Cf * L4;          // < 2^32 (checked by the launcher)
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned row = idx / (unsigned)L4, l4 = idx - row * (unsigned)L4;        // row = (nb * G + g) * Cf + c
+        const unsigned r2 = row / (unsigned)Cf, c = row - r2 * (unsigned)Cf, nb = r2 / (unsigned)p.G, g = r2 - nb * (unsigned)p.G;
+        auto value = [&](int o) {
+            const int ch = g * p.Cout + o;
+            const size_t ci = ((size_t)(nb * p.G * p.Cout + ch)) * p.L + 4 * l4;
+            const float mu = p.mean[ch], be = p.beta[g * p.affine_gstride + o];
+            const float is = p.invstd[ch], ga = p.gamma[g * p.affine_gstride + o];
+            const float4 x = ld4(p.conv + ci);
+            float4 a;
+            a.x = act_fwd(p.act, (x.x - mu) * is * ga + be); a.y = act_fwd(p.act, (x.y - mu) * is * ga + be);
+            a.z = act_fwd(p.act, (x.z - mu) * is * ga + be); a.w = act_fwd(p.act, (x.w - mu) * is * ga + be);
+
+            if (p.keep) {
+                const float4 k = keep4(p.keep, ci, p.keep_scale);
+                a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w;
+            }
+            return a;
+        };
+        const size_t oi = (size_t)row * p.L + 4 * l4;
+        if (p.highway) {
+            const float4 h1 = value(c), h2 = value(Cf + c), xi = ld4(p.xin + oi);
+            const float s0 = sigmoidf_acc(h1.x), s1 = sigmoidf_acc(h1.y), s2 = sigmoidf_acc(h1.z), s3 = sigmoidf_acc(h1.w);
+            st4(out + oi, make_float4(h2.x * s0 + xi.x * (1.f - s0), h2.y * s1 + xi.y * (1.f - s1), h2.z * s2 + xi.z * (1.f - s2),
+                                      h2.w * s3 + xi.w * (1.f - s3)));
+        } else {
+            st4(out + oi, value(c));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) block_bwd_prep_vec4_kernel(const BlockArgs p, const float* __restrict__ dout, float* __restrict__ dz,
+                                                                  float* __restrict__ dx_skip) {
+    const int Cf = p.highway ? p.Cout / 2 : p.Cout, L4 = p.L >> 2;
+    const unsigned total = (unsigned)p.NB * p.G * Cf * L4;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned row = idx / (unsigned)L4, l4 = idx - row * (unsigned)L4;
+        const unsigned r2 = row / (unsigned)Cf, c = row - r2 * (unsigned)Cf, nb = r2 / (unsigned)p.G, g = r2 - nb * (unsigned)p.G;
+        const size_t oi = (size_t)row * p.L + 4 * l4;
+        const float4 go4 = ld4(dout + oi);
+        const float go[4] = {go4.x, go4.y, go4.z, go4.w};
+        float zs[2][4], as[2][4], ks[2][4];
+        size_t cis[2];
+        const int nch = p.highway ? 2 : 1;
+        for (int j = 0; j < nch; ++j) {
+            const int o = c + j * Cf, ch = g * p.Cout + o;
+            cis[j] = ((size_t)(nb * p.G * p.Cout + ch)) * p.L + 4 * l4;
+            const float mu = p.mean[ch], is = p.invstd[ch], ga = p.gamma[g * p.affine_gstride + o], be = p.beta[g * p.affine_gstride + o];
+            const float4 x = ld4(p.conv + cis[j]);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            float4 k4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.keep) k4 = keep4(p.keep, cis[j], p.keep_scale);
+            const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                zs[j][e] = (xs[e] - mu) * is * ga + be;
+                as[j][e] = act_fwd(p.act, zs[j][e]);
+                ks[j][e] = kk[e];
+            }
+        }
+        if (p.highway) {
+            const float4 xi4 = ld4(p.xin + oi);
+            const float xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+            float d1[4], d2[4], dsk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float h1 = as[0][e] * ks[0][e], h2 = as[1][e] * ks[1][e];
+                const float sg = sigmoidf_acc(h1);
+                const float dh1 = go[e] * (h2 - xi[e]) * sg * (1.f - sg), dh2 = go[e] * sg;
+                d1[e] = dh1 * ks[0][e] * act_bwd(p.act, zs[0][e], as[0][e]);
+                d2[e] = dh2 * ks[1][e] * act_bwd(p.act, zs[1][e], as[1][e]);
+                dsk[e] = go[e] * (1.f - sg);
+            }
+            st4(dz + cis[0], make_float4(d1[0], d1[1], d1[2], d1[3]));
+            st4(dz + cis[1], make_float4(d2[0], d2[1], d2[2], d2[3]));
+            st4(dx_skip + oi, make_float4(dsk[0], dsk[1], dsk[2], dsk[3]));
+        } else {
+            float d[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[e] = go[e] * ks[0][e] * act_bwd(p.act, zs[0][e], as[0][e]);
+            st4(dz + cis[0], make_float4(d[0], d[1], d[2], d[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_vec4_kernel(float* __restrict__ dz, const float* __restrict__ conv,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, int affine_gstride, const float* __restrict__ s1,
+                                                                const float* __restrict__ s2, int NB, int G, int Cout, int L, int training) {
+    const int Ct = G * Cout, L4 = L >> 2;
+    const unsigned total = (unsigned)NB * Ct * L4;
+    const float inv_n = 1.f / (float)(NB * L);
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned row = idx / (unsigned)L4, l4 = idx - row * (unsigned)L4;
+        const int ch = (int)(row % (unsigned)Ct);
+        const float is = invstd[ch], gm = gamma[(ch / Cout) * affine_gstride + ch % Cout] * is;
+        const size_t i = (size_t)row * L + 4 * l4;
+        float4 d = ld4(dz + i);
+        if (training) {
+            const float a = s1[ch] * inv_n, b = is * s2[ch] * inv_n, mu = mean[ch];
+            const float4 x = ld4(conv + i);
+            d.x = d.x - a - (x.x - mu) * b; d.y = d.y - a - (x.y - mu) * b; d.z = d.z - a - (x.z - mu) * b; d.w = d.w - a - (x.w - mu) * b;
+        }
+        st4(dz + i, make_float4(gm * d.x, gm * d.y, gm * d.z, gm * d.w));
+    }
+}
+
 // backward through highway / dropout / activation: dz [NB, G*Cout, L] (grad wrt the batch-norm output) and,
 // for highway blocks, the skip-path gradient dx = dout * (1 - sigmoid(h1)).
 __global__ void block_bwd_prep_kernel(const BlockArgs p, const float* __restrict__ dout, float* __restrict__ dz, float* __restrict__ dx_skip) {
@@ -225,42 +343,66 @@ __global__ void embedding_fwd_kernel(float* __restrict__ out, int ldo, const flo
 }
 
 // dtable[v, :] += sum over tokens with id v of dout[token, :]   (one CTA per vocabulary row: deterministic token order).
-// The ids are staged through shared memory 1024 at a time, so the scan over all tokens costs one shared-memory read per token.
+// The ids are staged through shared memory 1024 at a time; the positions of the matching tokens of a tile are compacted IN ORDER
+// (4 consecutive tokens per thread, block-wide exclusive scan of the hit counts), so only the hits are visited afterwards.
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(float* __restrict__ dtable, const float* __restrict__ dout, int ldo,
                                                             const int* __restrict__ ids, int ntok, int E, int padding_idx) {
-    __shared__ int s_ids[1024];
+    __shared__ int s_hits[1024];
+    __shared__ int s_wsum[8];
     const int v = blockIdx.x;
     if (v == padding_idx) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int EPT = 4;                                   // embedding columns per thread (E <= 1024)
     float acc[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; ++j) acc[j] = 0.f;
     for (int t0 = 0; t0 < ntok; t0 += 1024) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < 1024; t += blockDim.x) s_ids[t] = t0 + t < ntok ? ids[t0 + t] : -1;
-        __syncthreads();
-        const int n = min(1024, ntok - t0);
-        for (int t = 0; t < n; t += 8) {                      // 8 tokens at a time: all matching rows in flight, added in token order
-            float val[8][EPT];
+        // this thread's 4 consecutive tokens of the tile
+        int mine[4], cnt = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const bool hit = t + u < n && s_ids[t + u] == v;          // uniform over the CTA
-                const float* row = dout + (size_t)(t0 + t + u) * ldo;
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + tid * 4 + u;
+            mine[u] = (t < ntok && ids[t] == v) ? 1 : 0;
+            cnt += mine[u];
+        }
+        int incl = cnt;                                       // inclusive scan inside the warp, then across the 8 warps
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        __syncthreads();                                      // the previous tile's hit list is no longer read
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int base = 0, nh = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { if (w < warp) base += s_wsum[w]; nh += s_wsum[w]; }
+        int pos = base + incl - cnt;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (mine[u]) s_hits[pos++] = tid * 4 + u;
+        __syncthreads();
+        for (int h = 0; h < nh; h += 4) {                    // 4 matching rows in flight, added in token order
+            float val[4][EPT];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool on = h + u < nh;
+                const float* row = dout + (size_t)(t0 + (on ? s_hits[h + u] : 0)) * ldo;
 #pragma unroll
                 for (int j = 0; j < EPT; ++j) {
-                    const int e = threadIdx.x + j * 256;
-                    val[u][j] = (hit && e < E) ? row[e] : 0.f;
+                    const int e = tid + j * 256;
+                    val[u][j] = (on && e < E) ? row[e] : 0.f;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
                 for (int j = 0; j < EPT; ++j) acc[j] += val[u][j];
         }
     }
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-        const int e = threadIdx.x + j * 256;
+        const int e = tid + j * 256;
         if (e < E) dtable[(size_t)v * E + e] += acc[j];
     }
 }
@@ -360,6 +502,13 @@ inline BlockDims block_dims(const b200tts_convblock_shape& s) {
 }
 constexpr size_t kGemmScratch = (size_t)4 * 1024 * 1024;
 
+// 4 positions per thread: needs L % 4 == 0, 16-byte aligned tensors and fewer than 2^32 float4 groups
+bool vec4_ok(const b200tts_convblock_shape& s, const BlockDims& d, const float* conv, const float* out, const float* xin, const uint8_t* keep) {
+    auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & m) == 0; };
+    return (s.L & 3) == 0 && al(conv, 15) && al(out, 15) && (!s.highway || al(xin, 15)) && (!keep || al(keep, 3)) &&
+           d.conv_elems / 4 < 0xffffffffull;
+}
+
 int validate_block(const b200tts_convblock_shape& s) {
     B200_REQUIRE(s.NB > 0 && s.G > 0 && s.Cin > 0 && s.Cout > 0 && s.L > 0 && s.k > 0 && s.dilation > 0, "convblock: non-positive dimension");
     B200_REQUIRE(s.k % 2 == 1, "convblock: even kernel sizes are not supported (k=%d)", s.k);
@@ -420,7 +569,10 @@ int convblock_forward_impl(const b200tts_convblock_shape& s, const float* x, con
     B200_LAUNCH_CHECK();
     BlockArgs a{conv, mean, invstd, gamma, beta, affine_gstride, (s.training && s.dropout > 0.f) ? keep : nullptr,
                 1.f / (1.f - s.dropout), x, s.NB, s.G, s.Cout, s.L, s.activation, s.highway};
-    block_fwd_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, out);
+    if (vec4_ok(s, d, conv, out, x, a.keep))
+        block_fwd_vec4_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * (s.L / 4)), 256, 0, st>>>(a, out);
+    else
+        block_fwd_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, out);
     B200_LAUNCH_CHECK();
     return B200TTS_OK;
 }
@@ -449,12 +601,20 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
     if (s.stage == 1) {      // convolution only: dout is the gradient of the product
         B200_CUDA(cudaMemcpyAsync(dz, dout, d.conv_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-    block_bwd_prep_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, dout, dz, dx);
+    const bool v4 = vec4_ok(s, d, conv, dz, x, a.keep) && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 && (!s.highway || (reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+    if (v4)
+        block_bwd_prep_vec4_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * (s.L / 4)), 256, 0, st>>>(a, dout, dz, dx);
+    else
+        block_bwd_prep_kernel<<<grid_for((size_t)s.NB * s.G * d.Cf * s.L), 256, 0, st>>>(a, dout, dz, dx);
     B200_LAUNCH_CHECK();
     bn_bwd_reduce_kernel<<<(int)d.Ct, 256, 0, st>>>(dz, conv, mean, invstd, s1, s2, dgamma, dbeta, affine_gstride, s.NB, s.G, s.Cout, s.L);
     B200_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<grid_for(d.conv_elems), 256, 0, st>>>(dz, conv, mean, invstd, gamma, affine_gstride, s1, s2, s.NB, s.G, s.Cout,
-                                                                s.L, s.training);
+    if (v4)
+        bn_bwd_apply_vec4_kernel<<<grid_for(d.conv_elems / 4), 256, 0, st>>>(dz, conv, mean, invstd, gamma, affine_gstride, s1, s2, s.NB, s.G,
+                                                                           s.Cout, s.L, s.training);
+    else
+        bn_bwd_apply_kernel<<<grid_for(d.conv_elems), 256, 0, st>>>(dz, conv, mean, invstd, gamma, affine_gstride, s1, s2, s.NB, s.G, s.Cout,
+                                                                    s.L, s.training);
     B200_LAUNCH_CHECK();
     }
     if (s.stage == 2) return B200TTS_OK;
