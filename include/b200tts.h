@@ -133,6 +133,11 @@ typedef struct {
 /* Bytes of the forward workspace; it also carries everything the backward pass re-reads. */
 size_t b200tts_decoder_workspace_bytes(const b200tts_decoder_shape* shape);
 size_t b200tts_decoder_bwd_workspace_bytes(const b200tts_decoder_shape* shape);
+/* Which kernels a bf16-mode training step of this shape runs on (pure host arithmetic, no device needed): bit 0 = persistent
+ * forward loops, bit 1 = their TMA + tcgen05 + TMEM variant, bit 2 = persistent generator reverse loop, bit 3 = its tcgen05
+ * variant, bit 4 = persistent attention reverse loop, bit 5 = its tcgen05 product.  0 = the per-step kernel chains.
+ * (The reference has no such limit anywhere: modules/attention.py:67-74 takes any length.) */
+int b200tts_decoder_path(const b200tts_decoder_shape* shape);
 /* Debug: byte offset, inside the decoder forward workspace, of the per-CTA phase cycle counters the persistent
  * kernels leave behind ([2][148][8] int64: attention loop, generator loop). */
 size_t b200tts_debug_persist_profile_offset(const b200tts_decoder_shape* shape);

@@ -87,6 +87,7 @@ SIGNATURES = {
                                  c_void_p]),
     'b200tts_decoder_workspace_bytes': (c_size_t, [POINTER(DecoderShape)]),
     'b200tts_decoder_bwd_workspace_bytes': (c_size_t, [POINTER(DecoderShape)]),
+    'b200tts_decoder_path': (c_int, [POINTER(DecoderShape)]),
     'b200tts_decoder_forward': (c_int, [POINTER(DecoderShape), POINTER(DecoderParams), POINTER(DecoderInputs),
                                         POINTER(DecoderOutputs), c_void_p, c_size_t, c_void_p]),
     'b200tts_decoder_forward_chunk': (c_int, [POINTER(DecoderShape), POINTER(DecoderParams), POINTER(DecoderInputs),

@@ -242,6 +242,26 @@ size_t b200tts_decoder_workspace_bytes(const b200tts_decoder_shape* shape) {
     return decoder_layout(*shape).total * sizeof(float);
 }
 
+int b200tts_decoder_path(const b200tts_decoder_shape* shape) {
+    if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
+    const b200tts_decoder_shape& s = *shape;
+    int bits = 0;
+    const bool att_bwd = persist_att_bwd_supported(s);
+    if (persist_supported(s) && (!s.training || att_bwd)) {
+        bits |= 1;
+        if (tc_persist_supported(s)) bits |= 2;
+    }
+    if (persist_bwd_supported(s)) {
+        bits |= 4;
+        if (tc_persist_gen_bwd_supported(s)) bits |= 8;
+    }
+    if (s.training && persist_supported(s) && att_bwd) {
+        bits |= 16;
+        if (persist_att_bwd_tc(s)) bits |= 32;
+    }
+    return bits;
+}
+
 size_t b200tts_decoder_bwd_workspace_bytes(const b200tts_decoder_shape* shape) {
     if (!shape || validate_decoder_shape(*shape) != B200TTS_OK) return 0;
     return decoder_bwd_workspace_floats(*shape) * sizeof(float);

@@ -117,6 +117,7 @@ int persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_param
 struct AttBwdExtra { int MT; size_t dgb, part, wcb, wcb2, memTf, de, dwpart, dvpart, barrier, total; };
 AttBwdExtra att_bwd_extra(const b200tts_decoder_shape& s);
 bool persist_att_bwd_supported(const b200tts_decoder_shape& s);
+bool persist_att_bwd_tc(const b200tts_decoder_shape& s);      // true: the tcgen05 product variant is the one picked
 int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                          const DecoderLayout& fl, const float* fws, const PersistLayout& pl, const unsigned char* pws,
                          const float* align, const float* dalign, const float* dh_static, const float* dctx_static, float* dgates,
@@ -172,5 +173,12 @@ int launch_cell_bwd(const CellBwdArgs& a, cudaStream_t st);
 int launch_copy2d(float* dst, int ldd, const float* src, int lds, int rows, int cols, cudaStream_t st);
 int launch_add_vec(float* dst, const float* a, const float* b, int n, cudaStream_t st);
 int launch_fill(float* dst, float value, size_t n, cudaStream_t st);
+
+// persistent packed bi-LSTM (bilstm_persist.cu): cluster-of-CTAs recurrence with distributed-shared-memory state exchange
+bool bilstm_persist_supported(const b200tts_bilstm_shape& s);
+int bilstm_persist_forward(const b200tts_bilstm_shape& s, const float* w_hh, const float* w_hh_reverse, float* gates, float* hs, float* cs,
+                           float* out, const int* lengths, cudaStream_t st);
+int bilstm_persist_backward(const b200tts_bilstm_shape& s, const float* w_hh, const float* w_hh_reverse, const float* gates, const float* cs,
+                            const float* dout, float* dg, const int* lengths, cudaStream_t st);
 
 }  // namespace b200tts

@@ -890,8 +890,9 @@ struct AttPostArgs {
 };
 
 __global__ void __launch_bounds__(PT) att_post_kernel(const AttPostArgs p) {
-    __shared__ uint32_t Ph[2][64], Pl[2][64];
-    __shared__ float s_de[2][16], s_q[2][128];
+    constexpr int NS = 4;                               // decoder steps per block barrier
+    __shared__ uint32_t Ph[2][NS][64], Pl[2][NS][64];
+    __shared__ float s_de[2][NS][16], s_q[2][NS][128];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x / p.MT, mt = blockIdx.x % p.MT;
     const int L = p.L, A = p.A, half = (p.KC - 1) / 2, l0 = mt * 16;
@@ -932,68 +933,92 @@ __global__ void __launch_bounds__(PT) att_post_kernel(const AttPostArgs p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) dwacc[nt][e] = 0.f;
 
-    auto stage = [&](int i, int buf) {
-        // window of cumpad needed by this tile: x in [l0, l0 + 16 + 32)
-        if (tid < 64) {
-            const float* cum = p.cum + ((size_t)i * p.B + b) * L;
-            const int x = l0 + tid;
-            float c0 = 0.f, c1 = 0.f;
-            const int la = x - half, lb = x + 1 - half;
-            if (la >= 0 && la < L) c0 = cum[la];
-            if (lb >= 0 && lb < L) c1 = cum[lb];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
-            __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
-            Ph[buf][tid] = *reinterpret_cast<uint32_t*>(&hp);
-            Pl[buf][tid] = pack2(c0 - __bfloat162float(h0), c1 - __bfloat162float(h1));
-        } else if (tid < 80) {
-            const int l = l0 + tid - 64;
-            s_de[buf][tid - 64] = l < L ? p.de[((size_t)i * p.B + b) * L + l] : 0.f;
-        } else if (tid >= 128 && tid < 128 + A) {
-            s_q[buf][tid - 128] = p.q[((size_t)i * p.B + b) * A + tid - 128];
+    // The T steps are independent here (only the accumulators chain), so they are processed in chunks of NS with ONE block barrier per
+    // chunk: the operands of the next chunk (cumulative-weight window, de, query of NS steps) are loaded into registers before the MMAs
+    // of the current chunk and stored to the other shared-memory buffer after them, i.e. their DRAM / L2 latency hides behind compute.
+    float r0[NS], r1[NS];
+    auto load = [&](int i0) {
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) {
+            const int i = i0 + s2;
+            r0[s2] = 0.f; r1[s2] = 0.f;
+            if (i >= p.T) continue;
+            if (tid < 64) {                    // window of cumpad needed by this tile: x in [l0, l0 + 16 + 32)
+                const float* cum = p.cum + ((size_t)i * p.B + b) * L;
+                const int la = l0 + tid - half, lb = la + 1;
+                if (la >= 0 && la < L) r0[s2] = __ldg(cum + la);
+                if (lb >= 0 && lb < L) r1[s2] = __ldg(cum + lb);
+            } else if (tid < 80) {
+                const int l = l0 + tid - 64;
+                if (l < L) r0[s2] = __ldg(p.de + ((size_t)i * p.B + b) * L + l);
+            } else if (tid >= 128 && tid < 128 + A) {
+                r0[s2] = __ldg(p.q + ((size_t)i * p.B + b) * A + tid - 128);
+            }
         }
     };
-    if (l0 < len) stage(0, 0);
-    __syncthreads();
-    for (int i = 0; i < p.T && l0 < len; ++i) {
-        const int buf = i & 1;
-        if (i + 1 < p.T) stage(i + 1, buf ^ 1);
-        if (active) {
-            // S^T[a, l] = sum_k Wcomb[a, k] * cumpad[l + k]
-            float sacc[2][4];
+    auto store = [&](int buf) {
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    // B fragment (k rows, l cols): (k = ks*16 + 2t (+1) (+8), l = nt*8 + g) -> cumpad[l + k]
-                    const int x = nt * 8 + g + ks * 16 + 2 * tq;
-                    mma_bf16(sacc[nt], wa[ks], Ph[buf][x], Ph[buf][x + 8]);
-                    mma_bf16(sacc[nt], wa[ks], Pl[buf][x], Pl[buf][x + 8]);
-                }
-            const float q0 = s_q[buf][a_base + g] + bias0, q1 = s_q[buf][a_base + g + 8] + bias1;
-            uint32_t dsA[2][2];
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const float dea = s_de[buf][nt * 8 + 2 * tq], deb = s_de[buf][nt * 8 + 2 * tq + 1];
-                const float t0 = tanh_fast(sacc[nt][0] + q0 + mT[nt][0]), t1 = tanh_fast(sacc[nt][1] + q0 + mT[nt][1]);
-                const float t2 = tanh_fast(sacc[nt][2] + q1 + mT[nt][2]), t3 = tanh_fast(sacc[nt][3] + q1 + mT[nt][3]);
-                const float d0 = dea * v0 * (1.f - t0 * t0), d1 = deb * v0 * (1.f - t1 * t1);
-                const float d2 = dea * v1 * (1.f - t2 * t2), d3 = deb * v1 * (1.f - t3 * t3);
-                dmacc[nt][0] += d0; dmacc[nt][1] += d1; dmacc[nt][2] += d2; dmacc[nt][3] += d3;
-                dvacc[0] += dea * t0 + deb * t1; dvacc[1] += dea * t2 + deb * t3;
-                dsA[nt][0] = pack2(d0, d1); dsA[nt][1] = pack2(d2, d3);
-            }
-            // d Wcomb[a, k] += sum_l ds^T[a, l] * cumpad[l + k]   (A = ds^T chained; B fragment (l rows, k cols) = cumpad[l + k])
-            const uint32_t af[4] = {dsA[0][0], dsA[0][1], dsA[1][0], dsA[1][1]};
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int x = 2 * tq + nt * 8 + g;                  // l = 2t (+1) (+8), k = nt*8 + g
-                mma_bf16(dwacc[nt], af, Ph[buf][x], Ph[buf][x + 8]);
+        for (int s2 = 0; s2 < NS; ++s2) {
+            if (tid < 64) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(r0[s2]), h1 = __float2bfloat16_rn(r1[s2]);
+                __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
+                Ph[buf][s2][tid] = *reinterpret_cast<uint32_t*>(&hp);
+                Pl[buf][s2][tid] = pack2(r0[s2] - __bfloat162float(h0), r1[s2] - __bfloat162float(h1));
+            } else if (tid < 80) {
+                s_de[buf][s2][tid - 64] = r0[s2];
+            } else if (tid >= 128 && tid < 128 + A) {
+                s_q[buf][s2][tid - 128] = r0[s2];
             }
         }
+    };
+    if (l0 < len) { load(0); store(0); }
+    __syncthreads();
+    for (int i0 = 0; i0 < p.T && l0 < len; i0 += NS) {
+        const int buf = (i0 / NS) & 1;
+        const bool more = i0 + NS < p.T;
+        if (more) load(i0 + NS);
+        if (active) {
+#pragma unroll
+            for (int s2 = 0; s2 < NS; ++s2) {
+                if (i0 + s2 >= p.T) break;
+                // S^T[a, l] = sum_k Wcomb[a, k] * cumpad[l + k]
+                float sacc[2][4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        // B fragment (k rows, l cols): (k = ks*16 + 2t (+1) (+8), l = nt*8 + g) -> cumpad[l + k]
+                        const int x = nt * 8 + g + ks * 16 + 2 * tq;
+                        mma_bf16(sacc[nt], wa[ks], Ph[buf][s2][x], Ph[buf][s2][x + 8]);
+                        mma_bf16(sacc[nt], wa[ks], Pl[buf][s2][x], Pl[buf][s2][x + 8]);
+                    }
+                const float q0 = s_q[buf][s2][a_base + g] + bias0, q1 = s_q[buf][s2][a_base + g + 8] + bias1;
+                uint32_t dsA[2][2];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const float dea = s_de[buf][s2][nt * 8 + 2 * tq], deb = s_de[buf][s2][nt * 8 + 2 * tq + 1];
+                    const float t0 = tanh_fast(sacc[nt][0] + q0 + mT[nt][0]), t1 = tanh_fast(sacc[nt][1] + q0 + mT[nt][1]);
+                    const float t2 = tanh_fast(sacc[nt][2] + q1 + mT[nt][2]), t3 = tanh_fast(sacc[nt][3] + q1 + mT[nt][3]);
+                    const float d0 = dea * v0 * (1.f - t0 * t0), d1 = deb * v0 * (1.f - t1 * t1);
+                    const float d2 = dea * v1 * (1.f - t2 * t2), d3 = deb * v1 * (1.f - t3 * t3);
+                    dmacc[nt][0] += d0; dmacc[nt][1] += d1; dmacc[nt][2] += d2; dmacc[nt][3] += d3;
+                    dvacc[0] += dea * t0 + deb * t1; dvacc[1] += dea * t2 + deb * t3;
+                    dsA[nt][0] = pack2(d0, d1); dsA[nt][1] = pack2(d2, d3);
+                }
+                // d Wcomb[a, k] += sum_l ds^T[a, l] * cumpad[l + k]   (A = ds^T chained; B fragment (l rows, k cols) = cumpad[l + k])
+                const uint32_t af[4] = {dsA[0][0], dsA[0][1], dsA[1][0], dsA[1][1]};
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int x = 2 * tq + nt * 8 + g;                  // l = 2t (+1) (+8), k = nt*8 + g
+                    mma_bf16(dwacc[nt], af, Ph[buf][s2][x], Ph[buf][s2][x + 8]);
+                }
+            }
+        }
+        if (more) store(buf ^ 1);
         __syncthreads();
     }
     if (a_base < A) {
@@ -1167,6 +1192,7 @@ static bool att_bwd_pick(const b200tts_decoder_shape& s, AttBwdGeom* out) {
 }
 
 bool persist_att_bwd_supported(const b200tts_decoder_shape& s) { return att_bwd_pick(s, nullptr); }
+bool persist_att_bwd_tc(const b200tts_decoder_shape& s) { AttBwdGeom g{}; return att_bwd_pick(s, &g) && g.tc; }
 
 int tc_make_mapN_bf16(void* map, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides, const unsigned* box);
 

@@ -455,6 +455,24 @@ void set_tc_enabled(int on) { g_tc_enabled = on; }
 int tc_enabled() { return g_tc_enabled; }
 
 // Returns B200TTS_OK and sets *handled = true when the tcgen05 path ran; *handled = false -> caller uses the mma.sync path.
+// Split-K decision shared by the dense and the convolution weight-gradient products: with fewer output tiles than CTA slots (2 per SM)
+// and a long K, K is cut into `splits` ranges of `kper` k-blocks; the partial tiles live at the END of the scratch, clear of the
+// packed (and cached) operands that occupy its first `used` bytes.  Leaves a.ksplit = 1 when it does not pay or does not fit.
+static void pick_ksplit(TcArgs& a, int M, int N, int K, size_t used) {
+    const int tiles = cdiv(N, TBN) * cdiv(M, TBM), nk = cdiv(K, TBK);
+    if (tiles > 148 || nk < 64) return;
+    int want = 296 / tiles;
+    if (want > nk / 16) want = nk / 16;
+    if (want > 32) want = 32;
+    if (want < 2) return;
+    const int kper = cdiv(nk, want), splits = cdiv(nk, kper);
+    const size_t pbytes = (size_t)splits * M * N * 4;
+    if (splits >= 2 && used + pbytes + 1024 <= g_scratch.bytes) {
+        a.ksplit = splits; a.kper = kper;
+        a.partial = reinterpret_cast<float*>(g_scratch.ptr + ((g_scratch.bytes - pbytes) & ~(size_t)1023));
+    }
+}
+
 int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     *handled = false;
     if (!g_tc_enabled || g_scratch.ptr == nullptr) return B200TTS_OK;
@@ -516,24 +534,9 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     a.batch = d.batch; a.a_batch_mod = d.a_batch_mod; a.strideC = d.strideC;
     a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
     a.ksplit = 1; a.kper = 0; a.partial = nullptr;
-    {   // few output tiles and a long K (weight gradients over all (step, utterance) rows): split K over the idle SMs
-        const int tiles = cdiv(d.N, TBN) * cdiv(d.M, TBM), nk = cdiv(d.K, TBK);
-        if (d.batch == 1 && tiles <= 37 && nk >= 64) {
-            int want = 148 / tiles;
-            if (want > nk / 16) want = nk / 16;
-            if (want > 32) want = 32;
-            if (want >= 2) {
-                const int kper = cdiv(nk, want), splits = cdiv(nk, kper);
-                const size_t pbytes = (size_t)splits * d.M * d.N * 4;
-                // the partial tiles live at the END of the scratch, clear of the packed (and cached) operands
-                const size_t hi = (g_cache_on ? g_cache_off : 0) + (pack_a ? a_bytes : 0) + (pack_b ? b_bytes : 0);
-                if (splits >= 2 && hi + pbytes + 1024 <= g_scratch.bytes) {
-                    a.ksplit = splits; a.kper = kper;
-                    a.partial = reinterpret_cast<float*>(g_scratch.ptr + ((g_scratch.bytes - pbytes) & ~(size_t)1023));
-                }
-            }
-        }
-    }
+    // few output tiles and a long K (weight gradients over all (step, utterance) rows): split K over the idle SMs
+    if (d.batch == 1)
+        pick_ksplit(a, d.M, d.N, d.K, (g_cache_on ? g_cache_off : 0) + (pack_a ? a_bytes : 0) + (pack_b ? b_bytes : 0));
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     static bool configured = false;
     if (!configured) {
@@ -636,14 +639,22 @@ int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int
     a.batch = G; a.a_batch_mod = 0; a.strideC = (long long)Cout * R;
     a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
     a.ksplit = 1; a.kper = 0; a.partial = nullptr;
+    if (G == 1) pick_ksplit(a, Cout, R, K, a_bytes + b_bytes);      // postnet convolutions: 16 .. 80 tiles over K = NB * L
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(R, TBN), cdiv(Cout, TBM), G);
+    dim3 grid(cdiv(R, TBN), cdiv(Cout, TBM), a.ksplit > 1 ? a.ksplit : G);
     {
         KernelTimer kt("gemm_tc_kernel", st);
         gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, a);
     }
     B200_LAUNCH_CHECK();
+    if (a.ksplit > 1) {
+        const size_t total = (size_t)Cout * R;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(a.partial, dweight, nullptr, Cout, R, R, a.ksplit, 1.f, 1.f);
+        B200_LAUNCH_CHECK();
+    }
     *handled = true;
     return B200TTS_OK;
 }

@@ -89,6 +89,7 @@ int bilstm_forward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_para
     const RnnLayout l = rnn_layout(s);
     const int B = s.B, L = s.L, E = s.E, H = s.H;
     const size_t BH = (size_t)B * H, B4H = 4 * BH;
+    const bool persist = bilstm_persist_supported(s);
     to_processing_order_kernel<<<grid_for(2 * (size_t)L * B * E), 256, 0, st>>>(saved + l.xp, x, B, L, E);
     B200_LAUNCH_CHECK();
     for (int dir = 0; dir < 2; ++dir) {
@@ -103,6 +104,7 @@ int bilstm_forward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_para
         g.A = saved + l.xp + (size_t)dir * L * B * E; g.lda = E; g.B = w_ih; g.ldb = E; g.transB = 1; g.C = gates; g.ldc = 4 * H;
         g.bias = bsum; g.M = L * B; g.N = 4 * H; g.K = E;
         B200_TRY(gemm_run(g, st));
+        if (persist) continue;           // the recurrence of both directions runs in ONE persistent launch below
         B200_TRY(launch_fill(hs, 0.f, BH, st));
         B200_TRY(launch_fill(cs, 0.f, BH, st));
         for (int j = 0; j < L; ++j) {
@@ -123,6 +125,8 @@ int bilstm_forward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_para
             B200_TRY(launch_cell_fwd(ca, st));
         }
     }
+    if (persist)
+        B200_TRY(bilstm_persist_forward(s, w.w_hh, w.w_hh_reverse, saved + l.gates, saved + l.hs, saved + l.cs, out, lengths, st));
     return B200TTS_OK;
 }
 
@@ -131,6 +135,7 @@ int bilstm_backward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_par
     const RnnLayout l = rnn_layout(s);
     const int B = s.B, L = s.L, E = s.E, H = s.H;
     const size_t BH = (size_t)B * H, B4H = 4 * BH;
+    const bool persist = bilstm_persist_supported(s);
     for (int dir = 0; dir < 2; ++dir) {
         const float* w_ih = dir ? w.w_ih_reverse : w.w_ih; const float* w_hh = dir ? w.w_hh_reverse : w.w_hh;
         float* dw_ih = dir ? dw.w_ih_reverse : dw.w_ih; float* dw_hh = dir ? dw.w_hh_reverse : dw.w_hh;
@@ -139,7 +144,9 @@ int bilstm_backward_impl(const b200tts_bilstm_shape& s, const b200tts_bilstm_par
         const float* hs = saved + l.hs + (size_t)dir * (L + 1) * BH;
         const float* cs = saved + l.cs + (size_t)dir * (L + 1) * BH;
         float* dg = ws + l.dg + (size_t)dir * L * B4H;
-        for (int j = L - 1; j >= 0; --j) {
+        if (persist && dir == 0)         // gate gradients of BOTH directions in one persistent launch
+            B200_TRY(bilstm_persist_backward(s, w.w_hh, w.w_hh_reverse, saved + l.gates, saved + l.cs, dout, ws + l.dg, lengths, st));
+        for (int j = L - 1; j >= 0 && !persist; --j) {
             const int t = dir ? L - 1 - j : j;
             CellBwdArgs ca{};
             ca.gates = gates + (size_t)j * B4H; ca.c_prev = cs + (size_t)j * BH;
