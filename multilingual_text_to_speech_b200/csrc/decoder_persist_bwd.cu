@@ -440,22 +440,62 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             }
             const int len = pa_len;                        // loaded once, before the loop
             const int mtiles = (len + 15) / 16;
-            for (int m = tid; m < M; m += PT) {
-                float g = p.dctx_static[((size_t)i * B + b) * M + m];
-                if (!last)
-                    for (int k2 = 0; k2 < KBA; ++k2) g += __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + m);
-                s_dctx[m] = g;
-                if (hf == 0) p.dctx_tot[((size_t)i * B + b) * M + m] = g;
+            constexpr int KT = 6;                          // k-tiles (16 memory dims) per register batch of the dw product
+            {   // Staging of the step's operands.  EVERY global load of the phase is issued before the first dependent instruction: ONE L2
+                // round trip instead of five serial ones (partial d ctx sums, alignment row, query, cumulative weights, d alignment);
+                // two register slots per thread cover M <= 2 PT and L16 + 48 <= 2 PT (checked on the host)
+                const size_t row = (size_t)i * B + b;
+                const float* cum = p.cum + row * L;
+                float r_g[2], r_p[2][KBA], r_w[2], r_da[2], r_c0[2], r_c1[2], r_q = 0.f, bias_r = 0.f, v_r = 0.f;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = tid + e * PT;            // memory dim / text position / Toeplitz index of this slot
+                    r_g[e] = 0.f; r_w[e] = 0.f; r_da[e] = 0.f; r_c0[e] = 0.f; r_c1[e] = 0.f;
+#pragma unroll
+                    for (int k2 = 0; k2 < KBA; ++k2) r_p[e][k2] = 0.f;
+                    if (m < M) {
+                        r_g[e] = p.dctx_static[row * M + m];
+                        if (!last) {
+#pragma unroll
+                            for (int k2 = 0; k2 < KBA; ++k2) r_p[e][k2] = __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + m);
+                        }
+                    }
+                    if (m < L) {
+                        r_w[e] = p.align[(size_t)b * p.align_bstride + (size_t)i * L + m];
+                        if (p.dalign && m < len) r_da[e] = p.dalign[(size_t)b * p.dalign_bstride + (size_t)i * L + m];
+                    }
+                    if (m < L16 + 48) {
+                        const int l0 = m - half, l1 = l0 + 1;
+                        if (l0 >= 0 && l0 < L) r_c0[e] = __ldcg(cum + l0);
+                        if (l1 >= 0 && l1 < L) r_c1[e] = __ldcg(cum + l1);
+                    }
+                }
+                if (tid < A) { r_q = p.q[row * A + tid]; bias_r = p.bias[tid]; v_r = p.v[tid]; }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = tid + e * PT;
+                    if (m < M) {
+                        float g = r_g[e];
+#pragma unroll
+                        for (int k2 = 0; k2 < KBA; ++k2) g += r_p[e][k2];
+                        s_dctx[m] = g;
+                        if (hf == 0) p.dctx_tot[row * M + m] = g;
+                    }
+                    if (m < L16) { s_w[m] = r_w[e]; s_de[m] = r_da[e]; }      // s_de starts as d alignment (or 0); the dw epilogue adds to it
+                    if (m < L16 + 48) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(r_c0[e]), h1 = __float2bfloat16_rn(r_c1[e]);
+                        __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
+                        s_Ph[m] = *reinterpret_cast<uint32_t*>(&hp);
+                        s_Pl[m] = pack2(r_c0[e] - __bfloat162float(h0), r_c1[e] - __bfloat162float(h1));
+                    }
+                }
+                if (tid < A) { s_qb[tid] = r_q + bias_r; s_vv[tid] = v_r; }
             }
-            for (int l = tid; l < L16; l += PT) s_w[l] = l < L ? p.align[(size_t)b * p.align_bstride + (size_t)i * L + l] : 0.f;
-            for (int a = tid; a < A; a += PT) { s_qb[a] = p.q[((size_t)i * B + b) * A + a] + p.bias[a]; s_vv[a] = p.v[a]; }
-            build_pairs(s_Ph, s_Pl, p.cum + ((size_t)i * B + b) * L, L, half, L16 + 48, tid, PT);
             __syncthreads();
             // dw[l] = dalign + dcum + <dctx, memory[l]> on the tensor cores: A = fragment-major memory (one 16-byte load per lane per
             // MMA), B = (hi(dctx), lo(dctx)) in columns 0 / 1; warp owns position tiles {warp, warp + 8}
             {
                 const int g = lane >> 2, tq = lane & 3;
-                constexpr int KT = 6;                         // k-tiles (16 memory dims) per register batch
                 for (int lt = t_lo + warp; lt < t_hi; lt += 8) {
                     float dacc[4] = {0.f, 0.f, 0.f, 0.f}, dacc2[4] = {0.f, 0.f, 0.f, 0.f};
                     if (lt * 16 < len) {
@@ -498,10 +538,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                         for (int rr = 0; rr < 2; ++rr) {
                             const int l = lt * 16 + g + 8 * rr;
                             float gv = 0.f;
-                            if (l < len) {
-                                gv = (rr ? dacc[2] + dacc[3] : dacc[0] + dacc[1]) + (last ? 0.f : dcum[l]);
-                                if (p.dalign) gv += p.dalign[(size_t)b * p.dalign_bstride + (size_t)i * L + l];
-                            }
+                            if (l < len) gv = (rr ? dacc[2] + dacc[3] : dacc[0] + dacc[1]) + (last ? 0.f : dcum[l]) + s_de[l];   // s_de[l]: d alignment
                             s_de[l] = gv;
                         }
                     }
@@ -629,6 +666,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             // d cum_{i-1}[j] = d cum_i[j] + sum_k G[j + half - k, k] for the own positions (their G rows: own tiles + the halo tile)
             for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) {
                 float acc = last ? 0.f : dcum[j];
+#pragma unroll 4
                 for (int k = 0; k < p.KC; ++k) {
                     const int l = j + half - k;
                     if (l >= 0 && l < mtiles * 16) acc += s_G[(size_t)(l - g_lo) * GLD + k];
@@ -648,20 +686,19 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
         // =========================== PB: attention-LSTM cell backward ===========================
         if (owner) {
             // recurrent partial sums of this thread's (b, u) pairs (written by the product of the previous reverse step)
+            // ... requested together with the query gradients of ALL utterances (staged below): one L2 round trip for both.  (The loop
+            // this replaces issued load -> dependent shared-memory store per iteration: eight serial round trips per step.)
             float rec_[MAXE];
+            float r8[MAXE][KBA];
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
                 const int idx = tid + e * PT;
-                rec_[e] = 0.f;
+#pragma unroll
+                for (int k2 = 0; k2 < KBA; ++k2) r8[e][k2] = 0.f;
                 if (idx < B * UOWN && !last) {
                     const int b = idx / UOWN, u = uo0 + idx % UOWN;
-                    float r8[KBA];
 #pragma unroll
-                    for (int k2 = 0; k2 < KBA; ++k2) r8[k2] = __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
-                    float rs = 0.f;
-#pragma unroll
-                    for (int k2 = 0; k2 < KBA; ++k2) rs += r8[k2];
-                    rec_[e] = rs;
+                    for (int k2 = 0; k2 < KBA; ++k2) r8[e][k2] = __ldcg(p.part + ((size_t)k2 * B + b) * p.NOUT + M + u);
                 }
             }
             // d h (query part) = dq[b, :] . Wq[:, u] on the tensor cores: A = dq rows staged in shared memory (bf16 hi + lo),
@@ -670,11 +707,28 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             float* s_dq = reinterpret_cast<float*>(As);
             float* s_dhq = s_dq + (size_t)B * A;
             {
-                const int nf4 = A / 4;
-                for (int idx = tid; idx < B * nf4; idx += PT) {
-                    const int b = idx / nf4, c4 = idx % nf4;
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(p.dq + ((size_t)i * B + b) * A) + c4);
-                    *reinterpret_cast<float4*>(s_dq + b * A + ((c4 * 4 + 8 * (b & 7)) & (A - 1))) = v;
+                constexpr int NQ = 8;                     // float4 per thread: B * A / 4 <= NQ * PT  (A = 128, B <= 64: checked on the host)
+                const float4* dq4 = reinterpret_cast<const float4*>(p.dq + (size_t)i * B * A);      // [B][A] block of this step, contiguous
+                float4 qv[NQ];
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    const int idx = tid + j * PT;
+                    if (idx < B * 32) qv[j] = __ldcg(dq4 + idx);         // A == 128 (host check): 32 float4 per utterance
+                }
+#pragma unroll
+                for (int e = 0; e < MAXE; ++e) {
+                    float rs = 0.f;
+#pragma unroll
+                    for (int k2 = 0; k2 < KBA; ++k2) rs += r8[e][k2];
+                    rec_[e] = rs;
+                }
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    const int idx = tid + j * PT;
+                    if (idx < B * 32) {
+                        const int b = idx >> 5, c4 = idx & 31;
+                        *reinterpret_cast<float4*>(s_dq + b * A + ((c4 * 4 + 8 * (b & 7)) & (A - 1))) = qv[j];
+                    }
                 }
                 __syncthreads();
                 const int g = lane >> 2, tq = lane & 3, mt = warp & 3, kh = warp >> 2;      // warp = (16-utterance tile, half of the A range)
@@ -1165,6 +1219,7 @@ static AttBwdGeom att_bwd_geom(const b200tts_decoder_shape& s, bool tc) {
 
 static bool att_bwd_variant_ok(const b200tts_decoder_shape& s, const AttBwdGeom& g) {
     if (s.A != 128 || s.K > 32 || s.B * 8 > 3 * PT || s.D % KBA != 0) return false;
+    if (s.M > 2 * PT || (s.L + 15) / 16 * 16 + 48 > 2 * PT || s.B * (s.A / 4) > 8 * PT) return false;      // register-slot staging of the attention backward
     if (s.D / 8 > g.grid) return false;                       // cell-backward ownership: 8 hidden units per CTA
     if (g.grid / 2 < s.B || g.grid > 148) return false;       // one CTA pair per utterance, all CTAs co-resident
     if (g.tc) {
