@@ -247,7 +247,8 @@ int b200tts_decoder_path(const b200tts_decoder_shape* shape) {
     const b200tts_decoder_shape& s = *shape;
     int bits = 0;
     const bool att_bwd = persist_att_bwd_supported(s);
-    if (persist_supported(s) && (!s.training || att_bwd)) {
+    const bool fwd_loops = tc_persist_supported(s) || persist_supported(s);
+    if (fwd_loops && (!s.training || att_bwd)) {
         bits |= 1;
         if (tc_persist_supported(s)) bits |= 2;
     }
@@ -255,7 +256,7 @@ int b200tts_decoder_path(const b200tts_decoder_shape* shape) {
         bits |= 4;
         if (tc_persist_gen_bwd_supported(s)) bits |= 8;
     }
-    if (s.training && persist_supported(s) && att_bwd) {
+    if (s.training && fwd_loops && att_bwd) {
         bits |= 16;
         if (persist_att_bwd_tc(s)) bits |= 32;
     }

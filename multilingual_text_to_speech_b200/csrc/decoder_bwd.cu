@@ -710,7 +710,8 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     }
 
     // ---- 3. attention LSTM + attention reverse loop ----
-    const bool persist_att = precision_mode() == B200TTS_PRECISION_BF16 && s.training && persist_supported(s) && persist_att_bwd_supported(s);
+    const bool persist_att = precision_mode() == B200TTS_PRECISION_BF16 && s.training && (tc_persist_supported(s) || persist_supported(s)) &&
+                             persist_att_bwd_supported(s);
     if (persist_att) {
         // bf16 perf mode: cooperative weight-stationary kernel (tensor-core attention backward inside), then a parallel post pass
         const PersistLayout pl = persist_layout(s);

@@ -538,8 +538,8 @@ int decoder_forward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_p
     }
 
     // the persistent forward rounds memory / memT to bf16; only the persistent backward recomputes with the same operands
-    const bool persistent = !sequential && state == nullptr && precision_mode() == B200TTS_PRECISION_BF16 && persist_supported(s) &&
-                            (!s.training || persist_att_bwd_supported(s));
+    const bool persistent = !sequential && state == nullptr && precision_mode() == B200TTS_PRECISION_BF16 &&
+                            (tc_persist_supported(s) || persist_supported(s)) && (!s.training || persist_att_bwd_supported(s));
     if (persistent) {
         // bf16 perf mode: one cooperative, weight-stationary kernel per recurrence (decoder_persist.cu)
         unsigned char* pws = reinterpret_cast<unsigned char*>(c.at(l.persist));

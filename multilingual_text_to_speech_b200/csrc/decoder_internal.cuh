@@ -102,7 +102,7 @@ static inline DecoderLayout decoder_layout(const b200tts_decoder_shape& s) {
 
 int validate_decoder_shape(const b200tts_decoder_shape& s);
 // tcgen05 / TMA persistent forward loops (decoder_persist_tc.cu): operand rows are [h | ctx | 0] in 64-column k-blocks
-struct TcPersistGeom { int Kp_att, Kp_gen, nkb_att, nkb_gen, nkb_h, ch_c_att, ch_h_att, slot_att, ch_h_gen, slot_gen; };
+struct TcPersistGeom { int Kp_att, Kp_gen, nkb_att, nkb_gen, nkb_h, ch_c_att, n_c_att, alias_att, ch_h_att, slot_att, ch_h_gen, slot_gen; };
 TcPersistGeom tc_persist_geom(const b200tts_decoder_shape& s);
 bool tc_persist_supported(const b200tts_decoder_shape& s);
 int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,

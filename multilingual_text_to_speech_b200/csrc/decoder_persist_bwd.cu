@@ -63,7 +63,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag, bool async_fence = false) {
+struct NoOverlap { __device__ __forceinline__ void operator()() const {} };
+// `overlap` runs on every thread BETWEEN the CTA's arrival and its wait: work that does not depend on other CTAs (next step's operand
+// prefetch) hides under the barrier latency instead of delaying the arrival
+template <typename Overlap = NoOverlap>
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag, bool async_fence = false,
+                                             Overlap overlap = Overlap()) {
     __shared__ int s_ok;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -72,6 +77,9 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
         // arrival = ONE release-reduction (cumulative over the CTA's writes, which the __syncthreads above made visible to thread 0);
         // the wait polls with relaxed loads and issues a single acquire fence after the last one
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
+    overlap();
+    if (threadIdx.x == 0) {
         int ok = 1;
         const long long t0 = clock64();
         unsigned polls = 0;
@@ -99,6 +107,8 @@ __device__ __forceinline__ void st_peer_f32(const float* local_smem, uint32_t pe
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// tanh of the recomputed cell state in the reverse loops: the same ex2-based form the forward loops of the bf16 mode use (~1e-6 relative)
+__device__ __forceinline__ float tanh_exp(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
 #define BPROF_DECL long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
 #define BPROF_MARK(slot)                                                                                         \
@@ -257,7 +267,8 @@ constexpr int GLD = 33;           // row stride of the G tile buffer (floats)
 // tcgen05 variant of the product: CTA (kb, nb) of 8 x 18 keeps W^T[n-block of 80 outputs, K-slice kb] as K-major SWIZZLE_128B tiles (UMMA B
 // operand, N = 80); the whole batch (<= 64 utterances, TMA zero-fills the rest) is the A operand (M = 64), ONE 5-D TMA box per step
 constexpr int NBT = 18;           // n-blocks of the tcgen05 variant  -> 8 x 18 = 144 CTAs (72 pairs)
-constexpr int TUN = 80;           // outputs per n-block (UMMA N)
+constexpr int TUN = 80;           // outputs per n-block (UMMA N); TUN_WIDE when M + D > NBT * TUN (memory dim 512)
+constexpr int TUN_WIDE = 96;
 constexpr int TMEM_COLS_ATT = 128;
 
 struct AttBwdArgs {
@@ -313,7 +324,8 @@ __device__ __forceinline__ void build_pairs(uint32_t* Ph, uint32_t* Pl, const fl
     }
 }
 
-template <bool TC>
+// UNC: outputs per n-block of the tcgen05 product (UMMA N), compile-time (80, or 96 for memory dim 512); 0 for the mma.sync variant
+template <bool TC, int UNC>
 __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_constant__ CUtensorMap tmG, const AttBwdArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw0) + 1023) & ~(uintptr_t)1023);
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
     }
     __syncthreads();
     if (TC) { tcx::tc_fence_after(); tmem_base = tmem_base_s; }
-    const uint32_t idesc = tcx::make_idesc_bf16(64, TUN);
+    const uint32_t idesc = tcx::make_idesc_bf16(64, UNC);
 
     const float inv_h = 1.f / (1.f - p.rate_h), inv_c = 1.f / (1.f - p.rate_c);
     constexpr int MAXE = 3;               // (b, u) pairs per thread: B * 8 / 256 <= 3 for B <= 64... (B <= 96)
@@ -397,6 +409,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
     float* s_dqx = s_dqp + 8 * A;                         // [A]  the peer's partial (written through distributed shared memory)
     float* s_dotx = s_dqx + A;                            // [4]  the peer's partial softmax dot
     float* s_stage = s_dotx + 4;                          // [L16] d cum staging
+    uint2* s_bf = reinterpret_cast<uint2*>(s_stage + L16); // [M16][32] B fragments (hi / lo split of d ctx) of the dw product, shared by all warps
     BPROF_DECL
 
     const int pc = cta >> 1;
@@ -492,6 +505,22 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 if (tid < A) { s_qb[tid] = r_q + bias_r; s_vv[tid] = v_r; }
             }
             __syncthreads();
+            // B fragments of the dw product: lanes g = 0 hold hi(dctx), g = 1 hold lo(dctx), other columns zero.  They depend on the k-tile only,
+            // so the CTA builds the M16 fragments ONCE (every warp used to rebuild all of them: ~40 instructions per fragment and warp)
+            for (int idx = tid; idx < p.M16 * 32; idx += PT) {
+                const int kt = idx >> 5, gg = (idx >> 2) & 7, tt = idx & 3;
+                const int m0 = kt * 16 + 2 * tt;
+                uint2 f = make_uint2(0u, 0u);
+                if (gg < 2) {
+                    const float w0 = m0 < M ? s_dctx[m0] : 0.f, w1 = m0 + 1 < M ? s_dctx[m0 + 1] : 0.f;
+                    const float w2 = m0 + 8 < M ? s_dctx[m0 + 8] : 0.f, w3 = m0 + 9 < M ? s_dctx[m0 + 9] : 0.f;
+                    const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
+                    const float h2 = __bfloat162float(__float2bfloat16_rn(w2)), h3 = __bfloat162float(__float2bfloat16_rn(w3));
+                    f = gg == 0 ? make_uint2(pack2(h0, h1), pack2(h2, h3)) : make_uint2(pack2(w0 - h0, w1 - h1), pack2(w2 - h2, w3 - h3));
+                }
+                s_bf[idx] = f;
+            }
+            __syncthreads();
             // dw[l] = dalign + dcum + <dctx, memory[l]> on the tensor cores: A = fragment-major memory (one 16-byte load per lane per
             // MMA), B = (hi(dctx), lo(dctx)) in columns 0 / 1; warp owns position tiles {warp, warp + 8}
             {
@@ -505,18 +534,11 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
 #pragma unroll
                             for (int j = 0; j < KT; ++j)
                                 if (kt0 + j < p.M16) av[j] = __ldg(fr + (size_t)(kt0 + j) * 32);
-                            // B fragments: lanes g = 0 hold hi(dctx), g = 1 hold lo(dctx), other columns zero (branch-free)
                             uint32_t bfr[KT][2];
 #pragma unroll
                             for (int j = 0; j < KT; ++j) {
-                                const int m0 = (kt0 + j) * 16 + 2 * tq;
-                                const float w0 = m0 < M ? s_dctx[m0] : 0.f, w1 = m0 + 1 < M ? s_dctx[m0 + 1] : 0.f;
-                                const float w2 = m0 + 8 < M ? s_dctx[m0 + 8] : 0.f, w3 = m0 + 9 < M ? s_dctx[m0 + 9] : 0.f;
-                                const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
-                                const float h2 = __bfloat162float(__float2bfloat16_rn(w2)), h3 = __bfloat162float(__float2bfloat16_rn(w3));
-                                const float s0 = g == 0 ? h0 : (g == 1 ? w0 - h0 : 0.f), s1 = g == 0 ? h1 : (g == 1 ? w1 - h1 : 0.f);
-                                const float s2 = g == 0 ? h2 : (g == 1 ? w2 - h2 : 0.f), s3 = g == 0 ? h3 : (g == 1 ? w3 - h3 : 0.f);
-                                bfr[j][0] = pack2(s0, s1); bfr[j][1] = pack2(s2, s3);
+                                bfr[j][0] = 0u; bfr[j][1] = 0u;
+                                if (kt0 + j < p.M16) { const uint2 f = s_bf[(kt0 + j) * 32 + lane]; bfr[j][0] = f.x; bfr[j][1] = f.y; }
                             }
 #pragma unroll
                             for (int j = 0; j < KT; j += 2) {        // two independent accumulation chains
@@ -783,7 +805,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                     }
                     const float gi = gi_[e], gf = gf_[e], gg = gg_[e], go = go_[e];
                     const float cp = cp_[e];
-                    const float tc = tanhf(gf * cp + gi * gg);
+                    const float tc = tanh_exp(gf * cp + gi * gg);
                     float dhn, dcn, dc_prev_direct = 0.f, dh_prev_direct = 0.f;
                     if (p.kind == B200TTS_CELL_ZONEOUT) {
                         float kh, kc;
@@ -816,9 +838,10 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 }
             }
         }
-        pb_prefetch(i - 1);
         BPROF_MARK(3);
-        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, TC)) break;
+        // the operands of the next cell backward are fetched between this CTA's arrival and its wait (the compiler parks them in local
+        // memory, i.e. the thread waits for the loads right there: under the barrier that wait is free)
+        if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag, TC, [&]() { pb_prefetch(i - 1); })) break;
         BPROF_MARK(4);
         if (i == 0) break;
 
@@ -850,20 +873,21 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             tcx::mbar_wait(&accum_bar, prod_it & 1);
             tcx::tc_fence_after();
             ++prod_it;
-            {   // M = 64 accumulator layout: utterance b sits in TMEM lane (b / 16) * 32 + b % 16; warp = (quadrant, half of the 80 columns)
+            {   // M = 64 accumulator layout: utterance b sits in TMEM lane (b / 16) * 32 + b % 16; warp = (quadrant, half of the UN = 80 / 96 columns)
+                constexpr int hc = UNC / 2, NJ = hc / 8;
                 const int q = warp & 3, ch = warp >> 2;
-                uint32_t r[5][8];
+                uint32_t r[NJ > 0 ? NJ : 1][8];
 #pragma unroll
-                for (int j = 0; j < 5; ++j) tcx::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 40 + j * 8), r[j]);
+                for (int j = 0; j < NJ; ++j) tcx::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * hc + j * 8), r[j]);
                 tcx::tmem_ld_wait();
                 const int b = q * 16 + lane;
                 if (lane < 16 && b < B) {
-                    float* dst = p.part + ((size_t)kb * B + b) * p.NOUT + n0 + ch * 40;
+                    float* dst = p.part + ((size_t)kb * B + b) * p.NOUT + n0 + ch * hc;
 #pragma unroll
-                    for (int j = 0; j < 5; ++j)
+                    for (int j = 0; j < NJ; ++j)
 #pragma unroll
                         for (int h4 = 0; h4 < 2; ++h4)
-                            if (n0 + ch * 40 + j * 8 + h4 * 4 < p.NOUT)         // NOUT % 4 == 0 (checked on the host)
+                            if (n0 + ch * hc + j * 8 + h4 * 4 < p.NOUT)         // NOUT % 4 == 0 (checked on the host)
                                 *reinterpret_cast<float4*>(dst + j * 8 + h4 * 4) =
                                     make_float4(__uint_as_float(r[j][h4 * 4]), __uint_as_float(r[j][h4 * 4 + 1]), __uint_as_float(r[j][h4 * 4 + 2]),
                                                 __uint_as_float(r[j][h4 * 4 + 3]));
@@ -1205,10 +1229,10 @@ static AttBwdGeom att_bwd_geom(const b200tts_decoder_shape& s, bool tc) {
     const int L16 = (s.L + 15) / 16 * 16;
     const size_t extras = (size_t)s.A * 40 * 2 + (size_t)32 * (s.A + 8) * 2 + (size_t)(L16 + 32) * 4 + (size_t)s.A * 9 * 4;
     if (tc) {
-        g.UN = TUN; g.NBH = 1; g.grid = KBA * NBT;
+        g.UN = (s.M + s.D <= NBT * TUN) ? TUN : TUN_WIDE; g.NBH = 1; g.grid = KBA * NBT;
         const int NKT = 4 * g.UK / 64;
         g.region = (size_t)NKT * 8192;
-        g.smem = 1024 + (size_t)NKT * TUN * 128 + g.region + extras;
+        g.smem = 1024 + (size_t)NKT * g.UN * 128 + g.region + extras;
     } else {
         g.UN = (cdiv(s.M + s.D, NBA) + 15) / 16 * 16; g.NBH = (s.B + BT - 1) / BT; g.grid = KBA * NBA * g.NBH;
         g.region = (size_t)BT * (4 * g.UK + 8) * 2;
@@ -1223,14 +1247,14 @@ static bool att_bwd_variant_ok(const b200tts_decoder_shape& s, const AttBwdGeom&
     if (s.D / 8 > g.grid) return false;                       // cell-backward ownership: 8 hidden units per CTA
     if (g.grid / 2 < s.B || g.grid > 148) return false;       // one CTA pair per utterance, all CTAs co-resident
     if (g.tc) {
-        if (g.UK % 64 != 0 || s.B > 64 || s.M + s.D > NBT * TUN || (s.M + s.D) % 4 != 0) return false;
+        if (g.UK % 64 != 0 || s.B > 64 || s.M + s.D > NBT * g.UN || (s.M + s.D) % 4 != 0) return false;
     } else {
         if (!persist_bwd_supported(s) || s.B > 2 * BT) return false;
     }
     const int MT = (s.L + 15) / 16, L16 = MT * 16, HT0 = (MT + 1) / 2;
     // attention-backward scratch of one CTA of the pair (aliases the activation stage)
     const size_t fl = (size_t)((s.M + 3) & ~3) + 3 * (size_t)L16 + 2 * s.A + 2 * (size_t)(L16 + 48) + 64 + (size_t)(HT0 + 1) * 16 * GLD +
-                      8 * (size_t)s.A + s.A + 4;
+                      8 * (size_t)s.A + s.A + 4 + (size_t)((s.M + 15) / 16) * 32 * 2;
     if (fl * 4 > g.region) return false;
     // the cell-backward phase stages the query gradients [B][A] fp32 + [64][8] products in the (then idle) activation stage
     if ((size_t)s.B * s.A * 4 + 64 * 8 * 4 > g.region) return false;
@@ -1287,7 +1311,8 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     att_bwd_prep_kernel<<<148 * 4, 256, 0, st>>>(wcb, wcb2, memTf, wcombT, fws + fl.memT, B, L, A, s.K, x.MT);
     B200_LAUNCH_CHECK();
     const size_t smem = geo.smem;
-    void* fn = geo.tc ? (void*)att_bwd_loop_kernel<true> : (void*)att_bwd_loop_kernel<false>;
+    void* fn = geo.tc ? (geo.UN == TUN ? (void*)att_bwd_loop_kernel<true, TUN> : (void*)att_bwd_loop_kernel<true, TUN_WIDE>)
+                      : (void*)att_bwd_loop_kernel<false, 0>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = geo.grid;
     int per_sm = 0, dev = 0, sms = 0;

@@ -108,6 +108,8 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// tanh of the recomputed cell state in the reverse loops: the same ex2-based form the forward loops of the bf16 mode use (~1e-6 relative)
+__device__ __forceinline__ float tanh_exp(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 // thread-block cluster (CTA pair) primitives: split arrive / wait barrier and a distributed-shared-memory store
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_tc_kernel(const __grid_co
                         dc_in = dc_reg[e];
                     }
                     const float gi = gi_[e], gf = gf_[e], gg = gg_[e], go = go_[e], cp = cp_[e];
-                    const float tc = tanhf(gf * cp + gi * gg);
+                    const float tc = tanh_exp(gf * cp + gi * gg);
                     float dhn, dcn, dc_prev_direct = 0.f, dh_prev_direct = 0.f;
                     if (p.kind == B200TTS_CELL_ZONEOUT) {
                         float kh, kc;

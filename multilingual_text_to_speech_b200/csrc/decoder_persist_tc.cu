@@ -41,7 +41,8 @@ constexpr int TMEM_COLS = 32;
 struct TcLoopArgs {
     int B, T, D, K, Kp, RB, NBH;
     int nkb, nkb_h;                           // k-blocks in total / in the h part
-    int ch_h, n_h, ch_c, slot_kb;             // TMA chunking: n_h instructions of ch_h k-blocks (h part), one of ch_c (ctx part); slot capacity
+    int ch_h, n_h, ch_c, n_c, slot_kb;        // TMA chunking: n_h instructions of ch_h k-blocks (h part), n_c of ch_c (ctx part); slot capacity
+    int alias_sum;                            // 1: the accumulator staging s_sum lives in the (then idle) TMA slot (large memory dims)
     const float* W; int ldw; int wcol_h, wcol_c;   // fp32 weights [4D, ldw]: operand column k < D -> wcol_h + k, else wcol_c + k - D
     __nv_bfloat16* actb;                      // [T+1, B, Kp] bf16 operand rows: [h | ctx | 0]
     float* actf; int ldf; int hcol;           // fp32 mirror ([T+1, B, ldf]); h at column hcol, ctx at column 0
@@ -202,12 +203,19 @@ __device__ __forceinline__ float cblock_sum(float v, float* scratch) {
 // Monotonic-counter grid barrier over ALL threads of every CTA.  Returns false if the watchdog fired.
 // Arrival is ONE release-reduction (cumulative: it orders the whole CTA's writes, which the preceding __syncthreads made
 // visible to thread 0); the wait polls with relaxed loads and issues a single acquire fence after the last one.
-__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag, int* s_ok) {
+struct NoOverlap { __device__ __forceinline__ void operator()() const {} };
+// `overlap` runs on every thread BETWEEN the CTA's arrival and its wait: work that does not depend on other CTAs (next step's operand
+// prefetch) hides under the barrier latency instead of delaying the arrival
+template <typename Overlap = NoOverlap>
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks, int* abort_flag, int* s_ok, Overlap overlap = Overlap()) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += nblocks;
         proxy_fence_global();          // the bf16 operand rows written above are read by other CTAs through TMA (async proxy)
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
+    overlap();
+    if (threadIdx.x == 0) {
         int ok = 1;
         const long long t0 = clock64();
         unsigned polls = 0;
@@ -226,7 +234,9 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& target
     return *s_ok != 0;
 }
 
-template <bool ATT>
+// ALIAS (large memory dims only): the accumulator staging lives in the TMA slot and the ctx part arrives in p.n_c TMA instructions; the
+// common instantiation keeps both compile-time constant (this kernel sits at its register cap: every live value counts)
+template <bool ATT, bool ALIAS>
 __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmC,
                                                              const TcLoopArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
@@ -254,10 +264,17 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     // ---- shared memory carve-up (1024-byte aligned base: SWIZZLE_128B atoms) ----
     size_t off = 0;
     unsigned char* sW = smem_raw + off; off += (size_t)p.nkb * WTILE;                 // [nkb][64 rows][128 B] swizzled
-    unsigned char* ring = smem_raw + off; off += (size_t)p.slot_kb * ATILE;           // one slot of [slot_kb][32 rows][128 B] swizzled (TMA)
-    float* s_sum = reinterpret_cast<float*>(smem_raw + off); off += (size_t)BT * (ROWS + 1) * 4;
+    unsigned char* ring = smem_raw + off;                                             // one slot of [slot_kb][32 rows][128 B] swizzled (TMA)
+    {
+        const size_t ring_b = (size_t)p.slot_kb * ATILE, sum_b = (size_t)BT * (ROWS + 1) * 4;
+        off += ALIAS ? (ring_b > sum_b ? ring_b : sum_b) : ring_b;
+    }
+    // accumulator staging [32 utterances][64 gate rows + 1]: its own buffer, or (large memory dims, where the resident weight slice leaves no
+    // room) the TMA slot itself -- between the commit of a step's last MMA and the next TMA issue nobody else touches the slot
+    float* s_sum = ALIAS ? reinterpret_cast<float*>(ring) : reinterpret_cast<float*>(smem_raw + off);
+    off += ALIAS ? 0 : (size_t)BT * (ROWS + 1) * 4;
     float* s_hs = reinterpret_cast<float*>(smem_raw + off); off += ATT ? (size_t)UNITS * (BT + 4) * 4 : 0;
-    __nv_bfloat16* sWcB = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += ATT ? (size_t)p.A * 40 * 2 : 0;
+    __nv_bfloat16* sWcB = reinterpret_cast<__nv_bfloat16*>(smem_raw + off); off += ATT ? (size_t)(p.A / 2) * 40 * 2 : 0;   // this rank's 64 attention dims
     float* scratch = reinterpret_cast<float*>(smem_raw + off);                        // attention scratch (ATT only)
 
     // ---- one-time: resident weight slice fp32 -> bf16 in the canonical K-major SWIZZLE_128B layout ----
@@ -270,7 +287,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         *reinterpret_cast<__nv_bfloat16*>(sW + (size_t)kb * WTILE + r * 128 + ((chunk ^ (r & 7)) << 4) + e * 2) = __float2bfloat16_rn(w);
     }
     if (ATT) {
-        for (int idx = tid; idx < p.A * 40; idx += PT) sWcB[idx] = p.WcB[idx];
+        for (int idx = tid; idx < (p.A / 2) * 40; idx += PT) sWcB[idx] = p.WcB[(size_t)(cta & 1) * (p.A / 2) * 40 + idx];
     }
     if (tid == 0) {
         mbar_init(&full_bar, 1); mbar_init(&empty_bar, 1);
@@ -299,12 +316,13 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         const long long t0 = clock64();
         proxy_fence_global();          // generic-proxy writes of other CTAs (ordered by the grid barrier) -> async-proxy reads
         const long long t1 = clock64();
-        const int n = part ? p.n_h : 1, ch = part ? p.ch_h : p.ch_c;
+        const int n = part ? p.n_h : (ALIAS ? p.n_c : 1), ch = part ? p.ch_h : p.ch_c;
         for (int j = 0; j < n; ++j) {
             mbar_wait(&empty_bar, (prod_it & 1) ^ 1);
             if (elect_one()) {
+                if (ALIAS) proxy_fence_shared();           // the slot doubled as the accumulator staging (generic proxy) since its last MMA
                 mbar_expect_tx(&full_bar, (uint32_t)ch * ATILE);
-                tma_load_3d(ring, part ? &tmH : &tmC, &full_bar, 0, step * B + b0, part ? j * ch : p.nkb_h);
+                tma_load_3d(ring, part ? &tmH : &tmC, &full_bar, 0, step * B + b0, part ? j * ch : p.nkb_h + j * ch);
             }
             __syncwarp();
             ++prod_it;
@@ -315,12 +333,12 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     auto consume = [&](int part, bool signal_accum) {
         const long long t0 = clock64();
         long long t1 = t0;
-        const int n = part ? p.n_h : 1, ch = part ? p.ch_h : p.ch_c;
+        const int n = part ? p.n_h : (ALIAS ? p.n_c : 1), ch = part ? p.ch_h : p.ch_c;
         for (int j = 0; j < n; ++j) {
             mbar_wait(&full_bar, cons_it & 1);
             if (j == 0) t1 = clock64();
             tc_fence_after();
-            const int kb0 = part ? j * ch : p.nkb_h;
+            const int kb0 = part ? j * ch : p.nkb_h + j * ch;
             if (elect_one()) {
                 for (int c = 0; c < ch; ++c) {
                     const uint64_t adesc = make_sw128_desc(smem_u32(sW + (size_t)(kb0 + c) * WTILE));
@@ -515,6 +533,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             }
         }
         PROF_MARK(1);
+        if (ALIAS) proxy_fence_shared();             // generic-proxy accesses of the staging precede the TMA writes that follow the barrier
         if (!grid_barrier(bar_counter, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
         PROF_MARK(2);
 
@@ -638,7 +657,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                             for (int np = 0; np < 2; ++np) {
                                 uint32_t bfr[4];
                                 ldmatrix_x4(bfr[0], bfr[1], bfr[2], bfr[3],
-                                            sWcB + (size_t)((hf * 4 + qh * 2 + np) * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
+                                            sWcB + (size_t)((qh * 2 + np) * 16 + (lane & 7) + ((lane >> 4) << 3)) * 40 + ks * 16 + ((lane >> 3) & 1) * 8);
                                 mma_bf16(sacc[2 * np], ah, bfr[0], bfr[1]);
                                 mma_bf16(sacc[2 * np], al, bfr[0], bfr[1]);
                                 mma_bf16(sacc[2 * np + 1], ah, bfr[2], bfr[3]);
@@ -760,9 +779,11 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
             } else {
                 cluster_wait();            // role warps: arrived before their TMA / MMA work (below the cell barrier)
             }
-            if (compute && i + 1 < p.T) prefetch(i + 1, false);      // L2 hits (prefetched a step ago); they land behind the barrier wait
             PROF_MARK(6);
-            if (!grid_barrier(bar_counter, target, nblocks, p.abort_flag, &s_ok)) { alive = false; break; }
+            // next step's epilogue operands (L2 hits: prefetched a step ago) are requested between the arrival and the wait
+            if (!grid_barrier(bar_counter, target, nblocks, p.abort_flag, &s_ok, [&]() { if (compute && i + 1 < p.T) prefetch(i + 1, false); })) {
+                alive = false; break;
+            }
             PROF_MARK(7);
         }
     }
@@ -778,12 +799,13 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     }
 }
 
-// shared memory of one loop CTA with a ring slot of slot_kb k-blocks
-size_t tc_loop_smem_bytes(int nkb, int slot_kb, int A, bool att, int L) {
-    size_t b = 1024 + (size_t)nkb * WTILE + (size_t)slot_kb * ATILE + (size_t)BT * (ROWS + 1) * 4;
+// shared memory of one loop CTA with a ring slot of slot_kb k-blocks; alias: the accumulator staging shares the slot
+size_t tc_loop_smem_bytes(int nkb, int slot_kb, int A, bool att, int L, bool alias = false) {
+    const size_t ring_b = (size_t)slot_kb * ATILE, sum_b = (size_t)BT * (ROWS + 1) * 4;
+    size_t b = 1024 + (size_t)nkb * WTILE + (alias ? (ring_b > sum_b ? ring_b : sum_b) : ring_b + sum_b);
     if (att) {
         const int L16 = (L + 15) / 16 * 16;
-        b += (size_t)UNITS * (BT + 4) * 4 + (size_t)A * 40 * 2;
+        b += (size_t)UNITS * (BT + 4) * 4 + (size_t)(A / 2) * 40 * 2;
         b += ((size_t)3 * (A / 2) + 6 * L16 + 64 + 16 * (A / 2) + 2 * (L16 + 48)) * 4;
     }
     return b;
@@ -791,9 +813,9 @@ size_t tc_loop_smem_bytes(int nkb, int slot_kb, int A, bool att, int L) {
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 1088;    // leave room for the static barriers (1 KB of static shared memory)
 
 // largest ring slot (in k-blocks, <= want) that fits
-int pick_slot(int nkb, int A, bool att, int L, int want) {
+int pick_slot(int nkb, int A, bool att, int L, int want, bool alias = false) {
     int kb = want;
-    while (kb >= 1 && tc_loop_smem_bytes(nkb, kb, A, att, L) > SMEM_LIMIT) --kb;
+    while (kb >= 1 && tc_loop_smem_bytes(nkb, kb, A, att, L, alias) > SMEM_LIMIT) --kb;
     return kb;
 }
 int largest_divisor_le(int n, int cap) {
@@ -812,8 +834,15 @@ TcPersistGeom tc_persist_geom(const b200tts_decoder_shape& s) {
     g.nkb_h = s.D / KB;
     g.Kp_att = g.nkb_att * KB;
     g.Kp_gen = g.nkb_gen * KB;
-    g.ch_c_att = g.nkb_att - g.nkb_h;
+    const int nkb_c = g.nkb_att - g.nkb_h;
+    g.alias_att = 0;
     g.slot_att = pick_slot(g.nkb_att, s.A, true, s.L, g.nkb_h);
+    if (g.slot_att < nkb_c) {           // large memory dims (M = 512: 192 KB of resident weights): the accumulator staging moves into the slot
+        g.alias_att = 1;                // and the ctx part arrives in several TMA instructions
+        g.slot_att = pick_slot(g.nkb_att, s.A, true, s.L, g.nkb_h, true);
+    }
+    g.ch_c_att = g.slot_att >= 1 ? largest_divisor_le(nkb_c, g.slot_att) : 0;
+    g.n_c_att = g.ch_c_att >= 1 ? nkb_c / g.ch_c_att : 0;
     g.ch_h_att = g.slot_att >= 1 ? largest_divisor_le(g.nkb_h, g.slot_att) : 0;
     g.slot_gen = pick_slot(g.nkb_gen, s.A, false, 0, g.nkb_gen);
     g.ch_h_gen = g.slot_gen >= 1 ? largest_divisor_le(g.nkb_gen, g.slot_gen) : 0;
@@ -826,11 +855,11 @@ bool tc_persist_supported(const b200tts_decoder_shape& s) {
     if (RB * NBH > 148 || s.B > RB * NBH) return false;
     if (s.K > 32 || s.A != 128) return false;
     const TcPersistGeom g = tc_persist_geom(s);
-    return g.ch_c_att >= 1 && g.ch_c_att <= 256 && g.slot_att >= g.ch_c_att && g.ch_h_att >= 1 && g.ch_h_gen >= 1;
+    return g.ch_c_att >= 1 && g.ch_c_att <= 256 && g.slot_att >= g.ch_c_att && g.ch_h_att >= 1 && g.ch_h_gen >= 1 && g.slot_att >= 2;
 }
 
 static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tmH, const CUtensorMap& tmC, size_t smem, cudaStream_t st) {
-    void* fn = att ? (void*)lstm_loop_tc_kernel<true> : (void*)lstm_loop_tc_kernel<false>;
+    void* fn = att ? (a.alias_sum ? (void*)lstm_loop_tc_kernel<true, true> : (void*)lstm_loop_tc_kernel<true, false>) : (void*)lstm_loop_tc_kernel<false, false>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.RB * a.NBH;
     TcLoopArgs args = a;
@@ -882,7 +911,8 @@ int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     B200_TRY(tc_make_map3_bf16(&tmC, aib, KB, (T + 1) * B, g.nkb_att, (size_t)g.Kp_att * 2, 128, KB, BT, g.ch_c_att));
     TcLoopArgs a{};
     a.B = B; a.T = T; a.D = D; a.K = MD; a.Kp = g.Kp_att; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
-    a.nkb = g.nkb_att; a.nkb_h = g.nkb_h; a.ch_h = g.ch_h_att; a.n_h = g.nkb_h / g.ch_h_att; a.ch_c = g.ch_c_att;
+    a.nkb = g.nkb_att; a.nkb_h = g.nkb_h; a.ch_h = g.ch_h_att; a.n_h = g.nkb_h / g.ch_h_att; a.ch_c = g.ch_c_att; a.n_c = g.n_c_att;
+    a.alias_sum = g.alias_att;
     a.slot_kb = g.ch_h_att > g.ch_c_att ? g.ch_h_att : g.ch_c_att;
     a.W = ws + fl.wcat_att; a.ldw = MD; a.wcol_h = M; a.wcol_c = 0;
     a.actb = aib; a.actf = ws + fl.ai; a.ldf = MD; a.hcol = M;
@@ -899,7 +929,7 @@ int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
     a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256);
     a.prof2 = a.prof + 2 * 148 * 8;
-    return launch_tc_loop(true, a, tmH, tmC, tc_loop_smem_bytes(g.nkb_att, a.slot_kb, s.A, true, s.L), st);
+    return launch_tc_loop(true, a, tmH, tmC, tc_loop_smem_bytes(g.nkb_att, a.slot_kb, s.A, true, s.L, g.alias_att != 0), st);
 }
 
 // Generator-LSTM loop.  Expects: gg = input projection, hg row 0 = 0, cg row 0 = 0.
@@ -916,7 +946,7 @@ int tc_persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     B200_TRY(tc_make_map3_bf16(&tmH, hgb, KB, (T + 1) * B, g.nkb_gen, (size_t)g.Kp_gen * 2, 128, KB, BT, g.ch_h_gen));
     TcLoopArgs a{};
     a.B = B; a.T = T; a.D = D; a.K = D; a.Kp = g.Kp_gen; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
-    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.ch_h = g.ch_h_gen; a.n_h = g.nkb_gen / g.ch_h_gen; a.ch_c = 0; a.slot_kb = g.ch_h_gen;
+    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.ch_h = g.ch_h_gen; a.n_h = g.nkb_gen / g.ch_h_gen; a.ch_c = 0; a.n_c = 0; a.alias_sum = 0; a.slot_kb = g.ch_h_gen;
     a.W = w.gen_w_hh; a.ldw = D; a.wcol_h = 0; a.wcol_c = 0;
     a.actb = hgb; a.actf = ws + fl.hg; a.ldf = D; a.hcol = 0;
     a.gates = ws + fl.gg; a.cstate = ws + fl.cg;

@@ -247,7 +247,7 @@ class DecoderFunction(torch.autograd.Function):
         bws = torch.empty(nbytes, dtype=torch.uint8, device=memory.device)
         if PROFILE.get('keep_ws'):
             PROFILE['last_bws'] = bws
-        grads = [torch.zeros_like(p) for p in params]
+        grads, returned = _grad_targets(params)
         gstruct = DecoderParams(*[ptr(g) for g in grads])
         d_memory = torch.empty_like(memory) if ctx.needs_input_grad[1] else None
         d_spec, d_stop, d_align = [None if t is None else _f32c(t) for t in (d_spec, d_stop, d_align)]
@@ -257,7 +257,7 @@ class DecoderFunction(torch.autograd.Function):
             check(lib.b200tts_decoder_backward(ctypes.byref(shape), ctypes.byref(pstruct), ctypes.byref(inputs),
                                                ctypes.byref(fouts), ctypes.byref(douts), ptr(ctx.ws), ptr(bws), nbytes,
                                                ctypes.byref(gstruct), ptr(d_memory), _stream()), 'b200tts_decoder_backward')
-        return (None, d_memory, None, None, *grads)
+        return (None, d_memory, None, None, *returned)
 
 
 class DecoderState:
@@ -383,27 +383,26 @@ class ConvBlockFunction(torch.autograd.Function):
         ws = _bytes(lib.b200tts_convblock_workspace_bytes(ctypes.byref(shape)), x.device)
         dout = _f32c(dout)
         dx = torch.empty_like(x)
-        dweight = torch.zeros_like(weight) if weight is not None else None
+        (dweight,), (r_weight,) = _grad_targets((weight,))           # leaf convolution weights accumulate straight into .grad
         # gamma / beta may be strided views of one generated-affine tensor: produce gradients in the same geometry
         G, Cout, gs = shape.G, shape.Cout, ctx.gstride
         if shape.stage == 1:    # convolution only: no affine parameters
             check(lib.b200tts_convblock_backward(ctypes.byref(shape), ptr(x), ptr(weight), None, None, gs, None, ptr(ctx.saved_buf), ptr(dout),
                                                  ptr(dx), ptr(dweight), None, None, ptr(ws), _stream()), 'b200tts_convblock_backward')
-            return dx, dweight, None, None, None, None, None, None
-        dgb = torch.zeros(2 * G * Cout, device=x.device, dtype=torch.float32)
-        if gs == Cout:      # plain batch norm: separate dense gamma / beta
-            dgamma, dbeta = dgb[:G * Cout], dgb[G * Cout:]
+            return dx, r_weight, None, None, None, None, None, None
+        if gs == Cout:      # plain batch norm: separate dense gamma / beta (leaf parameters accumulate straight into .grad)
+            (dgamma, dbeta), (g_gamma, g_beta) = _grad_targets((gamma, beta))
+            dgb = None
         else:               # generated affine [G, 2*Cout]: gamma = [:, :Cout], beta = [:, Cout:]
+            dgb = torch.zeros(2 * G * Cout, device=x.device, dtype=torch.float32)
             dgamma, dbeta = dgb, dgb[Cout:]
         check(lib.b200tts_convblock_backward(ctypes.byref(shape), ptr(x), ptr(weight), ptr(gamma), ptr(beta), gs, ptr(ctx.keep),
                                              ptr(ctx.saved_buf), ptr(dout), ptr(dx), ptr(dweight), ptr(dgamma), ptr(dbeta),
                                              ptr(ws), _stream()), 'b200tts_convblock_backward')
-        if gs == Cout:
-            g_gamma, g_beta = dgamma.view_as(gamma), dbeta.view_as(beta)
-        else:
+        if dgb is not None:
             full = dgb.view(G, gs)
             g_gamma, g_beta = full[:, :Cout], full[:, Cout:]
-        return dx, dweight, g_gamma, g_beta, None, None, None, None
+        return dx, r_weight, g_gamma, g_beta, None, None, None, None
 
 
 def conv_block(x, weight, gamma, beta, running_mean, running_var, keep, groups, kernel, dilation, activation, highway,
@@ -466,22 +465,38 @@ class GeneratorFunction(torch.autograd.Function):
         out = torch.empty(G, R, device=e.device, dtype=torch.float32)
         check(_lib.load().b200tts_generator_forward(G, gd, bn, R, ptr(e), ptr(Wb), ptr(bb), ptr(Wk), ptr(bk), ptr(eb), ptr(out),
                                                     _stream()), 'b200tts_generator_forward')
-        ctx.save_for_backward(e, Wb, Wk, eb)
+        ctx.save_for_backward(e, Wb, Wk, eb, bb, bk)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        e, Wb, Wk, eb = ctx.saved_tensors
+        e, Wb, Wk, eb, bb, bk = ctx.saved_tensors
         G, gd = e.shape
         bn, R = Wb.shape[0], Wk.shape[0]
         lib = _lib.load()
         dout = _f32c(dout)
-        de, dWb, dWk = torch.zeros_like(e), torch.zeros_like(Wb), torch.zeros_like(Wk)
-        dbb = torch.zeros(bn, device=e.device); dbk = torch.zeros(R, device=e.device)
+        (de, dWb, dbb, dWk, dbk), returned = _grad_targets((e, Wb, bb, Wk, bk))       # all accumulated (+=) by the library
         ws = _bytes(lib.b200tts_generator_workspace_bytes(G, bn), e.device)
         check(lib.b200tts_generator_backward(G, gd, bn, R, ptr(e), ptr(Wb), ptr(Wk), ptr(eb), ptr(dout), ptr(de), ptr(dWb),
                                              ptr(dbb), ptr(dWk), ptr(dbk), ptr(ws), _stream()), 'b200tts_generator_backward')
-        return de, dWb, dbb, dWk, dbk
+        return tuple(returned)
+
+
+def _grad_targets(params):
+    """Where the library accumulates (+=) the gradients of `params` (the saved inputs of a Function).  A leaf parameter whose `.grad` already
+    exists as a dense fp32 tensor of its own shape (the flat gradient bucket of distributed.GradBucket binds such views) is accumulated INTO
+    directly and reported to autograd as None: no zero-filled temporary, no AccumulateGrad add per parameter (~2 launches and 3x the
+    parameter bytes per tensor and step).  Everything else gets a fresh zero tensor that autograd accumulates as usual.
+    -> (targets, returned)"""
+    targets, returned = [], []
+    for q in params:
+        g = q.grad if (q is not None and q.is_leaf and q.requires_grad) else None
+        if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == q.shape and g.device == q.device:
+            targets.append(g); returned.append(None)
+        else:
+            t = None if q is None else torch.zeros_like(q, dtype=torch.float32)
+            targets.append(t); returned.append(t)
+    return targets, returned
 
 
 class EmbeddingFunction(torch.autograd.Function):
@@ -497,6 +512,7 @@ class EmbeddingFunction(torch.autograd.Function):
         check(_lib.load().b200tts_embedding_forward(ptr(out), E, ptr(table), ptr(ids32), ids32.numel(), E, _stream()),
               'b200tts_embedding_forward')
         ctx.save_for_backward(ids32)
+        ctx.table_ref = table          # the parameter itself (not saved for its values): its .grad may be the accumulation target
         ctx.V, ctx.E, ctx.padding_idx = table.shape[0], E, -1 if padding_idx is None else int(padding_idx)
         return out
 
@@ -504,10 +520,14 @@ class EmbeddingFunction(torch.autograd.Function):
     def backward(ctx, dout):
         (ids32,) = ctx.saved_tensors
         dout = _f32c(dout)
-        dtable = torch.zeros(ctx.V, ctx.E, device=dout.device, dtype=torch.float32)
+        table = ctx.table_ref
+        if table is not None and table.dtype == torch.float32 and table.is_contiguous():
+            (dtable,), (ret,) = _grad_targets((table,))
+        else:
+            dtable = ret = torch.zeros(ctx.V, ctx.E, device=dout.device, dtype=torch.float32)
         check(_lib.load().b200tts_embedding_backward(ptr(dtable), ctx.V, ptr(dout), ctx.E, ptr(ids32), ids32.numel(), ctx.E,
                                                      ctx.padding_idx, _stream()), 'b200tts_embedding_backward')
-        return dtable, None, None
+        return ret, None, None
 
 
 def embedding(table, ids, padding_idx=None):
@@ -545,12 +565,12 @@ class BiLSTMFunction(torch.autograd.Function):
         dout = _f32c(dout)
         ws = _bytes(lib.b200tts_bilstm_workspace_bytes(ctypes.byref(shape)), dout.device)
         dx = torch.empty(shape.B, shape.L, shape.E, device=dout.device, dtype=torch.float32)
-        grads = [torch.zeros_like(p) for p in params]
+        grads, returned = _grad_targets(params)
         pstruct = _lib.BiLSTMParams(*[ptr(p) for p in params])
         gstruct = _lib.BiLSTMParams(*[ptr(g) for g in grads])
         check(lib.b200tts_bilstm_backward(ctypes.byref(shape), ctypes.byref(pstruct), ptr(lengths32), ptr(ctx.saved_buf), ptr(dout),
                                           ptr(dx), ctypes.byref(gstruct), ptr(ws), _stream()), 'b200tts_bilstm_backward')
-        return (dx, None, *grads)
+        return (dx, None, *returned)
 
 
 def bilstm(x, lengths, params):

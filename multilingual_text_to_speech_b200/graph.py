@@ -19,6 +19,22 @@ import torch
 from . import _lib
 
 
+_CAPTURE_STREAMS = {}
+
+
+def capture_stream(device):
+    """THE side stream (one per device, shared by every GraphedTrainStep) that warm-ups and captures run on.  autograd binds a parameter's
+    AccumulateGrad node to the stream the parameter was first used on and keeps it for the life of the parameter; capturing on any other
+    stream makes that node a cross-stream consumer, which CUDA rejects (cudaErrorStreamCaptureIsolation) as soon as one backward sends it
+    no gradient -- and the library accumulates most gradients in place (functional._grad_targets).  So: one stream for all captures, and
+    eager steps that precede the first capture should run under `torch.cuda.stream(capture_stream(device))` as well."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _CAPTURE_STREAMS[key]
+
+
 class GraphedTrainStep:
     FIELDS = ('text', 'text_length', 'target', 'target_length', 'stop_target', 'speakers', 'languages')
 
@@ -29,15 +45,18 @@ class GraphedTrainStep:
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.check(_lib.load().b200tts_set_mask_epoch(ctypes.c_void_p(self.epoch.data_ptr())), 'b200tts_set_mask_epoch')
         self.loss, self.parts = None, None
-        side = torch.cuda.Stream(device=dev)
+        side = capture_stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up on a side stream (workspaces, lazy attribute settings, pack caches)
             for _ in range(warmup):
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # capture on the SAME side stream the warm-up ran on: autograd's AccumulateGrad nodes are bound to the stream their parameter was first
+        # used on, and the engine joins every such "leaf stream" at the end of backward -- a leaf stream that is not the capture stream would
+        # be a dependency on uncaptured work as soon as a step sends it no gradient (the library accumulates most gradients in place)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self._body()
         torch.cuda.synchronize(dev)
 

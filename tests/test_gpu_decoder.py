@@ -142,6 +142,11 @@ def test_gemm_bf16_mode(M, N, K, ta, tb, splitk):
     dict(B=12, L=300, T=12, kind='zoneout', seed=7),            # BASELINE configs[4]: texts up to 300 on the persistent kernels
     dict(B=80, L=50, T=10, kind='dropout', seed=8),             # B > 64 (configs[3..4] run 65 / 80 per GPU): decoded as two slices
     dict(B=65, L=44, T=9, M=292, kind='zoneout', seed=9),
+    # memory dim 512 (monolingual default, BASELINE configs[0]): accumulator staging aliased onto the TMA slot, ctx part in several TMA
+    # instructions (forward), UMMA N = 96 n-blocks (attention reverse product)
+    dict(B=16, L=60, T=14, M=512, kind='zoneout', seed=10),
+    dict(B=52, L=300, T=8, M=512, kind='dropout', seed=11),
+    dict(B=9, L=37, T=11, M=384, kind='dropout', seed=12),
 ])
 def test_decoder_bf16_perf_mode(kw):
     """Persistent weight-stationary bf16 kernels (decoder_persist.cu) + bf16 tensor-core GEMMs."""
