@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                                                              const TcLoopArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw0) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar, empty_bar, accum_bar;
+    __shared__ uint64_t full_bar, full2_bar, empty_bar, accum_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_ok;
 
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         for (int idx = tid; idx < (p.A / 2) * 40; idx += PT) sWcB[idx] = p.WcB[(size_t)(cta & 1) * (p.A / 2) * 40 + idx];
     }
     if (tid == 0) {
-        mbar_init(&full_bar, 1); mbar_init(&empty_bar, 1);
+        mbar_init(&full_bar, 1); mbar_init(&full2_bar, 1); mbar_init(&empty_bar, 1);
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -317,6 +317,22 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         proxy_fence_global();          // generic-proxy writes of other CTAs (ordered by the grid barrier) -> async-proxy reads
         const long long t1 = clock64();
         const int n = part ? p.n_h : (ALIAS ? p.n_c : 1), ch = part ? p.ch_h : p.ch_c;
+        if (!ATT) {
+            // generator loop: the whole operand fits in the ring, so its (<= 2) chunks go to their own offsets with their own barriers and
+            // are requested back to back -- the MMAs of the first half run while the second half is still in flight.  (All slots are free
+            // here: the previous step's MMAs completed before its cell phase, and the grid barrier lies in between.)
+            if (elect_one()) {
+                for (int j = 0; j < n; ++j) {
+                    uint64_t* fb = j ? &full2_bar : &full_bar;
+                    mbar_expect_tx(fb, (uint32_t)ch * ATILE);
+                    tma_load_3d(ring + (size_t)j * ch * ATILE, &tmH, fb, 0, step * B + b0, j * ch);
+                }
+            }
+            __syncwarp();
+            ++prod_it;
+            rp[2 * part] += t1 - t0; rp[2 * part + 1] += clock64() - t1;
+            return;
+        }
         for (int j = 0; j < n; ++j) {
             mbar_wait(&empty_bar, (prod_it & 1) ^ 1);
             if (elect_one()) {
@@ -334,6 +350,26 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         const long long t0 = clock64();
         long long t1 = t0;
         const int n = part ? p.n_h : (ALIAS ? p.n_c : 1), ch = part ? p.ch_h : p.ch_c;
+        if (!ATT) {
+            for (int j = 0; j < n; ++j) {
+                mbar_wait(j ? &full2_bar : &full_bar, cons_it & 1);
+                if (j == 0) t1 = clock64();
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int c = 0; c < ch; ++c) {
+                        const uint64_t adesc = make_sw128_desc(smem_u32(sW + (size_t)(j * ch + c) * WTILE));
+                        const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)(j * ch + c) * ATILE));
+#pragma unroll
+                        for (int k = 0; k < KB / 16; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (j == 0 && c == 0 && k == 0) ? 0u : 1u);
+                    }
+                    if (j == n - 1) umma_commit(&accum_bar);
+                }
+                __syncwarp();
+            }
+            ++cons_it;
+            rp[2 * part] += t1 - t0; rp[2 * part + 1] += clock64() - t1;
+            return;
+        }
         for (int j = 0; j < n; ++j) {
             mbar_wait(&full_bar, cons_it & 1);
             if (j == 0) t1 = clock64();
@@ -846,6 +882,8 @@ TcPersistGeom tc_persist_geom(const b200tts_decoder_shape& s) {
     g.ch_h_att = g.slot_att >= 1 ? largest_divisor_le(g.nkb_h, g.slot_att) : 0;
     g.slot_gen = pick_slot(g.nkb_gen, s.A, false, 0, g.nkb_gen);
     g.ch_h_gen = g.slot_gen >= 1 ? largest_divisor_le(g.nkb_gen, g.slot_gen) : 0;
+    // the generator loop requests its operand in (at most) two chunks with separate barriers; it needs the whole operand in the ring
+    if (g.slot_gen >= g.nkb_gen && g.nkb_gen % 2 == 0) g.ch_h_gen = g.nkb_gen / 2;
     return g;
 }
 
@@ -855,7 +893,8 @@ bool tc_persist_supported(const b200tts_decoder_shape& s) {
     if (RB * NBH > 148 || s.B > RB * NBH) return false;
     if (s.K > 32 || s.A != 128) return false;
     const TcPersistGeom g = tc_persist_geom(s);
-    return g.ch_c_att >= 1 && g.ch_c_att <= 256 && g.slot_att >= g.ch_c_att && g.ch_h_att >= 1 && g.ch_h_gen >= 1 && g.slot_att >= 2;
+    return g.ch_c_att >= 1 && g.ch_c_att <= 256 && g.slot_att >= g.ch_c_att && g.ch_h_att >= 1 && g.ch_h_gen >= 1 && g.slot_att >= 2 &&
+           g.slot_gen >= g.nkb_gen;          // generator loop: the whole operand row block is ring resident
 }
 
 static int launch_tc_loop(bool att, const TcLoopArgs& a, const CUtensorMap& tmH, const CUtensorMap& tmC, size_t smem, cudaStream_t st) {
@@ -946,7 +985,7 @@ int tc_persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     B200_TRY(tc_make_map3_bf16(&tmH, hgb, KB, (T + 1) * B, g.nkb_gen, (size_t)g.Kp_gen * 2, 128, KB, BT, g.ch_h_gen));
     TcLoopArgs a{};
     a.B = B; a.T = T; a.D = D; a.K = D; a.Kp = g.Kp_gen; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
-    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.ch_h = g.ch_h_gen; a.n_h = g.nkb_gen / g.ch_h_gen; a.ch_c = 0; a.n_c = 0; a.alias_sum = 0; a.slot_kb = g.ch_h_gen;
+    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.ch_h = g.ch_h_gen; a.n_h = g.nkb_gen / g.ch_h_gen; a.ch_c = 0; a.n_c = 0; a.alias_sum = 0; a.slot_kb = g.nkb_gen;
     a.W = w.gen_w_hh; a.ldw = D; a.wcol_h = 0; a.wcol_c = 0;
     a.actb = hgb; a.actf = ws + fl.hg; a.ldf = D; a.hcol = 0;
     a.gates = ws + fl.gg; a.cstate = ws + fl.cg;

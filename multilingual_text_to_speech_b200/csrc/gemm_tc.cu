@@ -97,6 +97,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major, 128-byte swizzled operand tile: 64-element (128 B) lines along MN, one line per k row, 8-row groups 1024 B apart (stride
+// byte offset), the next 64-element MN chunk 8 KB further (leading byte offset); a K = 16 instruction step advances 16 rows = 2048 B
+// (canonical layout Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, cute::UMMA::make_umma_desc<Major::MN>)
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(8192 >> 4) << 16;       // leading byte offset: next 64-wide MN chunk
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: next group of 8 k rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 struct TcArgs {
     float* C; const float* bias;
     int M, N, K, ldc;
@@ -111,6 +124,10 @@ struct TcArgs {
     // tile into partial[z][M][N]; a fixed-order reduction kernel applies alpha / beta / bias afterwards
     int ksplit, kper;
     float* partial;
+    // MN-major operands (batch == 1): the bf16 source is [K rows][MN columns] row-major (the natural layout of op(A) = A^T / op(B) = B of a
+    // weight-gradient product), fetched as two 64-column chunks of 64 k-rows per stage (3-D map {64, K, MN / 64}, box {64, 64, 2}) and
+    // described to the tensor core as MN-major SWIZZLE_128B tiles: no transposing pack
+    int a_mn, b_mn;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -151,8 +168,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 uint8_t* sa = ring + (size_t)s * STAGE_BYTES;
-                tma_load_3d(sa, &tmA, &full_bar[s], (kb_lo + kb) * TBK, m0, az);
-                if (p.conv_cb > 0) {
+                if (p.a_mn) tma_load_3d(sa, &tmA, &full_bar[s], 0, (kb_lo + kb) * TBK, m0 >> 6);
+                else tma_load_3d(sa, &tmA, &full_bar[s], (kb_lo + kb) * TBK, m0, az);
+                if (p.b_mn) {
+                    tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], 0, (kb_lo + kb) * TBK, n0 >> 6);
+                } else if (p.conv_cb > 0) {
                     const int t = (kb_lo + kb) / p.conv_cb, cb = (kb_lo + kb) % p.conv_cb;
                     tma_load_3d(sa + TBM * TBK * 2, &tmB, &full_bar[s], (bz % p.conv_G) * p.conv_cin + cb * TBK, n0 + t * p.conv_dil - p.conv_pad,
                                 bz / p.conv_G);
@@ -164,17 +184,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 5) {
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24) |
+                                   (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);      // bits 15 / 16: A / B MN-major
+            const uint64_t a_step = p.a_mn ? (2048 >> 4) : 2, b_step = p.b_mn ? (2048 >> 4) : 2;   // address-field advance per K = 16
             for (int kb = 0; kb < nk; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(ring + (size_t)s * STAGE_BYTES);
-                const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + TBM * TBK * 2);
+                const uint64_t adesc = p.a_mn ? make_sw128_mn_desc(a_addr) : make_sw128_desc(a_addr);
+                const uint64_t bdesc = p.b_mn ? make_sw128_mn_desc(a_addr + TBM * TBK * 2) : make_sw128_desc(a_addr + TBM * TBK * 2);
 #pragma unroll
-                for (int k = 0; k < TBK / 16; ++k)        // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the address field
-                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < TBK / 16; ++k)        // K-major: advance 16 bf16 = 32 B inside the swizzle atom (+2); MN-major: 16 rows
+                    umma_bf16(tmem_base, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
                 umma_commit(&empty_bar[s]);               // implicit tcgen05.fence::before_thread_sync
             }
             umma_commit(&tmem_full_bar);
@@ -317,14 +340,17 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, float
 // Convolution weights W[g][co][ci][t] (fp32) -> bf16 A operands with K ordered (tap, channel):
 //   forward : dst[g][co][t * Cin + ci]            (rows = output channels)
 //   backward: dst[g][ci][t * Cout + co]           (rows = input channels: the input-gradient convolution)
-__global__ void pack_conv_weight_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ w, int G, int Cout, int Cin, int k, int bwd) {
-    const size_t total = (size_t)G * Cout * Cin * k;
-    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        // idx enumerates dst: [g][row][t][col]
-        const int rows = bwd ? Cin : Cout, cols = bwd ? Cout : Cin;
-        const int col = idx % cols, t = (idx / cols) % k, row = (idx / ((size_t)cols * k)) % rows, g = idx / ((size_t)cols * k * rows);
+__global__ void pack_conv_weight_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ w, int G, int Cout, int Cin, int k, int bwd,
+                                        int colsP) {
+    // block (x, row, g): one destination row [t][col] of k * colsP elements (columns >= cols are zero padding: channel counts that are no
+    // multiple of the 64-wide k-block); 32-bit index arithmetic only
+    const int rows = bwd ? Cin : Cout, cols = bwd ? Cout : Cin;
+    const int row = blockIdx.y, g = blockIdx.z;
+    __nv_bfloat16* drow = dst + ((size_t)g * rows + row) * (size_t)(k * colsP);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k * colsP; j += gridDim.x * blockDim.x) {
+        const int t = j / colsP, col = j - t * colsP;
         const int co = bwd ? col : row, ci = bwd ? row : col;
-        dst[idx] = __float2bfloat16_rn(w[(((size_t)g * Cout + co) * Cin + ci) * k + t]);
+        drow[j] = __float2bfloat16_rn(col < cols ? w[(((size_t)g * Cout + co) * Cin + ci) * k + t] : 0.f);
     }
 }
 
@@ -483,11 +509,17 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     const int Kp = (d.K + 7) / 8 * 8;
     const int abatch = d.a_batch_mod > 0 ? d.a_batch_mod : d.batch;
     const bool a_ready = d.A16 != nullptr && d.batch == 1 && (d.lda16 % 8) == 0 && (reinterpret_cast<uintptr_t>(d.A16) & 15) == 0;
-    const size_t a_bytes = a_ready ? 0 : ((size_t)abatch * d.M * Kp * 2 + 1023) / 1024 * 1024;
-    const size_t b_bytes = ((size_t)d.batch * d.N * Kp * 2 + 1023) / 1024 * 1024;
+    // MN-major operands (op(A) = A^T with A [K, M], op(B) = B [K, N]: weight gradients): the bf16 copy keeps the source's row-major
+    // [K][MN] layout (a plain row conversion, no transpose; MN padded to 64) and is keyed exactly like the K-contiguous copy another product
+    // makes of the same matrix, so e.g. the gate gradients are converted ONCE for their dX (K-major use) and dW (MN-major use) products
+    const bool a_mn = d.transA && !a_ready && d.batch == 1 && d.kin == 0 && !getenv("B200TTS_NO_MN_MAJOR");
+    const bool b_mn = !d.transB && d.batch == 1 && d.kin == 0 && !getenv("B200TTS_NO_MN_MAJOR");
+    const int Mp64 = (d.M + 63) / 64 * 64, Np64 = (d.N + 63) / 64 * 64;
+    const size_t a_bytes = a_ready ? 0 : a_mn ? ((size_t)d.K * Mp64 * 2 + 1023) / 1024 * 1024 : ((size_t)abatch * d.M * Kp * 2 + 1023) / 1024 * 1024;
+    const size_t b_bytes = b_mn ? ((size_t)d.K * Np64 * 2 + 1023) / 1024 * 1024 : ((size_t)d.batch * d.N * Kp * 2 + 1023) / 1024 * 1024;
     if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
-    const PackKey ka{d.A, d.lda, d.M, d.K, Kp, !d.transA, abatch, d.kin, d.strideA, d.kosA};
-    const PackKey kb{d.B, d.ldb, d.N, d.K, Kp, d.transB != 0, d.batch, d.kin, d.strideB, d.kosB};
+    const PackKey ka = a_mn ? PackKey{d.A, d.lda, d.K, d.M, Mp64, 1, 1, 0, 0, 0} : PackKey{d.A, d.lda, d.M, d.K, Kp, !d.transA, abatch, d.kin, d.strideA, d.kosA};
+    const PackKey kb = b_mn ? PackKey{d.B, d.ldb, d.K, d.N, Np64, 1, 1, 0, 0, 0} : PackKey{d.B, d.ldb, d.N, d.K, Kp, d.transB != 0, d.batch, d.kin, d.strideB, d.kosB};
     auto cached = [&](const PackKey& k) -> __nv_bfloat16* {
         if (!g_cache_on) return nullptr;
         for (int e = 0; e < g_ncache; ++e)
@@ -522,18 +554,27 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
         B200_LAUNCH_CHECK();
         return B200TTS_OK;
     };
-    if (pack_a) B200_TRY(pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch, d.kosA));
-    if (pack_b) B200_TRY(pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch, d.kosB));
+    // row conversion of an MN-major source: `rows` = K lines of `cols` = M (or N) values, zero-padded to `colsP`
+    auto pack_rows = [&](__nv_bfloat16* dst, const float* src, int ld, int rows, int cols, int colsP) -> int {
+        const int gx = colsP > 32768 ? 16 : cdiv(colsP, 2048);
+        pack_kcontig_kernel<<<dim3(gx, rows < 32768 ? rows : 32768, 1), 256, 0, st>>>(dst, src, ld, 0, rows, cols, colsP, 0, 0);
+        B200_LAUNCH_CHECK();
+        return B200TTS_OK;
+    };
+    if (pack_a) B200_TRY(a_mn ? pack_rows(pa, d.A, d.lda, d.K, d.M, Mp64) : pack(pa, d.A, d.lda, d.strideA, d.M, !d.transA, abatch, d.kosA));
+    if (pack_b) B200_TRY(b_mn ? pack_rows(pb, d.B, d.ldb, d.K, d.N, Np64) : pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch, d.kosB));
 
     CUtensorMap tmA, tmB;
     if (a_ready) B200_TRY(make_map(&tmA, static_cast<const __nv_bfloat16*>(d.A16), d.M, d.K, d.lda16, 1, TBM));
+    else if (a_mn) B200_TRY(tc_make_map3_bf16(&tmA, pa, 64, d.K, Mp64 / 64, (size_t)Mp64 * 2, 128, 64, 64, 2));
     else B200_TRY(make_map(&tmA, pa, d.M, d.K, Kp, abatch, TBM));
-    B200_TRY(make_map(&tmB, pb, d.N, d.K, Kp, d.batch, TBN));
+    if (b_mn) B200_TRY(tc_make_map3_bf16(&tmB, pb, 64, d.K, Np64 / 64, (size_t)Np64 * 2, 128, 64, 64, 2));
+    else B200_TRY(make_map(&tmB, pb, d.N, d.K, Kp, d.batch, TBN));
     TcArgs a;
     a.C = d.C; a.bias = d.bias; a.M = d.M; a.N = d.N; a.K = d.K; a.ldc = d.ldc; a.alpha = d.alpha; a.beta = d.beta;
     a.batch = d.batch; a.a_batch_mod = d.a_batch_mod; a.strideC = d.strideC;
     a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
-    a.ksplit = 1; a.kper = 0; a.partial = nullptr;
+    a.ksplit = 1; a.kper = 0; a.partial = nullptr; a.a_mn = a_mn ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
     // few output tiles and a long K (weight gradients over all (step, utterance) rows): split K over the idle SMs
     if (d.batch == 1)
         pick_ksplit(a, d.M, d.N, d.K, (g_cache_on ? g_cache_off : 0) + (pack_a ? a_bytes : 0) + (pack_b ? b_bytes : 0));
@@ -571,22 +612,24 @@ int gemm_tc_conv(const float* weight, const float* in, float* out, int NB, int G
     *handled = false;
     const int Cred = bwd ? Cout : Cin, Mrows = bwd ? Cin : Cout;
     if (!g_tc_enabled || g_scratch.ptr == nullptr || g_cache_on) return B200TTS_OK;
-    if (Cred % TBK != 0 || Mrows < 64 || L < 64 || k < 1) return B200TTS_OK;
+    // reduction channels are processed in 64-wide k-blocks; an ungrouped convolution with another channel count (the 80 mel channels of the
+    // postnet's first / last layer) is zero-padded to the next multiple in the bf16 operand copies
+    const int CredP = (Cred + TBK - 1) / TBK * TBK;
+    if ((CredP != Cred && G != 1) || Mrows < 64 || L < 64 || k < 1) return B200TTS_OK;
     if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
-    const int K = k * Cred, Ctot = G * Cred;
+    const int K = k * CredP, Ctot = G * CredP;
     const size_t a_bytes = ((size_t)G * Mrows * K * 2 + 1023) / 1024 * 1024;
     const size_t b_bytes = ((size_t)NB * L * Ctot * 2 + 1023) / 1024 * 1024;
     if (a_bytes + b_bytes > g_scratch.bytes) return B200TTS_OK;
     __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr);
     __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(g_scratch.ptr + a_bytes);
     {
-        const size_t total = (size_t)G * Cout * Cin * k;
-        int gx = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-        pack_conv_weight_kernel<<<gx, 256, 0, st>>>(pa, weight, G, Cout, Cin, k, bwd);
+        const int prow = bwd ? Cin : Cout;
+        pack_conv_weight_kernel<<<dim3(cdiv((long long)k * CredP, 256 * 4), prow, G), 256, 0, st>>>(pa, weight, G, Cout, Cin, k, bwd, CredP);
         B200_LAUNCH_CHECK();
-        // position-major copy: element (row = l, k = channel) of sample n at in[n][channel][l]
+        // position-major copy: element (row = l, k = channel) of sample n at in[n][channel][l]; channels >= G * Cred are zero padding
         dim3 grid(cdiv(L, 32), cdiv(Ctot, 64), NB), block(32, 8);
-        pack_transpose_kernel<<<grid, block, 0, st>>>(pb, in, L, (long long)Ctot * L, L, Ctot, Ctot);
+        pack_transpose_kernel<<<grid, block, 0, st>>>(pb, in, L, (long long)G * Cred * L, L, G * Cred, Ctot);
         B200_LAUNCH_CHECK();
     }
     CUtensorMap tmA, tmB;
@@ -595,8 +638,8 @@ int gemm_tc_conv(const float* weight, const float* in, float* out, int NB, int G
     TcArgs a;
     a.C = out; a.bias = nullptr; a.M = Mrows; a.N = L; a.K = K; a.ldc = L; a.alpha = 1.f; a.beta = beta;
     a.batch = NB * G; a.a_batch_mod = G; a.strideC = (long long)Mrows * L;
-    a.conv_cb = Cred / TBK; a.conv_dil = bwd ? -dil : dil; a.conv_pad = bwd ? -pad : pad; a.conv_G = G; a.conv_cin = Cred;
-    a.ksplit = 1; a.kper = 0; a.partial = nullptr;
+    a.conv_cb = CredP / TBK; a.conv_dil = bwd ? -dil : dil; a.conv_pad = bwd ? -pad : pad; a.conv_G = G; a.conv_cin = CredP;
+    a.ksplit = 1; a.kper = 0; a.partial = nullptr; a.a_mn = 0; a.b_mn = 0;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(L, TBN), cdiv(Mrows, TBM), NB * G);
@@ -638,7 +681,7 @@ int gemm_tc_conv_dw(const float* dz, const float* x, float* dweight, int NB, int
     a.C = dweight; a.bias = nullptr; a.M = Cout; a.N = R; a.K = K; a.ldc = R; a.alpha = 1.f; a.beta = 1.f;
     a.batch = G; a.a_batch_mod = 0; a.strideC = (long long)Cout * R;
     a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
-    a.ksplit = 1; a.kper = 0; a.partial = nullptr;
+    a.ksplit = 1; a.kper = 0; a.partial = nullptr; a.a_mn = 0; a.b_mn = 0;
     if (G == 1) pick_ksplit(a, Cout, R, K, a_bytes + b_bytes);      // postnet convolutions: 16 .. 80 tiles over K = NB * L
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -20,7 +20,8 @@ def _rel(a, b):
 @pytest.mark.parametrize('cfg', [
     dict(NB=3, G=2, Cin=64, Cout=128, L=100, k=5, dil=1, highway=True, act='tanh'),      # grouped, highway (Cout = 2 Cin)
     dict(NB=2, G=1, Cin=128, Cout=128, L=77, k=3, dil=2, highway=False, act='relu'),     # dilated
-    dict(NB=4, G=1, Cin=64, Cout=80, L=130, k=5, dil=1, highway=False, act='identity'),  # Cout % 64 != 0: input gradient falls back
+    dict(NB=4, G=1, Cin=64, Cout=80, L=130, k=5, dil=1, highway=False, act='identity'),  # Cout % 64 != 0 (postnet's last layer): zero-padded k-blocks in the input gradient
+    dict(NB=3, G=1, Cin=80, Cout=128, L=150, k=5, dil=1, highway=False, act='tanh'),     # Cin % 64 != 0 (postnet's first layer): zero-padded k-blocks in the forward
     dict(NB=6, G=10, Cin=64, Cout=128, L=64, k=3, dil=4, highway=True, act='relu'),      # 10 language groups
 ])
 def test_convblock_bf16_paths_match_fp32(cfg):
