@@ -118,6 +118,11 @@ struct GemmDesc {
     // reads it through TMA directly (no packing pass); A / lda are then ignored by that path
     const void* A16 = nullptr;
     int lda16 = 0;
+    // optional (tcgen05 path, !transB, batch == 1): op(B) = B [K, N] already available as bf16 rows, row stride ldb16 elements (multiple of
+    // 64, 16-byte aligned base); the columns up to the next multiple of 64 beyond N must be readable (their products are never stored).
+    // Read in place through TMA as an MN-major operand: no packing pass
+    const void* B16 = nullptr;
+    int ldb16 = 0;
     // optional two-level K (tcgen05 path only; needs !transA && transB): K = kouter * kin, element (row, q * kin + l) of op(A) lives at
     // A[q * kosA + row * lda + l] (op(B) likewise with kosB): sums a product over `kouter` separately stored slabs in ONE GEMM
     int kin = 0;

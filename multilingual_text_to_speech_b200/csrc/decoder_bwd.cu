@@ -2,6 +2,7 @@
 // Restates what torch autograd replays for Decoder._decode (reference modules/tacotron2.py:148-209,
 // train.py:83): frame/stop projection grads -> generator LSTM reverse loop -> attention LSTM +
 // location-sensitive attention reverse loop (energies recomputed, never stored) -> time-batched dW GEMMs.
+#include <cuda_bf16.h>
 #include "decoder_internal.cuh"
 
 namespace b200tts {
@@ -581,6 +582,15 @@ int wgemm(cudaStream_t st, const BwdLayout& l, float* ws, int transA, int transB
     d.transB = transB; d.beta = beta; d.batch = batch; d.strideA = sA; d.strideB = sB; d.strideC = sC;
     return gemm_run_auto(d, ws + l.gpart, l.gpart_elems, st);
 }
+// weight gradient dW (+)= A^T . B with A [K, M] fp32 and B [K, N] fp32; B16 (optional) = the same B as bf16 rows (row stride ldb16) that
+// the persistent forward loops left behind: read in place by the tcgen05 path (MN-major TMA operand), no conversion pass
+int wgemm16(cudaStream_t st, const BwdLayout& l, float* ws, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+            const void* B16, int ldb16, float* C, int ldc, float beta) {
+    GemmDesc d;
+    d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.transA = 1; d.transB = 0; d.beta = beta;
+    d.B16 = B16; d.ldb16 = ldb16;
+    return gemm_run_auto(d, ws + l.gpart, l.gpart_elems, st);
+}
 
 }  // namespace
 
@@ -648,6 +658,17 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     auto W = [&](size_t off) { return bws + off; };
     const float* ai = F(fl.ai);                // [T+1, B, M+D]
     const float* ai1 = ai + (size_t)B * MD;    // rows 1..T
+    // bf16 operand rows the tcgen05 forward loops left in the persistent workspace: aib [T+1, B, Kp_att] = [h_att | ctx | 0], hgb [T+1, B, Kp_gen]
+    // = h_gen (row i+1 = state after step i, row 0 = 0).  The weight-gradient products read them in place (MN-major TMA operands).
+    const bool tc_rows = precision_mode() == B200TTS_PRECISION_BF16 && s.training && tc_persist_supported(s) && persist_att_bwd_supported(s);
+    const PersistLayout prl = persist_layout(s);
+    const TcPersistGeom tcg = tc_persist_geom(s);
+    const unsigned char* pws_rows = reinterpret_cast<const unsigned char*>(F(fl.persist));
+    const __nv_bfloat16* aib = tc_rows ? reinterpret_cast<const __nv_bfloat16*>(pws_rows + prl.aib) : nullptr;
+    const __nv_bfloat16* hgb = tc_rows ? reinterpret_cast<const __nv_bfloat16*>(pws_rows + prl.hgb) : nullptr;
+    const int ldab = tcg.Kp_att, ldhb = tcg.Kp_gen;
+    const __nv_bfloat16* aib1 = aib ? aib + (size_t)B * ldab : nullptr;      // rows 1..T
+    const __nv_bfloat16* hgb1 = hgb ? hgb + (size_t)B * ldhb : nullptr;
 
     // ---- 1. frame / stop projection backward (time-batched) ----
     gather_frame_grads_kernel<<<grid_for(TB * N1), 256, 0, st>>>(W(l.dfs), dout.d_spectrogram, dout.d_stop, B, T, N);
@@ -656,8 +677,8 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, D, N1, W(l.dfs), N1, F(fl.wfs), D + M, W(l.dhgd), D, 0.f));
     B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, M, N1, W(l.dfs), N1, F(fl.wfs) + D, D + M, W(l.dctxs), M, 0.f));
     // d [frame_w ; stop_w] = dFS^T . [h_gen | ctx]
-    B200_TRY(wgemm(st, l, bws, 1, 0, N1, D, (int)TB, W(l.dfs), N1, F(fl.hg) + BD, D, W(l.dwfs), D + M, 0.f));
-    B200_TRY(wgemm(st, l, bws, 1, 0, N1, M, (int)TB, W(l.dfs), N1, ai1, MD, W(l.dwfs) + D, D + M, 0.f));
+    B200_TRY(wgemm16(st, l, bws, N1, D, (int)TB, W(l.dfs), N1, F(fl.hg) + BD, D, hgb1, ldhb, W(l.dwfs), D + M, 0.f));
+    B200_TRY(wgemm16(st, l, bws, N1, M, (int)TB, W(l.dfs), N1, ai1, MD, aib1 ? aib1 + D : nullptr, ldab, W(l.dwfs) + D, D + M, 0.f));
     add2d_kernel<<<grid_for((size_t)N * (D + M)), 256, 0, st>>>(dw.frame_w, D + M, W(l.dwfs), D + M, N, D + M);
     B200_LAUNCH_CHECK();
     add2d_kernel<<<grid_for((size_t)(D + M)), 256, 0, st>>>(dw.stop_w, D + M, W(l.dwfs) + (size_t)N * (D + M), D + M, 1, D + M);
@@ -700,9 +721,9 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
         // time-batched generator gradients.  The gate gradients are final now: their packed (transposed / K-contiguous) bf16 copies are
         // made once and shared by the three weight-gradient and the two input-gradient products (pack cache of the tcgen05 GEMM).
         PackScope pack_scope;
-        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, F(fl.hg), D, dw.gen_w_hh, D, 1.f));
-        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dgg), 4 * D, ai1 + M, MD, dw.gen_w_ih, D + M, 1.f));
-        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dgg), 4 * D, ai1, MD, dw.gen_w_ih + D, D + M, 1.f));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dgg), 4 * D, F(fl.hg), D, hgb, ldhb, dw.gen_w_hh, D, 1.f));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dgg), 4 * D, ai1 + M, MD, aib1, ldab, dw.gen_w_ih, D + M, 1.f));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, M, (int)TB, W(l.dgg), 4 * D, ai1, MD, aib1 ? aib1 + D : nullptr, ldab, dw.gen_w_ih + D, D + M, 1.f));
         B200_TRY(colsum_add(dw.gen_b_ih, dw.gen_b_hh, W(l.dgg), TB, 4 * D, 4 * D, W(l.gpart), st));
         // d h_att (static part) and d ctx (generator-input part, accumulated onto the projection part)
         B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, D, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih, D + M, W(l.dhas), D, 0.f));
@@ -764,15 +785,15 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     {
         PackScope pack_scope;       // one transposed bf16 copy of the attention-LSTM gate gradients for the three weight-gradient products
         B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, P, (int)TB, W(l.dga), 4 * D, F(fl.p1), P, dw.att_w_ih, P + M, 1.f));
-        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, M, (int)TB, W(l.dga), 4 * D, ai, MD, dw.att_w_ih + P, P + M, 1.f));
-        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, D, (int)TB, W(l.dga), 4 * D, ai + M, MD, dw.att_w_hh, D, 1.f));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, M, (int)TB, W(l.dga), 4 * D, ai, MD, aib ? aib + D : nullptr, ldab, dw.att_w_ih + P, P + M, 1.f));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dga), 4 * D, ai + M, MD, aib, ldab, dw.att_w_hh, D, 1.f));
     }
     {
         B200_TRY(colsum_add(dw.att_b_ih, dw.att_b_hh, W(l.dga), TB, 4 * D, 4 * D, W(l.gpart), st));
         B200_TRY(colsum_add(dw.attn_bias, nullptr, W(l.dq), TB, A, A, W(l.gpart), st));
     }
     // d Wq = dQ^T . h_att
-    B200_TRY(wgemm(st, l, bws, 1, 0, A, D, (int)TB, W(l.dq), A, ai1 + M, MD, dw.attn_query, D, 1.f));
+    B200_TRY(wgemm16(st, l, bws, A, D, (int)TB, W(l.dq), A, ai1 + M, MD, aib1, ldab, dw.attn_query, D, 1.f));
     if (!persist_att) {
         batchsum_add_kernel<<<grid_for((size_t)A * C), 256, 0, st>>>(dw.attn_location, W(l.dWloc_acc), B, (size_t)A * C);
         B200_LAUNCH_CHECK();

@@ -514,9 +514,10 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     // makes of the same matrix, so e.g. the gate gradients are converted ONCE for their dX (K-major use) and dW (MN-major use) products
     const bool a_mn = d.transA && !a_ready && d.batch == 1 && d.kin == 0 && !getenv("B200TTS_NO_MN_MAJOR");
     const bool b_mn = !d.transB && d.batch == 1 && d.kin == 0 && !getenv("B200TTS_NO_MN_MAJOR");
+    const bool b_ready = b_mn && d.B16 != nullptr && (d.ldb16 % 64) == 0 && (reinterpret_cast<uintptr_t>(d.B16) & 15) == 0;
     const int Mp64 = (d.M + 63) / 64 * 64, Np64 = (d.N + 63) / 64 * 64;
     const size_t a_bytes = a_ready ? 0 : a_mn ? ((size_t)d.K * Mp64 * 2 + 1023) / 1024 * 1024 : ((size_t)abatch * d.M * Kp * 2 + 1023) / 1024 * 1024;
-    const size_t b_bytes = b_mn ? ((size_t)d.K * Np64 * 2 + 1023) / 1024 * 1024 : ((size_t)d.batch * d.N * Kp * 2 + 1023) / 1024 * 1024;
+    const size_t b_bytes = b_ready ? 0 : b_mn ? ((size_t)d.K * Np64 * 2 + 1023) / 1024 * 1024 : ((size_t)d.batch * d.N * Kp * 2 + 1023) / 1024 * 1024;
     if ((reinterpret_cast<uintptr_t>(g_scratch.ptr) & 1023) != 0) return B200TTS_OK;
     const PackKey ka = a_mn ? PackKey{d.A, d.lda, d.K, d.M, Mp64, 1, 1, 0, 0, 0} : PackKey{d.A, d.lda, d.M, d.K, Kp, !d.transA, abatch, d.kin, d.strideA, d.kosA};
     const PackKey kb = b_mn ? PackKey{d.B, d.ldb, d.K, d.N, Np64, 1, 1, 0, 0, 0} : PackKey{d.B, d.ldb, d.N, d.K, Kp, d.transB != 0, d.batch, d.kin, d.strideB, d.kosB};
@@ -527,8 +528,8 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
         return nullptr;
     };
     __nv_bfloat16* pa = a_ready ? nullptr : cached(ka);
-    __nv_bfloat16* pb = cached(kb);
-    const bool pack_a = !a_ready && pa == nullptr, pack_b = pb == nullptr;
+    __nv_bfloat16* pb = b_ready ? nullptr : cached(kb);
+    const bool pack_a = !a_ready && pa == nullptr, pack_b = !b_ready && pb == nullptr;
     {   // place what has to be packed now: behind the cached operands (kept, when a scope is open and there is room for more)
         size_t off = g_cache_on ? g_cache_off : 0;
         const size_t need = (pack_a ? a_bytes : 0) + (pack_b ? b_bytes : 0);
@@ -568,7 +569,8 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     if (a_ready) B200_TRY(make_map(&tmA, static_cast<const __nv_bfloat16*>(d.A16), d.M, d.K, d.lda16, 1, TBM));
     else if (a_mn) B200_TRY(tc_make_map3_bf16(&tmA, pa, 64, d.K, Mp64 / 64, (size_t)Mp64 * 2, 128, 64, 64, 2));
     else B200_TRY(make_map(&tmA, pa, d.M, d.K, Kp, abatch, TBM));
-    if (b_mn) B200_TRY(tc_make_map3_bf16(&tmB, pb, 64, d.K, Np64 / 64, (size_t)Np64 * 2, 128, 64, 64, 2));
+    if (b_ready) B200_TRY(tc_make_map3_bf16(&tmB, d.B16, 64, d.K, Np64 / 64, (size_t)d.ldb16 * 2, 128, 64, 64, 2));
+    else if (b_mn) B200_TRY(tc_make_map3_bf16(&tmB, pb, 64, d.K, Np64 / 64, (size_t)Np64 * 2, 128, 64, 64, 2));
     else B200_TRY(make_map(&tmB, pb, d.N, d.K, Kp, d.batch, TBN));
     TcArgs a;
     a.C = d.C; a.bias = d.bias; a.M = d.M; a.N = d.N; a.K = d.K; a.ldc = d.ldc; a.alpha = d.alpha; a.beta = d.beta;
