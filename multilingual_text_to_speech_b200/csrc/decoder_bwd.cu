@@ -527,7 +527,7 @@ int launch_attn_bwd(AttnBwdArgs a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 struct BwdLayout {
     size_t dfs, dhgd, dctxs, dgg, dhas, dga, dq, dctxt, dcum, dc, dhz, dmemT, dWloc_acc, dWc_acc, dv_acc, dp1, dp0, dwfs,
-        part, gpart, pextra, pextra2, total;
+        part, gpart, pextra, pextra2, dggb, dgab, total;      // dggb / dgab: bf16 [T, B, 4D] histories of the gate gradients (tcgen05 loops)
     int split_gen, split_att;
     size_t gpart_elems;
 };
@@ -564,6 +564,8 @@ BwdLayout bwd_layout(const b200tts_decoder_shape& s) {
     l.gpart = take(l.gpart_elems);
     l.pextra = take(persist_bwd_gen_extra_bytes(s) / sizeof(float) + 64);
     l.pextra2 = take(att_bwd_extra(s).total / sizeof(float) + 64);
+    l.dggb = take(T * B * 4 * D / 2 + 64);
+    l.dgab = take(T * B * 4 * D / 2 + 64);
     l.total = off;
     return l;
 }
@@ -585,10 +587,18 @@ int wgemm(cudaStream_t st, const BwdLayout& l, float* ws, int transA, int transB
 // weight gradient dW (+)= A^T . B with A [K, M] fp32 and B [K, N] fp32; B16 (optional) = the same B as bf16 rows (row stride ldb16) that
 // the persistent forward loops left behind: read in place by the tcgen05 path (MN-major TMA operand), no conversion pass
 int wgemm16(cudaStream_t st, const BwdLayout& l, float* ws, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-            const void* B16, int ldb16, float* C, int ldc, float beta) {
+            const void* B16, int ldb16, float* C, int ldc, float beta, const void* A16 = nullptr, int lda16 = 0) {
     GemmDesc d;
     d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.transA = 1; d.transB = 0; d.beta = beta;
-    d.B16 = B16; d.ldb16 = ldb16;
+    d.B16 = B16; d.ldb16 = ldb16; d.A16 = A16; d.lda16 = lda16;
+    return gemm_run_auto(d, ws + l.gpart, l.gpart_elems, st);
+}
+// input gradient dX = A . B with A [M, K] fp32 (A16: the same matrix as bf16 rows, read in place) and B [K, N] fp32
+int xgemm16(cudaStream_t st, const BwdLayout& l, float* ws, int M, int N, int K, const float* A, int lda, const void* A16, int lda16,
+            const float* B, int ldb, float* C, int ldc, float beta) {
+    GemmDesc d;
+    d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.transA = 0; d.transB = 0; d.beta = beta;
+    d.A16 = A16; d.lda16 = lda16;
     return gemm_run_auto(d, ws + l.gpart, l.gpart_elems, st);
 }
 
@@ -688,10 +698,15 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
 
     // ---- 2. generator LSTM reverse loop ----
     const bool zone = s.cell_kind == B200TTS_CELL_ZONEOUT;
+    // the tcgen05 reverse loops keep their bf16 gate gradients as [T, B, 4D] histories: the time-batched products below read them in place
+    // (K-major for dX, MN-major for dW) instead of converting the fp32 copies
+    const bool hist_gen = precision_mode() == B200TTS_PRECISION_BF16 && persist_bwd_supported(s) && tc_persist_gen_bwd_supported(s) &&
+                          !getenv("B200TTS_NO_DGB_HISTORY");
+    void* dggb = hist_gen ? static_cast<void*>(W(l.dggb)) : nullptr;
     if (precision_mode() == B200TTS_PRECISION_BF16 && persist_bwd_supported(s)) {
         // bf16 perf mode: one cooperative weight-stationary kernel for the whole reverse recurrence
         if (tc_persist_gen_bwd_supported(s))      // TMA + tcgen05 + TMEM variant (decoder_persist_bwd_tc.cu)
-            B200_TRY(tc_persist_gen_bwd_loop(s, w, in, fl, fws, W(l.dhgd), W(l.dgg), reinterpret_cast<unsigned char*>(W(l.pextra)), st));
+            B200_TRY(tc_persist_gen_bwd_loop(s, w, in, fl, fws, W(l.dhgd), W(l.dgg), reinterpret_cast<unsigned char*>(W(l.pextra)), st, dggb));
         else
             B200_TRY(persist_gen_bwd_loop(s, w, in, fl, fws, W(l.dhgd), W(l.dgg), reinterpret_cast<unsigned char*>(W(l.pextra)), st));
     } else {
@@ -721,24 +736,25 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
         // time-batched generator gradients.  The gate gradients are final now: their packed (transposed / K-contiguous) bf16 copies are
         // made once and shared by the three weight-gradient and the two input-gradient products (pack cache of the tcgen05 GEMM).
         PackScope pack_scope;
-        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dgg), 4 * D, F(fl.hg), D, hgb, ldhb, dw.gen_w_hh, D, 1.f));
-        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dgg), 4 * D, ai1 + M, MD, aib1, ldab, dw.gen_w_ih, D + M, 1.f));
-        B200_TRY(wgemm16(st, l, bws, 4 * D, M, (int)TB, W(l.dgg), 4 * D, ai1, MD, aib1 ? aib1 + D : nullptr, ldab, dw.gen_w_ih + D, D + M, 1.f));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dgg), 4 * D, F(fl.hg), D, hgb, ldhb, dw.gen_w_hh, D, 1.f, dggb, 4 * D));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dgg), 4 * D, ai1 + M, MD, aib1, ldab, dw.gen_w_ih, D + M, 1.f, dggb, 4 * D));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, M, (int)TB, W(l.dgg), 4 * D, ai1, MD, aib1 ? aib1 + D : nullptr, ldab, dw.gen_w_ih + D, D + M, 1.f, dggb, 4 * D));
         B200_TRY(colsum_add(dw.gen_b_ih, dw.gen_b_hh, W(l.dgg), TB, 4 * D, 4 * D, W(l.gpart), st));
         // d h_att (static part) and d ctx (generator-input part, accumulated onto the projection part)
-        B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, D, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih, D + M, W(l.dhas), D, 0.f));
-        B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, M, 4 * D, W(l.dgg), 4 * D, w.gen_w_ih + D, D + M, W(l.dctxs), M, 1.f));
+        B200_TRY(xgemm16(st, l, bws, (int)TB, D, 4 * D, W(l.dgg), 4 * D, dggb, 4 * D, w.gen_w_ih, D + M, W(l.dhas), D, 0.f));
+        B200_TRY(xgemm16(st, l, bws, (int)TB, M, 4 * D, W(l.dgg), 4 * D, dggb, 4 * D, w.gen_w_ih + D, D + M, W(l.dctxs), M, 1.f));
     }
 
     // ---- 3. attention LSTM + attention reverse loop ----
     const bool persist_att = precision_mode() == B200TTS_PRECISION_BF16 && s.training && (tc_persist_supported(s) || persist_supported(s)) &&
                              persist_att_bwd_supported(s);
+    void* dgab = (persist_att && persist_att_bwd_tc(s) && !getenv("B200TTS_NO_DGB_HISTORY")) ? static_cast<void*>(W(l.dgab)) : nullptr;
     if (persist_att) {
         // bf16 perf mode: cooperative weight-stationary kernel (tensor-core attention backward inside), then a parallel post pass
         const PersistLayout pl = persist_layout(s);
         B200_TRY(persist_att_bwd_loop(s, w, in, fl, fws, pl, reinterpret_cast<const unsigned char*>(F(fl.persist)), fwd_out.alignments,
                                       dout.d_alignments, W(l.dhas), W(l.dctxs), W(l.dga), W(l.dq), W(l.dctxt), W(l.dmemT),
-                                      reinterpret_cast<unsigned char*>(W(l.pextra2)), dw, st));
+                                      reinterpret_cast<unsigned char*>(W(l.pextra2)), dw, st, dgab));
     } else {
     B200_TRY(launch_fill(W(l.dmemT), 0.f, (size_t)B * L * A, st));
         B200_TRY(launch_fill(W(l.dWloc_acc), 0.f, (size_t)B * A * C, st));
@@ -784,9 +800,9 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     // ---- 4. time-batched gradients of the attention LSTM, attention parameters, prenet, memory ----
     {
         PackScope pack_scope;       // one transposed bf16 copy of the attention-LSTM gate gradients for the three weight-gradient products
-        B200_TRY(wgemm(st, l, bws, 1, 0, 4 * D, P, (int)TB, W(l.dga), 4 * D, F(fl.p1), P, dw.att_w_ih, P + M, 1.f));
-        B200_TRY(wgemm16(st, l, bws, 4 * D, M, (int)TB, W(l.dga), 4 * D, ai, MD, aib ? aib + D : nullptr, ldab, dw.att_w_ih + P, P + M, 1.f));
-        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dga), 4 * D, ai + M, MD, aib, ldab, dw.att_w_hh, D, 1.f));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, P, (int)TB, W(l.dga), 4 * D, F(fl.p1), P, nullptr, 0, dw.att_w_ih, P + M, 1.f, dgab, 4 * D));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, M, (int)TB, W(l.dga), 4 * D, ai, MD, aib ? aib + D : nullptr, ldab, dw.att_w_ih + P, P + M, 1.f, dgab, 4 * D));
+        B200_TRY(wgemm16(st, l, bws, 4 * D, D, (int)TB, W(l.dga), 4 * D, ai + M, MD, aib, ldab, dw.att_w_hh, D, 1.f, dgab, 4 * D));
     }
     {
         B200_TRY(colsum_add(dw.att_b_ih, dw.att_b_hh, W(l.dga), TB, 4 * D, 4 * D, W(l.gpart), st));
@@ -813,7 +829,7 @@ int decoder_backward_impl(const b200tts_decoder_shape& s, const b200tts_decoder_
     {
         const float scale1 = in.mask_prenet1 ? 1.f / (1.f - s.prenet_rate) : 1.f;
         const float scale0 = in.mask_prenet0 ? 1.f / (1.f - s.prenet_rate) : 1.f;
-        B200_TRY(wgemm(st, l, bws, 0, 0, (int)TB, P, 4 * D, W(l.dga), 4 * D, w.att_w_ih, P + M, W(l.dp1), P, 0.f));
+        B200_TRY(xgemm16(st, l, bws, (int)TB, P, 4 * D, W(l.dga), 4 * D, dgab, 4 * D, w.att_w_ih, P + M, W(l.dp1), P, 0.f));
         relu_dropout_bwd_kernel<<<grid_for(TB * P), 256, 0, st>>>(W(l.dp1), W(l.dp1), F(fl.p1), scale1, TB * P);
         B200_LAUNCH_CHECK();
         B200_TRY(wgemm(st, l, bws, 1, 0, P, P, (int)TB, W(l.dp1), P, F(fl.p0), P, dw.prenet_w1, P, 1.f));

@@ -122,7 +122,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
                          const DecoderLayout& fl, const float* fws, const PersistLayout& pl, const unsigned char* pws,
                          const float* align, const float* dalign, const float* dh_static, const float* dctx_static, float* dgates,
                          float* dq, float* dctx_tot, float* dmemT, unsigned char* extra, const b200tts_decoder_params& dw,
-                         cudaStream_t st);
+                         cudaStream_t st, void* dgb_hist = nullptr);      // dgb_hist: optional [T, B, 4D] bf16 history of the gate gradients
 bool persist_bwd_supported(const b200tts_decoder_shape& s);
 size_t persist_bwd_gen_extra_bytes(const b200tts_decoder_shape& s);
 int persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
@@ -131,7 +131,7 @@ int persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
 bool tc_persist_gen_bwd_supported(const b200tts_decoder_shape& s);
 int tc_persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                             const DecoderLayout& fl, const float* fws, const float* dh_static, float* dgates, unsigned char* extra,
-                            cudaStream_t st);
+                            cudaStream_t st, void* dgb_hist = nullptr);
 int persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                      const DecoderLayout& fl, float* ws, unsigned char* pws, cudaStream_t st);
 

@@ -280,6 +280,8 @@ struct AttBwdArgs {
     const uint8_t* mask_h; const uint8_t* mask_c;
     int kind, training; float rate_h, rate_c;
     float* dgates; __nv_bfloat16* dgb; float* part;       // as in BwdLoopArgs; part [KBA, B, NOUT]
+    long long dgb_step;                                   // bf16 gate gradients: 0 = [B, 4D] staging reused every step, B * 4D = [T, B, 4D] history
+    int dgb_rows;                                         // rows of one step inside the TMA source (0 for the staging, B for the history)
     // attention
     const float* q; const float* cum; const float* align; long long align_bstride;
     const float* dalign; long long dalign_bstride;        // may be null
@@ -823,7 +825,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                     const float di = dcn * gg * gi * (1.f - gi), df = dcn * cp * gf * (1.f - gf);
                     const float dg = dcn * gi * (1.f - gg * gg), dO = dhn * tc * go * (1.f - go);
                     p.dgates[g0] = di; p.dgates[g0 + D] = df; p.dgates[g0 + 2 * D] = dg; p.dgates[g0 + 3 * D] = dO;
-                    __nv_bfloat16* db = p.dgb + (size_t)b * 4 * D + u;
+                    __nv_bfloat16* db = p.dgb + (size_t)i * p.dgb_step + (size_t)b * 4 * D + u;
                     db[0] = __float2bfloat16_rn(di); db[D] = __float2bfloat16_rn(df);
                     db[2 * D] = __float2bfloat16_rn(dg); db[3 * D] = __float2bfloat16_rn(dO);
                     dc_reg[e] = dcn * gf + dc_prev_direct;
@@ -854,7 +856,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                     tcx::proxy_fence_shared();       // the slot was last touched through the generic proxy (attention scratch, dq staging)
                     tcx::proxy_fence_global();
                     tcx::mbar_expect_tx(&full_bar, (uint32_t)NKT * 8192);
-                    tcx::tma_load_5d(As, &tmG, &full_bar, 0, 0, 0, kb, 0);
+                    tcx::tma_load_5d(As, &tmG, &full_bar, 0, i * p.dgb_rows, 0, kb, 0);
                 }
                 __syncwarp();
                 tcx::mbar_wait(&full_bar, prod_it & 1);
@@ -899,7 +901,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             for (int idx = tid; idx < BT * 4 * segs; idx += PT) {
                 const int r = idx / (4 * segs), rem = idx % (4 * segs), g = rem / segs, sg = rem % segs;
                 __nv_bfloat16* d = As + r * ALD + g * UK + sg * 8;
-                if (b0 + r < B) cp_async16(d, p.dgb + (size_t)(b0 + r) * 4 * D + g * D + kb * UK + sg * 8);
+                if (b0 + r < B) cp_async16(d, p.dgb + (size_t)i * p.dgb_step + (size_t)(b0 + r) * 4 * D + g * D + kb * UK + sg * 8);
                 else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
             }
             cp_async_commit_wait();
@@ -1279,7 +1281,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
                          const DecoderLayout& fl, const float* fws, const PersistLayout& pl, const unsigned char* pws,
                          const float* align, const float* dalign, const float* dh_static, const float* dctx_static, float* dgates,
                          float* dq, float* dctx_tot, float* dmemT, unsigned char* extra, const b200tts_decoder_params& dw,
-                         cudaStream_t st) {
+                         cudaStream_t st, void* dgb_hist) {
     const AttBwdExtra x = att_bwd_extra(s);
     const int B = s.B, D = s.D, M = s.M, T = s.T, L = s.L, A = s.A;
     AttBwdArgs a{};
@@ -1291,7 +1293,10 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     a.gates = fws + fl.ga; a.cstate = fws + fl.ca; a.dh_static = dh_static; a.dctx_static = dctx_static;
     a.mask_h = in.mask_att_h; a.mask_c = in.mask_att_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
     a.dgates = dgates;
-    a.dgb = reinterpret_cast<__nv_bfloat16*>(extra + x.dgb);
+    // bf16 gate gradients: a [T, B, 4D] history when the caller wants to feed the time-batched products from it (no conversion pass),
+    // else a [B, 4D] staging reused every step
+    a.dgb = dgb_hist ? static_cast<__nv_bfloat16*>(dgb_hist) : reinterpret_cast<__nv_bfloat16*>(extra + x.dgb);
+    a.dgb_step = dgb_hist ? (long long)B * 4 * D : 0; a.dgb_rows = dgb_hist ? B : 0;
     a.part = reinterpret_cast<float*>(extra + x.part);
     a.q = fws + fl.q; a.cum = fws + fl.cum; a.align = align; a.align_bstride = (long long)T * L;
     a.dalign = dalign; a.dalign_bstride = (long long)T * L;
@@ -1325,7 +1330,7 @@ int persist_att_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_p
     if (geo.tc) {
         // bf16 gate gradients dgb [B, 4D] as {64 k, B rows, UK/64 halves, KBA k-slices, 4 gates}: element (b, g, kb, h, c) at
         // b * 4D + g * D + kb * UK + h * 64 + c; one box = {64, 64 rows, UK/64, 1, 4} = the whole K-slice of a CTA
-        const unsigned long long dims[5] = {64ull, (unsigned long long)B, (unsigned long long)(geo.UK / 64), (unsigned long long)KBA, 4ull};
+        const unsigned long long dims[5] = {64ull, (unsigned long long)(dgb_hist ? (size_t)T * B : (size_t)B), (unsigned long long)(geo.UK / 64), (unsigned long long)KBA, 4ull};
         const unsigned long long strides[4] = {(unsigned long long)4 * D * 2, 128ull, (unsigned long long)geo.UK * 2, (unsigned long long)D * 2};
         const unsigned box[5] = {64u, 64u, (unsigned)(geo.UK / 64), 1u, 4u};
         B200_TRY(tc_make_mapN_bf16(&tm, a.dgb, 5, dims, strides, box));

@@ -40,7 +40,8 @@ struct TcBwdArgs {
     const uint8_t* mask_h; const uint8_t* mask_c;
     int kind, training; float rate_h, rate_c;
     float* dgates;                            // [T, B, 4D] out (fp32)
-    __nv_bfloat16* dgb;                       // [B, 4D] staging (bf16), TMA source
+    __nv_bfloat16* dgb;                       // [B, 4D] staging (bf16), TMA source -- or a [T, B, 4D] history (dgb_step = B * 4D, dgb_rows = B)
+    long long dgb_step; int dgb_rows;
     float* part;                              // [NG, B, D] partial products of the previous reverse step
     unsigned* barrier; int* abort_flag;
     long long* prof;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_tc_kernel(const __grid_co
                     const float di = dcn * gg * gi * (1.f - gi), df = dcn * cp * gf * (1.f - gf);
                     const float dg = dcn * gi * (1.f - gg * gg), dO = dhn * tc * go * (1.f - go);
                     p.dgates[g0] = di; p.dgates[g0 + D] = df; p.dgates[g0 + 2 * D] = dg; p.dgates[g0 + 3 * D] = dO;
-                    __nv_bfloat16* db = p.dgb + (size_t)b * 4 * D + u;
+                    __nv_bfloat16* db = p.dgb + (size_t)i * p.dgb_step + (size_t)b * 4 * D + u;
                     db[0] = __float2bfloat16_rn(di); db[D] = __float2bfloat16_rn(df);
                     db[2 * D] = __float2bfloat16_rn(dg); db[3 * D] = __float2bfloat16_rn(dO);
                     dc_reg[e] = dcn * gf + dc_prev_direct;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_bwd_loop_tc_kernel(const __grid_co
             proxy_fence_global();
             if (elect_one()) {
                 mbar_expect_tx(&full_bar, (uint32_t)NNB * ATILE);
-                tma_load_3d(ring, &tmG, &full_bar, 0, b0, gsel * NNB);
+                tma_load_3d(ring, &tmG, &full_bar, 0, i * p.dgb_rows + b0, gsel * NNB);
             }
             __syncwarp();
         }
@@ -372,7 +373,7 @@ bool tc_persist_gen_bwd_supported(const b200tts_decoder_shape& s) {
 // mma.sync variant: dgb [B, 4D] bf16, then the partial buffer (4 of its 8 slabs are used), then barrier + profile counters).
 int tc_persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decoder_params& w, const b200tts_decoder_inputs& in,
                             const DecoderLayout& fl, const float* fws, const float* dh_static, float* dgates, unsigned char* extra,
-                            cudaStream_t st) {
+                            cudaStream_t st, void* dgb_hist) {
     const int B = s.B, D = s.D;
     TcBwdArgs a{};
     a.B = B; a.T = s.T; a.D = D; a.NNB = D / KB; a.NBH = (B + BT - 1) / BT;
@@ -381,14 +382,16 @@ int tc_persist_gen_bwd_loop(const b200tts_decoder_shape& s, const b200tts_decode
     a.mask_h = in.mask_gen_h; a.mask_c = in.mask_gen_c; a.kind = s.cell_kind; a.training = s.training; a.rate_h = s.rate_h; a.rate_c = s.rate_c;
     a.dgates = dgates;
     size_t off = 0;
-    a.dgb = reinterpret_cast<__nv_bfloat16*>(extra + off); off += ((size_t)B * 4 * D * 2 + 255) / 256 * 256;
+    a.dgb = dgb_hist ? static_cast<__nv_bfloat16*>(dgb_hist) : reinterpret_cast<__nv_bfloat16*>(extra + off);
+    a.dgb_step = dgb_hist ? (long long)B * 4 * D : 0; a.dgb_rows = dgb_hist ? B : 0;
+    off += ((size_t)B * 4 * D * 2 + 255) / 256 * 256;
     a.part = reinterpret_cast<float*>(extra + off); off += ((size_t)8 * B * D * 4 + 255) / 256 * 256;
     a.barrier = reinterpret_cast<unsigned*>(extra + off);
     a.abort_flag = reinterpret_cast<int*>(a.barrier + 32);
     a.prof = reinterpret_cast<long long*>(extra + off + 256);
     B200_CUDA(cudaMemsetAsync(a.barrier, 0, 256, st));
     CUtensorMap tm;        // {64 columns, B rows, 4D/64 k-blocks}: k-block stride 128 B, row stride 4D * 2 B
-    B200_TRY(tc_make_map3_bf16(&tm, a.dgb, KB, B, 4 * D / KB, (size_t)4 * D * 2, 128, KB, BT, a.NNB));
+    B200_TRY(tc_make_map3_bf16(&tm, a.dgb, KB, dgb_hist ? s.T * B : B, 4 * D / KB, (size_t)4 * D * 2, 128, KB, BT, a.NNB));
     const size_t smem = bwd_tc_smem_bytes(D);
     void* fn = (void*)lstm_bwd_loop_tc_kernel;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -508,7 +508,10 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     if ((long long)d.M * d.N * d.K * d.batch < (1ll << 24)) return B200TTS_OK;
     const int Kp = (d.K + 7) / 8 * 8;
     const int abatch = d.a_batch_mod > 0 ? d.a_batch_mod : d.batch;
-    const bool a_ready = d.A16 != nullptr && d.batch == 1 && (d.lda16 % 8) == 0 && (reinterpret_cast<uintptr_t>(d.A16) & 15) == 0;
+    const bool a16ok = d.A16 != nullptr && d.batch == 1 && (d.lda16 % 8) == 0 && (reinterpret_cast<uintptr_t>(d.A16) & 15) == 0;
+    // A16 with transA: the bf16 matrix is [K, M] row-major (e.g. the gate-gradient history of the reverse loops) = an MN-major operand in place
+    const bool a_mn_ready = a16ok && d.transA && d.kin == 0 && (d.lda16 % 64) == 0 && !getenv("B200TTS_NO_MN_MAJOR");
+    const bool a_ready = (a16ok && !d.transA) || a_mn_ready;
     // MN-major operands (op(A) = A^T with A [K, M], op(B) = B [K, N]: weight gradients): the bf16 copy keeps the source's row-major
     // [K][MN] layout (a plain row conversion, no transpose; MN padded to 64) and is keyed exactly like the K-contiguous copy another product
     // makes of the same matrix, so e.g. the gate gradients are converted ONCE for their dX (K-major use) and dW (MN-major use) products
@@ -566,7 +569,8 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     if (pack_b) B200_TRY(b_mn ? pack_rows(pb, d.B, d.ldb, d.K, d.N, Np64) : pack(pb, d.B, d.ldb, d.strideB, d.N, d.transB != 0, d.batch, d.kosB));
 
     CUtensorMap tmA, tmB;
-    if (a_ready) B200_TRY(make_map(&tmA, static_cast<const __nv_bfloat16*>(d.A16), d.M, d.K, d.lda16, 1, TBM));
+    if (a_mn_ready) B200_TRY(tc_make_map3_bf16(&tmA, d.A16, 64, d.K, Mp64 / 64, (size_t)d.lda16 * 2, 128, 64, 64, 2));
+    else if (a_ready) B200_TRY(make_map(&tmA, static_cast<const __nv_bfloat16*>(d.A16), d.M, d.K, d.lda16, 1, TBM));
     else if (a_mn) B200_TRY(tc_make_map3_bf16(&tmA, pa, 64, d.K, Mp64 / 64, (size_t)Mp64 * 2, 128, 64, 64, 2));
     else B200_TRY(make_map(&tmA, pa, d.M, d.K, Kp, abatch, TBM));
     if (b_ready) B200_TRY(tc_make_map3_bf16(&tmB, d.B16, 64, d.K, Np64 / 64, (size_t)d.ldb16 * 2, 128, 64, 64, 2));
@@ -576,7 +580,7 @@ int gemm_tc_try(const GemmDesc& d, cudaStream_t st, bool* handled) {
     a.C = d.C; a.bias = d.bias; a.M = d.M; a.N = d.N; a.K = d.K; a.ldc = d.ldc; a.alpha = d.alpha; a.beta = d.beta;
     a.batch = d.batch; a.a_batch_mod = d.a_batch_mod; a.strideC = d.strideC;
     a.conv_cb = 0; a.conv_dil = 0; a.conv_pad = 0; a.conv_G = 1; a.conv_cin = 0;
-    a.ksplit = 1; a.kper = 0; a.partial = nullptr; a.a_mn = a_mn ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
+    a.ksplit = 1; a.kper = 0; a.partial = nullptr; a.a_mn = (a_mn || a_mn_ready) ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
     // few output tiles and a long K (weight gradients over all (step, utterance) rows): split K over the idle SMs
     if (d.batch == 1)
         pick_ksplit(a, d.M, d.N, d.K, (g_cache_on ? g_cache_off : 0) + (pack_a ? a_bytes : 0) + (pack_b ? b_bytes : 0));
