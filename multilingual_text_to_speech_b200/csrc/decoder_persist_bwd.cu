@@ -969,7 +969,7 @@ struct AttPostArgs {
     float* dv_part;                    // [B*MT][A]
 };
 
-__global__ void __launch_bounds__(PT) att_post_kernel(const AttPostArgs p) {
+__global__ void __launch_bounds__(PT, 3) att_post_kernel(const AttPostArgs p) {
     constexpr int NS = 4;                               // decoder steps per block barrier
     __shared__ uint32_t Ph[2][NS][64], Pl[2][NS][64];
     __shared__ float s_de[2][NS][16], s_q[2][NS][128];

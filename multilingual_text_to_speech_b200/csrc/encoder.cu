@@ -415,10 +415,18 @@ __global__ void generator_expand_kernel(float* __restrict__ out, const float* __
     __shared__ float s_eb[GEN_MAXG * GEN_MAXBN];
     for (int i = threadIdx.x; i < G * bn; i += blockDim.x) s_eb[i] = eb[i];
     __syncthreads();
+    const bool vec8 = (reinterpret_cast<uintptr_t>(Wk) & 15) == 0;
     for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < R; r += (size_t)gridDim.x * blockDim.x) {
         float w[GEN_MAXBN];
+        if (bn == 8 && vec8) {           // one 32-byte row per thread: two 16-byte loads
+            const float4 w0 = reinterpret_cast<const float4*>(Wk)[2 * r], w1 = reinterpret_cast<const float4*>(Wk)[2 * r + 1];
+            w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
 #pragma unroll
-        for (int j = 0; j < GEN_MAXBN; ++j) w[j] = j < bn ? Wk[r * bn + j] : 0.f;
+            for (int j = 8; j < GEN_MAXBN; ++j) w[j] = 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < GEN_MAXBN; ++j) w[j] = j < bn ? Wk[r * bn + j] : 0.f;
+        }
         const float b = bk ? bk[r] : 0.f;
         for (int g = 0; g < G; ++g) {
             float a = b;
@@ -448,6 +456,57 @@ __global__ void generator_dwk_kernel(float* __restrict__ dWk, float* __restrict_
 #pragma unroll
         for (int j = 0; j < GEN_MAXBN; ++j) if (j < bn) dWk[r * bn + j] += acc[j];
         if (dbk) dbk[r] += sb;
+    }
+}
+// Fused backward of the expansion for bn == 8 and G <= 10 (every shipped configuration): ONE pass over dout and Wk, both read coalesced
+// (thread = generated element r): dWk[r, :] += dout[:, r]^T eb, dbk[r] += sum_g dout[g, r], and per-block partial sums of
+// deb[g, j] = sum_r dout[g, r] Wk[r, j] kept in 80 registers and reduced once per block (fixed order: deterministic).
+constexpr int GEN_FG = 10;
+__global__ void __launch_bounds__(256) generator_bwd_fused_kernel(float* __restrict__ dWk, float* __restrict__ dbk, float* __restrict__ partial,
+                                                                  const float* __restrict__ dout, const float* __restrict__ Wk,
+                                                                  const float* __restrict__ eb, int G, size_t R) {
+    __shared__ float s_eb[GEN_FG * 8];
+    __shared__ float s_red[8][GEN_FG * 8];
+    for (int i = threadIdx.x; i < GEN_FG * 8; i += blockDim.x) s_eb[i] = i < G * 8 ? eb[i] : 0.f;
+    __syncthreads();
+    float acc[GEN_FG][8];
+#pragma unroll
+    for (int g = 0; g < GEN_FG; ++g)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[g][j] = 0.f;
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < R; r += (size_t)gridDim.x * blockDim.x) {
+        float d[GEN_FG];
+#pragma unroll
+        for (int g = 0; g < GEN_FG; ++g) d[g] = g < G ? dout[(size_t)g * R + r] : 0.f;
+        const float4 w0 = reinterpret_cast<const float4*>(Wk)[2 * r], w1 = reinterpret_cast<const float4*>(Wk)[2 * r + 1];
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sb = 0.f;
+#pragma unroll
+        for (int g = 0; g < GEN_FG; ++g) {
+            sb += d[g];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = fmaf(d[g], s_eb[g * 8 + j], a[j]); acc[g][j] = fmaf(d[g], w[j], acc[g][j]); }
+        }
+        float4* o = reinterpret_cast<float4*>(dWk) + 2 * r;
+        float4 o0 = o[0], o1 = o[1];
+        o0.x += a[0]; o0.y += a[1]; o0.z += a[2]; o0.w += a[3]; o1.x += a[4]; o1.y += a[5]; o1.z += a[6]; o1.w += a[7];
+        o[0] = o0; o[1] = o1;
+        if (dbk) dbk[r] += sb;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int g = 0; g < GEN_FG; ++g)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = warp_sum(acc[g][j]);
+            if (lane == 0) s_red[warp][g * 8 + j] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < G * 8) {
+        float t = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) t += s_red[w8][threadIdx.x];
+        partial[(size_t)blockIdx.x * G * 8 + threadIdx.x] = t;
     }
 }
 // partial[blk][g, j] = sum over this block's r-chunk of dout[g, r] Wk[r, j]   (thread = (g, j); fixed chunking: deterministic)
@@ -708,7 +767,15 @@ int generator_backward_impl(int G, int gd, int bn, long long R, const float* e, 
     float* scratch = ws + align_up_sz((size_t)G * bn, 64);
     const size_t chunk = 256;
     const int nblk = (int)((R + chunk - 1) / chunk);
-    if (G <= GEN_MAXG && bn <= GEN_MAXBN && (size_t)nblk * G * bn <= kGemmScratch && G * bn <= 256) {
+    if (bn == 8 && G <= GEN_FG && (reinterpret_cast<uintptr_t>(Wk) & 15) == 0 && (reinterpret_cast<uintptr_t>(dWk) & 15) == 0 &&
+        !getenv("B200TTS_GENERATOR_UNFUSED")) {
+        // ONE coalesced pass over dout and Wk (fused dWk / dbk / per-block deb partials), then the fixed-order reduction of the partials
+        const int fblk = (int)(((size_t)R + 255) / 256 < 148 * 2 ? ((size_t)R + 255) / 256 : 148 * 2);
+        generator_bwd_fused_kernel<<<fblk, 256, 0, st>>>(dWk, dbk, scratch, dout, Wk, eb, G, (size_t)R);
+        B200_LAUNCH_CHECK();
+        generator_deb_finish_kernel<<<G * bn, 128, 0, st>>>(deb, scratch, fblk, G * bn);
+        B200_LAUNCH_CHECK();
+    } else if (G <= GEN_MAXG && bn <= GEN_MAXBN && (size_t)nblk * G * bn <= kGemmScratch && G * bn <= 256) {
         // dWk [R, bn] += dout^T . eb and dbk += column sums of dout, in one pass over dout
         generator_dwk_kernel<<<grid_for((size_t)R), 256, 0, st>>>(dWk, dbk, dout, eb, G, bn, (size_t)R);
         B200_LAUNCH_CHECK();

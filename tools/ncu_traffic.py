@@ -9,7 +9,8 @@ import csv
 import json
 import re
 
-SHORT = [('lstm_loop_tc_kernel<1>', 'lstm_loop_tc_kernel<att>'), ('lstm_loop_tc_kernel<0>', 'lstm_loop_tc_kernel<gen>'),
+SHORT = [('lstm_loop_tc_kernel<1', 'lstm_loop_tc_kernel<att>'), ('lstm_loop_tc_kernel<0', 'lstm_loop_tc_kernel<gen>'),
+         ('lstm_loop_tc_kernel<true', 'lstm_loop_tc_kernel<att>'), ('lstm_loop_tc_kernel<false', 'lstm_loop_tc_kernel<gen>'),
          ('lstm_loop_tc_kernel<true>', 'lstm_loop_tc_kernel<att>'), ('lstm_loop_tc_kernel<false>', 'lstm_loop_tc_kernel<gen>'),
          ('att_bwd_loop_kernel', 'att_bwd_loop_kernel'), ('lstm_bwd_loop_tc_kernel', 'lstm_bwd_loop_tc_kernel'),
          ('lstm_bwd_loop_kernel', 'lstm_bwd_loop_kernel'), ('att_post_kernel', 'att_post_kernel')]
