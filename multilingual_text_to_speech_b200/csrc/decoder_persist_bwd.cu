@@ -107,6 +107,14 @@ __device__ __forceinline__ void st_peer_f32(const float* local_smem, uint32_t pe
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// remote store that completes its 4 bytes on the PEER's mbarrier (data + signal in one instruction): the pair exchanges need no cluster
+// barrier and none of the memory fence its release semantics imply
+__device__ __forceinline__ void st_async_peer_f32(const float* local_smem, const uint64_t* local_bar, uint32_t peer_rank, float v) {
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((uint32_t)__cvta_generic_to_shared(local_smem)), "r"(peer_rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"((uint32_t)__cvta_generic_to_shared(local_bar)), "r"(peer_rank));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb) : "memory");
+}
 // tanh of the recomputed cell state in the reverse loops: the same ex2-based form the forward loops of the bf16 mode use (~1e-6 relative)
 __device__ __forceinline__ float tanh_exp(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
@@ -331,7 +339,7 @@ template <bool TC, int UNC>
 __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_constant__ CUtensorMap tmG, const AttBwdArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw0) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar, accum_bar;
+    __shared__ uint64_t full_bar, accum_bar, xb1, xb2;      // xb1 / xb2: arrival of the peer's softmax dot / query-gradient partial + G halo tile
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
@@ -375,6 +383,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
     if (owner)
         for (int idx = tid; idx < A * UOWN; idx += PT) wq8[(idx / UOWN) * (UOWN + 1) + idx % UOWN] = p.Wq[(size_t)(idx / UOWN) * D + uo0 + idx % UOWN];
     uint32_t tmem_base = 0, prod_it = 0;
+    if (tid == 0) { tcx::mbar_init(&xb1, 1); tcx::mbar_init(&xb2, 1); tcx::mbar_init_fence(); }
     if (TC) {
         if (tid == 0) { tcx::mbar_init(&full_bar, 1); tcx::mbar_init(&accum_bar, 1); tcx::mbar_init_fence(); }
         if (warp == 1) tcx::tmem_alloc<TMEM_COLS_ATT>(&tmem_base_s);
@@ -382,6 +391,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
         tcx::tc_fence_before();
     }
     __syncthreads();
+    cluster_arrive(); cluster_wait();      // one-time: the peer's exchange mbarriers are initialised before the first remote st.async targets them
     if (TC) { tcx::tc_fence_after(); tmem_base = tmem_base_s; }
     const uint32_t idesc = tcx::make_idesc_bf16(64, UNC);
 
@@ -573,9 +583,8 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             float pdot = 0.f;
             for (int l = t_lo * 16 + tid; l < t_hi * 16 && l < len; l += PT) pdot = fmaf(s_w[l], s_de[l], pdot);
             pdot = block_sum(pdot, s_red);
-            if (tid == 0) st_peer_f32(s_dotx, (uint32_t)(hf ^ 1), pdot);
-            cluster_arrive();
-            cluster_wait();
+            if (tid == 0) { tcx::mbar_expect_tx(&xb1, 4); st_async_peer_f32(s_dotx, &xb1, (uint32_t)(hf ^ 1), pdot); }
+            tcx::mbar_wait(&xb1, (uint32_t)(p.T - 1 - i) & 1);
             const float dot = pdot + s_dotx[0];           // a + b == b + a: both ranks get the same value
             for (int l = t_lo * 16 + tid; l < t_hi * 16; l += PT) {
                 const float d = l < len ? s_w[l] * (s_de[l] - dot) : 0.f;
@@ -673,7 +682,7 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             if (tid < A) {
 #pragma unroll
                 for (int w8 = 0; w8 < 8; ++w8) pdq += s_dqp[w8 * A + tid];
-                st_peer_f32(s_dqx + tid, (uint32_t)(hf ^ 1), pdq);
+                st_async_peer_f32(s_dqx + tid, &xb2, (uint32_t)(hf ^ 1), pdq);
             }
             {   // the boundary tile of G goes to the peer's halo rows (rank 0 sends its last tile, rank 1 its first)
                 const int ht = hf ? HT0 : HT0 - 1;             // tile sent
@@ -681,11 +690,14 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
                 if (ht >= t_lo && ht < t_hi)
                     for (int idx = tid; idx < 16 * GLD; idx += PT) {
                         const int l = ht * 16 + idx / GLD, k = idx % GLD;
-                        st_peer_f32(s_G + (size_t)(l - peer_g_lo) * GLD + k, (uint32_t)(hf ^ 1), s_G[(size_t)(l - g_lo) * GLD + k]);
+                        st_async_peer_f32(s_G + (size_t)(l - peer_g_lo) * GLD + k, &xb2, (uint32_t)(hf ^ 1), s_G[(size_t)(l - g_lo) * GLD + k]);
                     }
+                // what the PEER sends here: its A query-gradient partials, and its boundary tile if it has one (rank 0 always does; rank 1 only
+                // when it owns tiles at all)
+                const bool peer_sends_tile = hf ? true : (HT0 < p.MT);
+                if (tid == 0) tcx::mbar_expect_tx(&xb2, (uint32_t)(A * 4 + (peer_sends_tile ? 16 * GLD * 4 : 0)));
             }
-            cluster_arrive();
-            cluster_wait();
+            tcx::mbar_wait(&xb2, (uint32_t)(p.T - 1 - i) & 1);
             if (hf == 0 && tid < A) p.dq[((size_t)i * B + b) * A + tid] = pdq + s_dqx[tid];
             // d cum_{i-1}[j] = d cum_i[j] + sum_k G[j + half - k, k] for the own positions (their G rows: own tiles + the halo tile)
             for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) {
@@ -699,9 +711,6 @@ __global__ void __launch_bounds__(PT, 1) att_bwd_loop_kernel(const __grid_consta
             }
             __syncthreads();
             for (int j = t_lo * 16 + tid; j < t_hi * 16 && j < L; j += PT) dcum[j] = s_stage[j];
-        } else {
-            cluster_arrive(); cluster_wait();               // idle pairs: every thread of the cluster takes part in the two pair barriers
-            cluster_arrive(); cluster_wait();
         }
         BPROF_MARK(1);
         if (!grid_barrier(p.barrier, target, nblocks, p.abort_flag)) break;

@@ -134,6 +134,14 @@ __device__ __forceinline__ void st_peer_f32(const float* local_smem, uint32_t pe
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(peer_rank));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+// remote store that completes bytes on the PEER's mbarrier: data + signal in one instruction, no cluster barrier (and none of the memory
+// fence its release semantics imply) on the exchange path
+__device__ __forceinline__ void st_async_peer_f32(const float* local_smem, const uint64_t* local_bar, uint32_t peer_rank, float v) {
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(peer_rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(peer_rank));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb) : "memory");
+}
 // named barrier among the compute warps only
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                                                              const TcLoopArgs p) {
     extern __shared__ __align__(1024) unsigned char smem_raw0[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw0) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar, full2_bar, empty_bar, accum_bar;
+    __shared__ uint64_t full_bar, full2_bar, empty_bar, accum_bar, xchg_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_ok;
 
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         for (int idx = tid; idx < (p.A / 2) * 40; idx += PT) sWcB[idx] = p.WcB[(size_t)(cta & 1) * (p.A / 2) * 40 + idx];
     }
     if (tid == 0) {
-        mbar_init(&full_bar, 1); mbar_init(&full2_bar, 1); mbar_init(&empty_bar, 1);
+        mbar_init(&full_bar, 1); mbar_init(&full2_bar, 1); mbar_init(&empty_bar, 1); mbar_init(&xchg_bar, 1);
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -301,6 +309,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
     proxy_fence_shared();              // the weight tiles were written through the generic proxy; tcgen05.mma reads via the async proxy
     tc_fence_before();
     __syncthreads();
+    if (ATT) { cluster_arrive(); cluster_wait(); }      // one-time: the peer's exchange mbarrier is initialised before any remote st.async targets it
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
@@ -574,7 +583,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
         PROF_MARK(2);
 
         // =================== h part of step i+1: TMA + tcgen05 run while the attention of step i is computed ===================
-        if (ATT && !compute) cluster_arrive();      // role warps: non-blocking arrival at this step's pair barrier (waited on after the role work)
         if (i + 1 < p.T) {
             if (is_producer) produce(i + 1, 1);
             if (is_mma) { tc_fence_after(); consume(1, !ATT || p.nkb_h == p.nkb); }
@@ -721,14 +729,16 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     }
                 }
                 csync();
-                // this rank's partial energies: own copy + the peer's copy through distributed shared memory, then the pair barrier
+                // this rank's partial energies: own copy + the peer's copy through distributed shared memory.  Every remote store completes its
+                // 4 bytes on the PEER's exchange mbarrier (st.async), which that CTA armed with the L16 * 4 bytes it expects: no cluster barrier
+                if (tid == 0) mbar_expect_tx(&xchg_bar, (uint32_t)L16 * 4);
                 for (int l = tid; l < L16; l += CT) {
                     const float v = l < mtiles * 16 ? eq[l] + eq[L16 + l] : 0.f;
                     epart[hf * L16 + l] = v;
-                    st_peer_f32(epart + hf * L16 + l, (uint32_t)(hf ^ 1), v);
+                    st_async_peer_f32(epart + hf * L16 + l, &xchg_bar, (uint32_t)(hf ^ 1), v);
                 }
-                cluster_arrive();
-                cluster_wait();
+                csync();                                   // own copies visible to the whole CTA
+                mbar_wait(&xchg_bar, i & 1);               // the peer's L16 values have landed (acquire)
                 PROF_MARK(4);
                 float mx = -INFINITY;
                 for (int l = tid; l < len; l += CT) { const float ev = epart[l] + epart[L16 + l]; e[l] = ev; mx = fmaxf(mx, ev); }
@@ -809,11 +819,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         }
                     }
                 }
-            } else if (compute) {
-                cluster_arrive();          // idle pairs: every thread of the cluster takes part in the pair barrier
-                cluster_wait();
-            } else {
-                cluster_wait();            // role warps: arrived before their TMA / MMA work (below the cell barrier)
             }
             PROF_MARK(6);
             // next step's epilogue operands (L2 hits: prefetched a step ago) are requested between the arrival and the wait

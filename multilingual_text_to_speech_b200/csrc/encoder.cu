@@ -49,21 +49,36 @@ __global__ void col2im1d_kernel(float* __restrict__ dx, const float* __restrict_
     }
 }
 
-// Sum over the (NB, L) slab of channel c of f(x): rows are contiguous, so every thread walks whole rows with 16-byte loads and
-// four independent accumulators (no div / mod, plenty of loads in flight).  blockDim = 256.
+// Sum over the (NB, L) slab of channel c of f(x).  The slab is NB rows of L contiguous values; the (row, 16-byte group) pairs are
+// flattened over the 256 threads and walked four at a time, so that every thread keeps four independent 16-byte loads in flight whatever
+// L is (a row of the encoder has only 45 such groups: walking row by row left 80 % of the block idle behind one load latency per row).
 template <class F>
 __device__ __forceinline__ float channel_sum(const float* __restrict__ x, int c, int NB, int Ct, int L, F f) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const bool vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    for (int q = 0; q < NB; ++q) {
-        const float* row = x + ((size_t)q * Ct + c) * L;
-        if (vec) {
-            const float4* r4 = reinterpret_cast<const float4*>(row);
-            for (int l4 = threadIdx.x; l4 < (L >> 2); l4 += blockDim.x) {
-                const float4 v = r4[l4];
-                a0 += f(v.x, q, 4 * l4); a1 += f(v.y, q, 4 * l4 + 1); a2 += f(v.z, q, 4 * l4 + 2); a3 += f(v.w, q, 4 * l4 + 3);
+    if (vec) {
+        const int L4 = L >> 2, total = NB * L4;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * (int)blockDim.x) {
+            float4 v[4]; int qq[4], ll[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * (int)blockDim.x;
+                qq[u] = -1;
+                if (i < total) {
+                    const int q = i / L4, l4 = i - q * L4;
+                    qq[u] = q; ll[u] = 4 * l4;
+                    v[u] = reinterpret_cast<const float4*>(x + ((size_t)q * Ct + c) * L)[l4];
+                }
             }
-        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (qq[u] >= 0) {
+                    a0 += f(v[u].x, qq[u], ll[u]); a1 += f(v[u].y, qq[u], ll[u] + 1); a2 += f(v[u].z, qq[u], ll[u] + 2); a3 += f(v[u].w, qq[u], ll[u] + 3);
+                }
+        }
+    } else {
+        for (int q = 0; q < NB; ++q) {
+            const float* row = x + ((size_t)q * Ct + c) * L;
             for (int l = threadIdx.x; l < L; l += blockDim.x) a0 += f(row[l], q, l);
         }
     }
@@ -303,8 +318,37 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     __shared__ float red[64];
     const int ch = blockIdx.x, Ct = G * Cout;
     const float mu = mean[ch], is = invstd[ch];
-    float s1 = channel_sum(dz, ch, NB, Ct, L, [](float d, int, int) { return d; });
-    float s2 = channel_sum(dz, ch, NB, Ct, L, [=](float d, int q, int l) { return d * (conv[((size_t)q * Ct + ch) * L + l] - mu) * is; });
+    float s1, s2;
+    const bool vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (reinterpret_cast<uintptr_t>(conv) & 15) == 0;
+    if (vec) {      // ONE pass over dz and conv (16-byte loads of both at the same position, two of them in flight per thread)
+        float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+        const int L4 = L >> 2, total = NB * L4;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 2 * (int)blockDim.x) {
+            float4 d4[2], c4[2]; bool ok[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u * (int)blockDim.x;
+                ok[u] = i < total;
+                if (ok[u]) {
+                    const int q = i / L4, l4 = i - q * L4;
+                    const size_t off = ((size_t)q * Ct + ch) * L;
+                    d4[u] = reinterpret_cast<const float4*>(dz + off)[l4];
+                    c4[u] = reinterpret_cast<const float4*>(conv + off)[l4];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ok[u]) {
+                    p1[0] += d4[u].x; p1[1] += d4[u].y; p1[2] += d4[u].z; p1[3] += d4[u].w;
+                    p2[0] += d4[u].x * (c4[u].x - mu) * is; p2[1] += d4[u].y * (c4[u].y - mu) * is;
+                    p2[2] += d4[u].z * (c4[u].z - mu) * is; p2[3] += d4[u].w * (c4[u].w - mu) * is;
+                }
+        }
+        s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]); s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+    } else {
+        s1 = channel_sum(dz, ch, NB, Ct, L, [](float d, int, int) { return d; });
+        s2 = channel_sum(dz, ch, NB, Ct, L, [=](float d, int q, int l) { return d * (conv[((size_t)q * Ct + ch) * L + l] - mu) * is; });
+    }
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
     if (threadIdx.x == 0) {
@@ -410,10 +454,19 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(float* __restrict__ 
 // ---- parameter generator: skinny products with one huge dimension R (the generated kernel) ----
 constexpr int GEN_MAXG = 16, GEN_MAXBN = 16;
 // out[g, r] = sum_j eb[g, j] Wk[r, j] + bk[r]
-__global__ void generator_expand_kernel(float* __restrict__ out, const float* __restrict__ eb, const float* __restrict__ Wk,
-                                        const float* __restrict__ bk, int G, int bn, size_t R) {
+// The bottleneck eb[g, j] = e[g, :] . Wb[j, :] + bb[j] (G * bn values, gd terms each) is recomputed by every block in its prologue -- cheaper
+// than a separate launch -- and block 0 stores it for the backward pass.
+__global__ void generator_expand_kernel(float* __restrict__ out, float* __restrict__ eb, const float* __restrict__ Wk,
+                                        const float* __restrict__ bk, int G, int bn, size_t R, const float* __restrict__ e,
+                                        const float* __restrict__ Wb, const float* __restrict__ bb, int gd) {
     __shared__ float s_eb[GEN_MAXG * GEN_MAXBN];
-    for (int i = threadIdx.x; i < G * bn; i += blockDim.x) s_eb[i] = eb[i];
+    for (int i = threadIdx.x; i < G * bn; i += blockDim.x) {
+        const int g = i / bn, j = i - g * bn;
+        float a = bb ? bb[j] : 0.f;
+        for (int d = 0; d < gd; ++d) a = fmaf(e[g * gd + d], Wb[j * gd + d], a);
+        s_eb[i] = a;
+        if (blockIdx.x == 0) eb[i] = a;
+    }
     __syncthreads();
     const bool vec8 = (reinterpret_cast<uintptr_t>(Wk) & 15) == 0;
     for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < R; r += (size_t)gridDim.x * blockDim.x) {
@@ -743,19 +796,58 @@ int convblock_backward_impl(const b200tts_convblock_shape& s, const float* x, co
 // ---------------------------------------------------------------------------------------------
 // parameter generator: out[g, :] = (e[g] . Wb^T + bb) . Wk^T + bk        (modules/generated.py:38-39, 81-84)
 // ---------------------------------------------------------------------------------------------
+// Tail of the generator backward in ONE small launch: deb = fixed-order sum of the per-block partials, then
+// dWb[j, d] += sum_g deb[g, j] e[g, d];  dbb[j] += sum_g deb[g, j];  de[g, d] += sum_j deb[g, j] Wb[j, d]
+__global__ void __launch_bounds__(256) generator_tail_bwd_kernel(float* __restrict__ deb, const float* __restrict__ partial, int nblk,
+                                                                 const float* __restrict__ e, const float* __restrict__ Wb,
+                                                                 float* __restrict__ de, float* __restrict__ dWb, float* __restrict__ dbb,
+                                                                 int G, int gd, int bn) {
+    __shared__ float s_deb[GEN_MAXG * GEN_MAXBN];
+    const int n = G * bn;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int b = 0;
+        for (; b + 3 < nblk; b += 4) {
+            a0 += partial[(size_t)b * n + t]; a1 += partial[(size_t)(b + 1) * n + t];
+            a2 += partial[(size_t)(b + 2) * n + t]; a3 += partial[(size_t)(b + 3) * n + t];
+        }
+        for (; b < nblk; ++b) a0 += partial[(size_t)b * n + t];
+        const float v = (a0 + a1) + (a2 + a3);
+        s_deb[t] = v; deb[t] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bn * gd; i += blockDim.x) {
+        const int j = i / gd, d = i - j * gd;
+        float a = 0.f;
+        for (int g = 0; g < G; ++g) a = fmaf(s_deb[g * bn + j], e[g * gd + d], a);
+        dWb[i] += a;
+    }
+    for (int j = threadIdx.x; j < bn; j += blockDim.x) {
+        float a = 0.f;
+        for (int g = 0; g < G; ++g) a += s_deb[g * bn + j];
+        dbb[j] += a;
+    }
+    for (int i = threadIdx.x; i < G * gd; i += blockDim.x) {
+        const int g = i / gd, d = i - g * gd;
+        float a = 0.f;
+        for (int j = 0; j < bn; ++j) a = fmaf(s_deb[g * bn + j], Wb[j * gd + d], a);
+        de[i] += a;
+    }
+}
+
 size_t generator_workspace_floats(int G, int bn) { return align_up_sz((size_t)G * bn, 64) + kGemmScratch; }
 
 int generator_forward_impl(int G, int gd, int bn, long long R, const float* e, const float* Wb, const float* bb, const float* Wk,
                            const float* bk, float* eb, float* out, cudaStream_t st) {
     B200_REQUIRE(G > 0 && gd > 0 && bn > 0 && R > 0 && R < (1ll << 31), "generator: bad dimensions");
-    GemmDesc a;
-    a.A = e; a.lda = gd; a.B = Wb; a.ldb = gd; a.transB = 1; a.C = eb; a.ldc = bn; a.bias = bb; a.M = G; a.N = bn; a.K = gd;
-    B200_TRY(gemm_f32(a, st));
-    if (G <= GEN_MAXG && bn <= GEN_MAXBN) {      // skinny product, bound by reading Wk / writing the generated kernel once
-        generator_expand_kernel<<<grid_for((size_t)R), 256, 0, st>>>(out, eb, Wk, bk, G, bn, (size_t)R);
+    if (G <= GEN_MAXG && bn <= GEN_MAXBN) {      // skinny product, bound by reading Wk / writing the generated kernel once (bottleneck folded in)
+        generator_expand_kernel<<<grid_for((size_t)R), 256, 0, st>>>(out, eb, Wk, bk, G, bn, (size_t)R, e, Wb, bb, gd);
         B200_LAUNCH_CHECK();
         return B200TTS_OK;
     }
+    GemmDesc a;
+    a.A = e; a.lda = gd; a.B = Wb; a.ldb = gd; a.transB = 1; a.C = eb; a.ldc = bn; a.bias = bb; a.M = G; a.N = bn; a.K = gd;
+    B200_TRY(gemm_f32(a, st));
     GemmDesc b;
     b.A = eb; b.lda = bn; b.B = Wk; b.ldb = bn; b.transB = 1; b.C = out; b.ldc = (int)R; b.bias = bk; b.M = G; b.N = (int)R; b.K = bn;
     return gemm_f32(b, st);
@@ -773,8 +865,9 @@ int generator_backward_impl(int G, int gd, int bn, long long R, const float* e, 
         const int fblk = (int)(((size_t)R + 255) / 256 < 148 * 2 ? ((size_t)R + 255) / 256 : 148 * 2);
         generator_bwd_fused_kernel<<<fblk, 256, 0, st>>>(dWk, dbk, scratch, dout, Wk, eb, G, (size_t)R);
         B200_LAUNCH_CHECK();
-        generator_deb_finish_kernel<<<G * bn, 128, 0, st>>>(deb, scratch, fblk, G * bn);
+        generator_tail_bwd_kernel<<<1, 256, 0, st>>>(deb, scratch, fblk, e, Wb, de, dWb, dbb, G, gd, bn);     // finish + dWb + dbb + de
         B200_LAUNCH_CHECK();
+        return B200TTS_OK;
     } else if (G <= GEN_MAXG && bn <= GEN_MAXBN && (size_t)nblk * G * bn <= kGemmScratch && G * bn <= 256) {
         // dWk [R, bn] += dout^T . eb and dbk += column sums of dout, in one pass over dout
         generator_dwk_kernel<<<grid_for((size_t)R), 256, 0, st>>>(dWk, dbk, dout, eb, G, bn, (size_t)R);

@@ -61,7 +61,7 @@ def main():
                     boff = _lib.load().b200tts_debug_persist_bwd_profile_offset(ctypes.byref(shp), which)
                     ns = 8
                     rb = F.PROFILE['last_bws'][boff:boff + 148 * ns * 8].view(torch.int64).view(148, ns).cpu().double()
-                    act = rb[rb.sum(1) > 0]
+                    act = rb[(rb.sum(1) > 0) & (rb.abs().max(1).values < 1e12)]        # rows of CTAs that do not exist hold whatever the allocator left there
                     if len(act):
                         print(f'{loop} loop: cycles/step by phase, CTA0 | mean | max over CTAs')
                         for j, nme in enumerate(bnames[which]):
@@ -72,7 +72,7 @@ def main():
             raw = raw4[:2]
             names = ['gemm+tmem', 'cell+q', 'barrier1', 'attn:q/load', 'attn:energy', 'attn:softmax', 'attn:ctx', 'barrier2']
             for k, loop in enumerate(('att', 'gen')):
-                act = raw[k][raw[k].sum(1) > 0]
+                act = raw[k][(raw[k].sum(1) > 0) & (raw[k].abs().max(1).values < 1e12)]
                 if len(act):
                     print(f'{loop} loop: cycles/step by phase, CTA0 | mean | max over CTAs')
                     for j, nme in enumerate(names):
@@ -82,7 +82,7 @@ def main():
                   'tma h: proxy fence', 'tma h: issue']
             for k, loop in enumerate(('att', 'gen')):
                 rr = raw4[2 + k]
-                act = rr[rr.sum(1) > 0]
+                act = rr[(rr.sum(1) > 0) & (rr.abs().max(1).values < 1e12)]
                 if len(act):
                     print(f'{loop} loop role threads: cycles/step, CTA0 | mean | max')
                     for j, nme in enumerate(rn):
