@@ -43,6 +43,7 @@ struct TcLoopArgs {
     int nkb, nkb_h;                           // k-blocks in total / in the h part
     int ch_h, n_h, ch_c, n_c, slot_kb;        // TMA chunking: n_h instructions of ch_h k-blocks (h part), n_c of ch_c (ctx part); slot capacity
     int alias_sum;                            // 1: the accumulator staging s_sum lives in the (then idle) TMA slot (large memory dims)
+    int use_btab;                             // 1: the context product's B fragments come from a per-step shared table (built once per CTA)
     const float* W; int ldw; int wcol_h, wcol_c;   // fp32 weights [4D, ldw]: operand column k < D -> wcol_h + k, else wcol_c + k - D
     __nv_bfloat16* actb;                      // [T+1, B, Kp] bf16 operand rows: [h | ctx | 0]
     float* actf; int ldf; int hcol;           // fp32 mirror ([T+1, B, ldf]); h at column hcol, ctx at column 0
@@ -608,6 +609,7 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                 float* cred = red + 64;                    // [16][AH] query partials
                 uint32_t* Ph = reinterpret_cast<uint32_t*>(cred + 16 * AH);   // [L16 + 48] Toeplitz pair arrays (hi / lo bf16 split)
                 uint32_t* Pl = Ph + (L16 + 48);
+                uint2* btab = reinterpret_cast<uint2*>(Pl + (L16 + 48));     // [MT][32] B fragments of the context product (p.use_btab)
                 const int len = att_len;                   // text length of this pair's utterance (loaded once, before the loop)
                 const int mtiles = (len + 15) / 16, ktiles = mtiles;
                 if (i == 0) {                              // one-time: constants and the initial cumulative weights into shared memory
@@ -759,6 +761,23 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     }
                 }
                 csync();
+                if (p.use_btab) {
+                    // B fragments (hi(w) in column 0, lo(w) in column 1) of every 16-position k-tile, built ONCE per CTA: they depend on the k-tile
+                    // only, and every warp used to rebuild all of them (~40 instructions per fragment and warp)
+                    for (int idx = tid; idx < ktiles * 32; idx += CT) {
+                        const int kt = idx >> 5, gg = (idx >> 2) & 7, tt = idx & 3;
+                        uint2 f = make_uint2(0u, 0u);
+                        if (gg < 2) {
+                            const float* wl = e + kt * 16 + 2 * tt;
+                            const float w0 = wl[0], w1 = wl[1], w2 = wl[8], w3 = wl[9];
+                            const float h0 = __bfloat162float(__float2bfloat16_rn(w0)), h1 = __bfloat162float(__float2bfloat16_rn(w1));
+                            const float h2 = __bfloat162float(__float2bfloat16_rn(w2)), h3 = __bfloat162float(__float2bfloat16_rn(w3));
+                            f = gg == 0 ? make_uint2(pack2(h0, h1), pack2(h2, h3)) : make_uint2(pack2(w0 - h0, w1 - h1), pack2(w2 - h2, w3 - h3));
+                        }
+                        btab[idx] = f;
+                    }
+                    csync();
+                }
                 PROF_MARK(5);
                 // context on the tensor cores: ctx[m] = sum_l memory[l, m] * w[l] for this rank's half of the 16-row tiles.  A = memory^T
                 // fragments (fragment-major bf16, one 16-byte load per lane per MMA), B = (hi(w), lo(w)) in columns 0 / 1, so that
@@ -767,6 +786,14 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                     const int g = lane >> 2, tq = lane & 3;
                     uint32_t bfr[KTMAX][2];                // B fragments: lanes g = 0 hold hi(w), g = 1 hold lo(w), other columns zero
                     auto build_b = [&](int kt0) {
+                        if (p.use_btab) {
+#pragma unroll
+                            for (int j = 0; j < KTMAX; ++j) {
+                                bfr[j][0] = 0u; bfr[j][1] = 0u;
+                                if (kt0 + j < ktiles) { const uint2 f = btab[(kt0 + j) * 32 + lane]; bfr[j][0] = f.x; bfr[j][1] = f.y; }
+                            }
+                            return;
+                        }
 #pragma unroll
                         for (int j = 0; j < KTMAX; ++j) {
                             bfr[j][0] = 0u; bfr[j][1] = 0u;
@@ -973,7 +1000,11 @@ int tc_persist_att_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     a.barrier = barrier; a.abort_flag = reinterpret_cast<int*>(barrier + 32);
     a.prof = reinterpret_cast<long long*>(pws + l.barrier + 256);
     a.prof2 = a.prof + 2 * 148 * 8;
-    return launch_tc_loop(true, a, tmH, tmC, tc_loop_smem_bytes(g.nkb_att, a.slot_kb, s.A, true, s.L, g.alias_att != 0), st);
+    size_t smem = tc_loop_smem_bytes(g.nkb_att, a.slot_kb, s.A, true, s.L, g.alias_att != 0);
+    const size_t tab = (size_t)l.MT * 32 * 8;          // shared B-fragment table of the context product, when it fits behind the scratch
+    a.use_btab = (smem + tab <= SMEM_LIMIT && !getenv("B200TTS_NO_BTAB")) ? 1 : 0;
+    if (a.use_btab) smem += tab;
+    return launch_tc_loop(true, a, tmH, tmC, smem, st);
 }
 
 // Generator-LSTM loop.  Expects: gg = input projection, hg row 0 = 0, cg row 0 = 0.
@@ -990,7 +1021,7 @@ int tc_persist_gen_loop(const b200tts_decoder_shape& s, const b200tts_decoder_pa
     B200_TRY(tc_make_map3_bf16(&tmH, hgb, KB, (T + 1) * B, g.nkb_gen, (size_t)g.Kp_gen * 2, 128, KB, BT, g.ch_h_gen));
     TcLoopArgs a{};
     a.B = B; a.T = T; a.D = D; a.K = D; a.Kp = g.Kp_gen; a.RB = D / UNITS; a.NBH = (B + BT - 1) / BT;
-    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.ch_h = g.ch_h_gen; a.n_h = g.nkb_gen / g.ch_h_gen; a.ch_c = 0; a.n_c = 0; a.alias_sum = 0; a.slot_kb = g.nkb_gen;
+    a.nkb = g.nkb_gen; a.nkb_h = g.nkb_gen; a.ch_h = g.ch_h_gen; a.n_h = g.nkb_gen / g.ch_h_gen; a.ch_c = 0; a.n_c = 0; a.alias_sum = 0; a.use_btab = 0; a.slot_kb = g.nkb_gen;
     a.W = w.gen_w_hh; a.ldw = D; a.wcol_h = 0; a.wcol_c = 0;
     a.actb = hgb; a.actf = ws + fl.hg; a.ldf = D; a.hcol = 0;
     a.gates = ws + fl.gg; a.cstate = ws + fl.cg;

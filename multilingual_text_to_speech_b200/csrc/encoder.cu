@@ -803,17 +803,34 @@ __global__ void __launch_bounds__(256) generator_tail_bwd_kernel(float* __restri
                                                                  float* __restrict__ de, float* __restrict__ dWb, float* __restrict__ dbb,
                                                                  int G, int gd, int bn) {
     __shared__ float s_deb[GEN_MAXG * GEN_MAXBN];
+    __shared__ float s_part[256];
     const int n = G * bn;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    // `parts` threads per output share the nblk partials (interleaved, four accumulators each), then a fixed-order combine: deterministic
+    const int parts = n <= 256 ? 256 / n : 1;
+    if (n <= 256) {
+        const int t = threadIdx.x % n, part = threadIdx.x / n;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int b = 0;
-        for (; b + 3 < nblk; b += 4) {
-            a0 += partial[(size_t)b * n + t]; a1 += partial[(size_t)(b + 1) * n + t];
-            a2 += partial[(size_t)(b + 2) * n + t]; a3 += partial[(size_t)(b + 3) * n + t];
+        if (part < parts) {
+            int b = part;
+            for (; b + 3 * parts < nblk; b += 4 * parts) {
+                a0 += partial[(size_t)b * n + t]; a1 += partial[(size_t)(b + parts) * n + t];
+                a2 += partial[(size_t)(b + 2 * parts) * n + t]; a3 += partial[(size_t)(b + 3 * parts) * n + t];
+            }
+            for (; b < nblk; b += parts) a0 += partial[(size_t)b * n + t];
+            s_part[threadIdx.x] = (a0 + a1) + (a2 + a3);
         }
-        for (; b < nblk; ++b) a0 += partial[(size_t)b * n + t];
-        const float v = (a0 + a1) + (a2 + a3);
-        s_deb[t] = v; deb[t] = v;
+        __syncthreads();
+        if (threadIdx.x < n) {
+            float v = 0.f;
+            for (int q = 0; q < parts; ++q) v += s_part[q * n + threadIdx.x];
+            s_deb[threadIdx.x] = v; deb[threadIdx.x] = v;
+        }
+    } else {
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            float v = 0.f;
+            for (int b = 0; b < nblk; ++b) v += partial[(size_t)b * n + t];
+            s_deb[t] = v; deb[t] = v;
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < bn * gd; i += blockDim.x) {
