@@ -81,3 +81,21 @@ def test_decoder_path_covers_baseline_configs(lib):
     assert path(64, 180, 900, 288, training=0) & 0b11 == 0b11          # inference / evaluation: forward loops on tcgen05
     for B, L in ((16, 180), (52, 180), (64, 300)):
         assert path(B, L, 900, 512) == 0b111111, (B, L, bin(path(B, L, 900, 512)))
+
+
+def test_grad_targets_accumulate_in_place_only_into_bound_leaf_gradients():
+    """functional._grad_targets: a leaf parameter whose .grad is a dense fp32 tensor of its own shape (the GradBucket views) is the
+    accumulation target itself and autograd gets None; anything else gets a fresh zero tensor that autograd accumulates as usual."""
+    from multilingual_text_to_speech_b200 import functional as F
+    bound = torch.nn.Parameter(torch.ones(3, 4))
+    bound.grad = torch.full((3, 4), 2.0)
+    fresh = torch.nn.Parameter(torch.ones(5))
+    non_leaf = bound * 2.0
+    strided = torch.nn.Parameter(torch.ones(4, 6))
+    strided.grad = torch.zeros(6, 4).t()                      # not contiguous: must not be written through a flat pointer
+    targets, returned = F._grad_targets((bound, fresh, non_leaf, None, strided))
+    assert targets[0] is bound.grad and returned[0] is None
+    assert returned[1] is targets[1] and float(targets[1].abs().sum()) == 0.0 and targets[1].shape == fresh.shape
+    assert returned[2] is targets[2] and targets[2].shape == non_leaf.shape
+    assert targets[3] is None and returned[3] is None
+    assert returned[4] is targets[4] and targets[4].is_contiguous()
