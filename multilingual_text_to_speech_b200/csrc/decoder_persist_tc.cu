@@ -643,6 +643,18 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                         for (int j = 0; j < KTMAX; ++j)
                             if (j < ktiles) av[j] = __ldg(fr + (size_t)j * 32);
                     }
+                    // cumulative weights -> (hi, lo) bf16 pairs: Ph[x] = (c[x], c[x+1]) with c[j] = cum[j - half].  Pair-local state only: done here,
+                    // while the query partials requested above are still on their way from L2
+                    for (int x = tid; x < L16 + 48; x += CT) {
+                        float c0 = 0.f, c1 = 0.f;
+                        const int la = x - half, lb = x + 1 - half;
+                        if (la >= 0 && la < L) c0 = cum_s[la];
+                        if (lb >= 0 && lb < L) c1 = cum_s[lb];
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
+                        __nv_bfloat162 hp2; hp2.x = h0; hp2.y = h1;
+                        Ph[x] = *reinterpret_cast<uint32_t*>(&hp2);
+                        Pl[x] = pack2(c0 - __bfloat162float(h0), c1 - __bfloat162float(h1));
+                    }
                     float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { qs.x += qv[j].x; qs.y += qv[j].y; qs.z += qv[j].z; qs.w += qv[j].w; }
@@ -655,17 +667,6 @@ __global__ void __launch_bounds__(PT, 1) lstm_loop_tc_kernel(const __grid_consta
                             }
                     }
                     *reinterpret_cast<float4*>(cred + sl * AH + a4 * 4) = qs;
-                    // cumulative weights -> (hi, lo) bf16 pairs: Ph[x] = (c[x], c[x+1]) with c[j] = cum[j - half]
-                    for (int x = tid; x < L16 + 48; x += CT) {
-                        float c0 = 0.f, c1 = 0.f;
-                        const int la = x - half, lb = x + 1 - half;
-                        if (la >= 0 && la < L) c0 = cum_s[la];
-                        if (lb >= 0 && lb < L) c1 = cum_s[lb];
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(c0), h1 = __float2bfloat16_rn(c1);
-                        __nv_bfloat162 hp2; hp2.x = h0; hp2.y = h1;
-                        Ph[x] = *reinterpret_cast<uint32_t*>(&hp2);
-                        Pl[x] = pack2(c0 - __bfloat162float(h0), c1 - __bfloat162float(h1));
-                    }
                     csync();
                     for (int a2 = tid; a2 < AH; a2 += CT) {
                         float q = 0.f;
